@@ -1,0 +1,585 @@
+// api.cu - host-level batched modset: the reference's caller loops as C-ABI
+// calls taking HOST (or device) buffers.
+//
+//   modgpuModsetAdd  ==  the addSequence loop of addSequenceFile
+//                        (reference modutils.c:19-51): for every sequence,
+//                        every selected modimizer is found-or-inserted and its
+//                        depth incremented.
+//
+// Pipeline per chunk of whole sequences: H2D (copy stream, double buffered,
+// overlapped with the previous chunk's kernels) -> K1 pack2bit + end flags ->
+// K2 hash_select -> K3 table insert.  There is no CPU path: every step is a
+// kernel launch or a CUDA copy, and errors surface as return codes.
+#include <string.h>
+#include <stdlib.h>
+#include <vector>
+#include <algorithm>
+#include "mg_device.cuh"
+
+MgKHasher mg_khasher_from(const ModgpuHasher *h);
+int mg_table_insert_dev(ModgpuTable *t, const uint64_t *d_kmers, const uint64_t *d_n, uint64_t nMax,
+                        uint32_t *d_slot, int exactOrder, cudaStream_t st);
+int mg_table_lookup_dev(const ModgpuTable *t, const uint64_t *d_kmers, const uint64_t *d_n, uint64_t nMax,
+                        uint32_t *d_out, cudaStream_t st);
+uint64_t mg_table_numbered(const ModgpuTable *t);
+int mg_table_classify(ModgpuTable *t, int mode, int c1, int c2, int cM, int zeroDepth, uint32_t *d_classCounts, cudaStream_t st);
+
+// bases per pipelined chunk when the batch comes from host memory / is resident
+static const uint64_t MG_HOST_CHUNK = 1ull << 28;
+static const uint64_t MG_DEV_CHUNK = 1ull << 31;
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes)
+  {
+    if (bytes <= cap) return MODGPU_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    MG_CUDA(cudaMalloc(&p, want));
+    cap = want;
+    return MODGPU_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PinBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes)
+  {
+    if (bytes <= cap) return MODGPU_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    MG_CUDA(cudaMallocHost(&p, want));
+    cap = want;
+    return MODGPU_OK;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct TimedSpan { cudaEvent_t a, b; int cat; };
+
+struct ModgpuModset {
+  ModgpuHasher hasher;
+  ModgpuTable *table = nullptr;
+  int bits = 0;
+  cudaStream_t stream = nullptr, copyStream = nullptr;
+  bool ownStream = false;
+  int selFlags = 0;
+  int exactOrder = 0;
+  bool depthIsZero = false;         // modmap-built sets keep ms->depth at 0
+  bool dirty = false;               // entries inserted since the last numbering
+  DevBuf bases[2], offs[2], packed, ends, kmers, gpos, slot, work, misc, expo;
+  PinBuf hOffs[2], hMisc;
+  cudaEvent_t evCopied[2] = { nullptr, nullptr }, evFree[2] = { nullptr, nullptr };
+  uint64_t totalHashes = 0;
+  // profiling
+  bool profile = false;
+  std::vector<TimedSpan> spans;
+  std::vector<cudaEvent_t> evPool;
+  double ms[MODGPU_T_N] = { 0, 0, 0, 0 };
+  uint64_t launches[MODGPU_T_N] = { 0, 0, 0, 0 };
+};
+
+// ------------------------------------------------------------- profiling --
+static cudaEvent_t prof_event(ModgpuModset *ms)
+{
+  if (!ms->evPool.empty()) { cudaEvent_t e = ms->evPool.back(); ms->evPool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+struct ProfScope {
+  ModgpuModset *ms; TimedSpan s; bool on;
+  ProfScope(ModgpuModset *m, int cat, int nLaunch = 1) : ms(m), on(m->profile)
+  {
+    ms->launches[cat] += (uint64_t)nLaunch;
+    if (!on) return;
+    s.cat = cat; s.a = prof_event(ms); s.b = prof_event(ms);
+    cudaEventRecord(s.a, ms->stream);
+  }
+  ~ProfScope()
+  {
+    if (!on) return;
+    cudaEventRecord(s.b, ms->stream);
+    ms->spans.push_back(s);
+  }
+};
+
+static void prof_collect(ModgpuModset *ms)
+{
+  for (TimedSpan &s : ms->spans)
+    { float t = 0.f;
+      if (cudaEventSynchronize(s.b) == cudaSuccess && cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) ms->ms[s.cat] += t;
+      ms->evPool.push_back(s.a); ms->evPool.push_back(s.b);
+    }
+  ms->spans.clear();
+}
+
+// ---------------------------------------------------------------- create --
+extern "C" ModgpuModset *modgpuModsetCreate(int bits, int k, int w, int seed)
+{
+  if (modgpuDeviceCount() < 1)
+    { if (!modgpuLastError()[0]) mg_set_error("no CUDA device: libmodgpu has no CPU fallback");
+      return nullptr;
+    }
+  ModgpuModset *ms = new ModgpuModset();
+  if (modgpuHasherInit(&ms->hasher, k, w, seed)) { delete ms; return nullptr; }
+  ms->bits = bits;
+  if (mg_check_cuda(cudaStreamCreateWithFlags(&ms->stream, cudaStreamNonBlocking), "cudaStreamCreate", __FILE__, __LINE__) ||
+      mg_check_cuda(cudaStreamCreateWithFlags(&ms->copyStream, cudaStreamNonBlocking), "cudaStreamCreate", __FILE__, __LINE__))
+    { delete ms; return nullptr; }
+  ms->ownStream = true;
+  for (int i = 0; i < 2; ++i)
+    { cudaEventCreateWithFlags(&ms->evCopied[i], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&ms->evFree[i], cudaEventDisableTiming);
+    }
+  ms->table = modgpuTableCreate(bits, ms->stream);
+  if (!ms->table) { modgpuModsetDestroy(ms); return nullptr; }
+  if (ms->misc.ensure(4096) || ms->hMisc.ensure(4096)) { modgpuModsetDestroy(ms); return nullptr; }
+  return ms;
+}
+
+extern "C" void modgpuModsetDestroy(ModgpuModset *ms)
+{
+  if (!ms) return;
+  if (ms->stream) cudaStreamSynchronize(ms->stream);
+  if (ms->copyStream) cudaStreamSynchronize(ms->copyStream);
+  prof_collect(ms);
+  for (cudaEvent_t e : ms->evPool) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i)
+    { ms->bases[i].release(); ms->offs[i].release(); ms->hOffs[i].release();
+      if (ms->evCopied[i]) cudaEventDestroy(ms->evCopied[i]);
+      if (ms->evFree[i]) cudaEventDestroy(ms->evFree[i]);
+    }
+  ms->packed.release(); ms->ends.release(); ms->kmers.release(); ms->gpos.release(); ms->slot.release();
+  ms->work.release(); ms->misc.release(); ms->expo.release(); ms->hMisc.release();
+  if (ms->table) modgpuTableDestroy(ms->table);
+  if (ms->ownStream && ms->stream) cudaStreamDestroy(ms->stream);
+  if (ms->copyStream) cudaStreamDestroy(ms->copyStream);
+  delete ms;
+}
+
+extern "C" const ModgpuHasher *modgpuModsetHasher(const ModgpuModset *ms) { return &ms->hasher; }
+extern "C" ModgpuTable *modgpuModsetTable(ModgpuModset *ms) { return ms->table; }
+
+extern "C" int modgpuModsetSetStream(ModgpuModset *ms, void *stream)
+{
+  MG_CUDA(cudaStreamSynchronize(ms->stream));
+  if (ms->ownStream) cudaStreamDestroy(ms->stream);
+  ms->stream = (cudaStream_t)stream;
+  ms->ownStream = false;
+  return MODGPU_OK;
+}
+
+extern "C" int modgpuModsetSetFlags(ModgpuModset *ms, int flags) { ms->selFlags = flags; return MODGPU_OK; }
+extern "C" int modgpuModsetSetExactOrder(ModgpuModset *ms, int e) { ms->exactOrder = e ? 1 : 0; return MODGPU_OK; }
+
+extern "C" int modgpuModsetProfile(ModgpuModset *ms, int enable)
+{
+  MG_CUDA(cudaStreamSynchronize(ms->stream));
+  prof_collect(ms);
+  ms->profile = enable != 0;
+  for (int i = 0; i < MODGPU_T_N; ++i) { ms->ms[i] = 0; ms->launches[i] = 0; }
+  return MODGPU_OK;
+}
+
+extern "C" int modgpuModsetTimes(ModgpuModset *ms, double ms_out[MODGPU_T_N], uint64_t launches_out[MODGPU_T_N])
+{
+  MG_CUDA(cudaStreamSynchronize(ms->stream));
+  prof_collect(ms);
+  for (int i = 0; i < MODGPU_T_N; ++i) { if (ms_out) ms_out[i] = ms->ms[i]; if (launches_out) launches_out[i] = ms->launches[i]; }
+  return MODGPU_OK;
+}
+
+// ----------------------------------------------------------------- chunks --
+// K1 + K2 over one device-resident chunk; leaves the selected k-mers (and, if
+// wantPos, their global offsets) in ms->kmers / ms->gpos and returns the count.
+// Synchronises the stream once (to learn the count and size the next kernels).
+int mg_modset_select_chunk(ModgpuModset *ms, const uint8_t *d_bases, const uint64_t *d_offs,
+                           uint64_t nSeq, uint64_t nBases, int isAscii, bool wantPos, int extraFlags,
+                           uint64_t *nSelected)
+{
+  cudaStream_t st = ms->stream;
+  *nSelected = 0;
+  if (!nBases) return MODGPU_OK;
+  const uint64_t words = modgpuPackedWords(nBases);
+  int rc;
+  if ((rc = ms->packed.ensure(words * 8)) || (rc = ms->ends.ensure(words * 4)) ||
+      (rc = ms->work.ensure(modgpuHashSelectWorkspace(nBases))))
+    return rc;
+  { ProfScope p(ms, MODGPU_T_PACK, 2);
+    if ((rc = modgpuPack2bit(d_bases, nBases, isAscii, (uint64_t *)ms->packed.p, st))) return rc;
+    if ((rc = modgpuMarkEnds(d_offs, nSeq, nBases, (uint32_t *)ms->ends.p, st))) return rc;
+  }
+  const uint64_t d = (uint64_t)ms->hasher.w;
+  uint64_t cap = (d <= 2) ? nBases : (nBases / d + nBases / (4 * d) + 65536);
+  if (cap > nBases) cap = nBases;
+  uint64_t *dCount = (uint64_t *)ms->misc.p;
+  volatile uint64_t *hCount = (volatile uint64_t *)ms->hMisc.p;
+  const int flags = ms->selFlags | extraFlags | (ms->exactOrder ? MODGPU_SEL_ORDERED : 0);
+  for (int attempt = 0; attempt < 2; ++attempt)
+    { if ((rc = ms->kmers.ensure(cap * 8))) return rc;
+      if (wantPos && (rc = ms->gpos.ensure(cap * 4))) return rc;
+      { ProfScope p(ms, MODGPU_T_SELECT, 1);
+        if ((rc = modgpuHashSelect(&ms->hasher, (const uint64_t *)ms->packed.p, (const uint32_t *)ms->ends.p, nBases,
+                                   (uint64_t *)ms->kmers.p, wantPos ? (uint32_t *)ms->gpos.p : nullptr, cap, dCount,
+                                   ms->work.p, flags, st)))
+          return rc;
+      }
+      MG_CUDA(cudaMemcpyAsync((void *)hCount, dCount, 8, cudaMemcpyDeviceToHost, st));
+      MG_CUDA(cudaStreamSynchronize(st));
+      if (*hCount <= cap) break;
+      cap = *hCount;                                     // denser than expected: redo with the exact size
+    }
+  *nSelected = *hCount;
+  return MODGPU_OK;
+}
+
+static int add_chunk_device(ModgpuModset *ms, const uint8_t *d_bases, const uint64_t *d_offs, uint64_t nSeq,
+                            uint64_t nBases, int isAscii, uint64_t *nHashes)
+{
+  uint64_t n = 0;
+  int rc = mg_modset_select_chunk(ms, d_bases, d_offs, nSeq, nBases, isAscii, false, 0, &n);
+  if (rc) return rc;
+  *nHashes = n;
+  if (!n) return MODGPU_OK;
+  uint32_t *dSlot = nullptr;
+  if (ms->exactOrder)
+    { if ((rc = ms->slot.ensure(n * 4))) return rc;
+      dSlot = (uint32_t *)ms->slot.p;
+    }
+  { ProfScope p(ms, MODGPU_T_INSERT, 1);
+    if ((rc = mg_table_insert_dev(ms->table, (const uint64_t *)ms->kmers.p, nullptr, n, dSlot, ms->exactOrder, ms->stream))) return rc;
+  }
+  if (ms->exactOrder)
+    { ProfScope p(ms, MODGPU_T_OTHER, 3);
+      if ((rc = modgpuTableNumber(ms->table, dSlot, n, nullptr, ms->stream))) return rc;
+    }
+  else ms->dirty = true;
+  return MODGPU_OK;
+}
+
+// greedy groups of whole sequences of at most `limit` bases
+static void plan_chunks(const uint64_t *offs, uint64_t nSeq, uint64_t limit, std::vector<uint64_t> &cuts)
+{
+  cuts.clear();
+  cuts.push_back(0);
+  uint64_t r = 0;
+  while (r < nSeq)
+    { uint64_t r1 = r + 1;
+      while (r1 < nSeq && offs[r1 + 1] - offs[r] <= limit) ++r1;
+      cuts.push_back(r1);
+      r = r1;
+    }
+}
+
+static int check_offsets(const uint64_t *offs, uint64_t nSeq)
+{
+  if (!offs || offs[0] != 0) { mg_set_error("offsets must start at 0"); return MODGPU_EINVAL; }
+  for (uint64_t r = 0; r < nSeq; ++r)
+    { if (offs[r + 1] < offs[r]) { mg_set_error("offsets must be non-decreasing (sequence %llu)", (unsigned long long)r); return MODGPU_EINVAL; }
+      if (offs[r + 1] - offs[r] > 0x7FFFFFFFull)         // reference: int len, seqhash.h:50
+        { mg_set_error("sequence %llu longer than 2^31-1", (unsigned long long)r); return MODGPU_EINVAL; }
+    }
+  return MODGPU_OK;
+}
+
+// stage chunk c (sequences cuts[c]..cuts[c+1]) into device buffer c&1
+static int stage_chunk(ModgpuModset *ms, const char *bases, const uint64_t *offs, const std::vector<uint64_t> &cuts, size_t c)
+{
+  const int b = (int)(c & 1);
+  const uint64_t r0 = cuts[c], r1 = cuts[c + 1];
+  const uint64_t nb = offs[r1] - offs[r0], ns = r1 - r0;
+  int rc;
+  // the device buffer is free once the kernels of chunk c-2 are done
+  MG_CUDA(cudaStreamWaitEvent(ms->copyStream, ms->evFree[b], 0));
+  // the pinned offsets buffer is free once the copy of chunk c-2 has completed
+  MG_CUDA(cudaEventSynchronize(ms->evCopied[b]));
+  if ((rc = ms->bases[b].ensure(nb + 64)) || (rc = ms->offs[b].ensure((ns + 1) * 8)) || (rc = ms->hOffs[b].ensure((ns + 1) * 8)))
+    return rc;
+  uint64_t *ho = (uint64_t *)ms->hOffs[b].p;
+  for (uint64_t r = 0; r <= ns; ++r) ho[r] = offs[r0 + r] - offs[r0];
+  if (nb) MG_CUDA(cudaMemcpyAsync(ms->bases[b].p, bases + offs[r0], nb, cudaMemcpyHostToDevice, ms->copyStream));
+  MG_CUDA(cudaMemcpyAsync(ms->offs[b].p, ho, (ns + 1) * 8, cudaMemcpyHostToDevice, ms->copyStream));
+  MG_CUDA(cudaEventRecord(ms->evCopied[b], ms->copyStream));
+  return MODGPU_OK;
+}
+
+extern "C" uint64_t modgpuModsetAdd(ModgpuModset *ms, const char *bases, const uint64_t *offs, uint64_t nSeq, int isAscii)
+{
+  const uint64_t FAIL = 0xFFFFFFFFFFFFFFFFull;
+  if (!ms || !offs) { mg_set_error("modgpuModsetAdd: null argument"); return FAIL; }
+  if (!nSeq) return 0;
+  if (check_offsets(offs, nSeq)) return FAIL;
+  if (!bases && offs[nSeq]) { mg_set_error("modgpuModsetAdd: null bases"); return FAIL; }
+  std::vector<uint64_t> cuts;
+  plan_chunks(offs, nSeq, MG_HOST_CHUNK, cuts);
+  const size_t nChunks = cuts.size() - 1;
+  uint64_t total = 0;
+  // a buffer whose allocation grows must not be in use: growth only happens while staging,
+  // after the waits in stage_chunk have retired the previous user of that buffer
+  if (stage_chunk(ms, bases, offs, cuts, 0)) return FAIL;
+  for (size_t c = 0; c < nChunks; ++c)
+    { const int b = (int)(c & 1);
+      if (c + 1 < nChunks && stage_chunk(ms, bases, offs, cuts, c + 1)) return FAIL;
+      if (mg_check_cuda(cudaStreamWaitEvent(ms->stream, ms->evCopied[b], 0), "cudaStreamWaitEvent", __FILE__, __LINE__)) return FAIL;
+      uint64_t n = 0;
+      const uint64_t r0 = cuts[c], r1 = cuts[c + 1];
+      if (add_chunk_device(ms, (const uint8_t *)ms->bases[b].p, (const uint64_t *)ms->offs[b].p, r1 - r0,
+                           offs[r1] - offs[r0], isAscii, &n))
+        return FAIL;
+      if (mg_check_cuda(cudaEventRecord(ms->evFree[b], ms->stream), "cudaEventRecord", __FILE__, __LINE__)) return FAIL;
+      total += n;
+    }
+  ms->totalHashes += total;
+  if (modgpuTableEntries(ms->table, ms->stream) == FAIL) return FAIL;      // reference: die() on overflow
+  return total;
+}
+
+extern "C" uint64_t modgpuModsetAddDevice(ModgpuModset *ms, const uint8_t *d_bases, const uint64_t *d_offs,
+                                          uint64_t nSeq, uint64_t nBases, int isAscii)
+{
+  const uint64_t FAIL = 0xFFFFFFFFFFFFFFFFull;
+  if (!ms) { mg_set_error("modgpuModsetAddDevice: null modset"); return FAIL; }
+  if (!nSeq || !nBases) return 0;
+  uint64_t total = 0;
+  if (nBases <= MG_DEV_CHUNK)
+    { if (add_chunk_device(ms, d_bases, d_offs, nSeq, nBases, isAscii, &total)) return FAIL; }
+  else
+    { // split at sequence boundaries: needs the offsets on the host
+      std::vector<uint64_t> ho(nSeq + 1);
+      if (mg_check_cuda(cudaMemcpyAsync(ho.data(), d_offs, (nSeq + 1) * 8, cudaMemcpyDeviceToHost, ms->stream), "offsets readback", __FILE__, __LINE__) ||
+          mg_check_cuda(cudaStreamSynchronize(ms->stream), "sync", __FILE__, __LINE__))
+        return FAIL;
+      if (check_offsets(ho.data(), nSeq)) return FAIL;
+      std::vector<uint64_t> cuts;
+      plan_chunks(ho.data(), nSeq, MG_DEV_CHUNK, cuts);
+      for (size_t c = 0; c + 1 < cuts.size(); ++c)
+        { const uint64_t r0 = cuts[c], r1 = cuts[c + 1];
+          const uint64_t nb = ho[r1] - ho[r0], ns = r1 - r0;
+          if (nb >= (1ull << 32)) { mg_set_error("sequence group of %llu bases exceeds 2^32-1", (unsigned long long)nb); return FAIL; }
+          // local offsets for the group
+          if (ms->offs[0].ensure((ns + 1) * 8) || ms->hOffs[0].ensure((ns + 1) * 8)) return FAIL;
+          if (mg_check_cuda(cudaStreamSynchronize(ms->stream), "sync", __FILE__, __LINE__)) return FAIL;
+          uint64_t *hl = (uint64_t *)ms->hOffs[0].p;
+          for (uint64_t r = 0; r <= ns; ++r) hl[r] = ho[r0 + r] - ho[r0];
+          if (mg_check_cuda(cudaMemcpyAsync(ms->offs[0].p, hl, (ns + 1) * 8, cudaMemcpyHostToDevice, ms->stream), "offsets upload", __FILE__, __LINE__)) return FAIL;
+          uint64_t n = 0;
+          if (add_chunk_device(ms, d_bases + ho[r0], (const uint64_t *)ms->offs[0].p, ns, nb, isAscii, &n)) return FAIL;
+          total += n;
+        }
+    }
+  ms->totalHashes += total;
+  if (modgpuTableEntries(ms->table, ms->stream) == FAIL) return FAIL;
+  return total;
+}
+
+extern "C" int modgpuModsetSelectDevice(ModgpuModset *ms, const uint8_t *d_bases, const uint64_t *d_offs,
+                                        uint64_t nSeq, uint64_t nBases, int isAscii,
+                                        const uint64_t **d_kmers, uint64_t *nSelected)
+{
+  if (nBases >= (1ull << 32)) { mg_set_error("modgpuModsetSelectDevice: batch exceeds 2^32-1 bases"); return MODGPU_EINVAL; }
+  int rc = mg_modset_select_chunk(ms, d_bases, d_offs, nSeq, nBases, isAscii, false, 0, nSelected);
+  if (rc) return rc;
+  *d_kmers = (const uint64_t *)ms->kmers.p;
+  return MODGPU_OK;
+}
+
+extern "C" int modgpuModsetSelectHost(ModgpuModset *ms, const char *bases, const uint64_t *offs,
+                                      uint64_t nSeq, int isAscii, const uint64_t **d_kmers, uint64_t *nSelected)
+{
+  *nSelected = 0; *d_kmers = nullptr;
+  if (!nSeq) return MODGPU_OK;
+  int rc = check_offsets(offs, nSeq);
+  if (rc) return rc;
+  const uint64_t nb = offs[nSeq];
+  if (nb >= (1ull << 32)) { mg_set_error("modgpuModsetSelectHost: batch exceeds 2^32-1 bases"); return MODGPU_EINVAL; }
+  if ((rc = ms->bases[0].ensure(nb + 64)) || (rc = ms->offs[0].ensure((nSeq + 1) * 8))) return rc;
+  if (nb) MG_CUDA(cudaMemcpyAsync(ms->bases[0].p, bases, nb, cudaMemcpyHostToDevice, ms->stream));
+  MG_CUDA(cudaMemcpyAsync(ms->offs[0].p, offs, (nSeq + 1) * 8, cudaMemcpyHostToDevice, ms->stream));
+  return modgpuModsetSelectDevice(ms, (const uint8_t *)ms->bases[0].p, (const uint64_t *)ms->offs[0].p, nSeq, nb, isAscii, d_kmers, nSelected);
+}
+
+extern "C" int modgpuModsetInsertDevice(ModgpuModset *ms, const uint64_t *d_kmers, uint64_t n)
+{
+  if (!n) return MODGPU_OK;
+  { ProfScope p(ms, MODGPU_T_INSERT, 1);
+    int rc = mg_table_insert_dev(ms->table, d_kmers, nullptr, n, nullptr, 0, ms->stream);
+    if (rc) return rc;
+  }
+  ms->dirty = true;
+  ms->totalHashes += n;
+  return MODGPU_OK;
+}
+
+extern "C" int modgpuModsetClear(ModgpuModset *ms)
+{
+  ProfScope p(ms, MODGPU_T_OTHER, 1);
+  ms->dirty = false; ms->totalHashes = 0;
+  return modgpuTableClear(ms->table, ms->stream);
+}
+
+// ------------------------------------------------------------- whole set --
+static int ensure_numbered(ModgpuModset *ms)
+{
+  if (!ms->dirty) return MODGPU_OK;
+  ProfScope p(ms, MODGPU_T_OTHER, 3);
+  int rc = modgpuTableNumber(ms->table, nullptr, 0, nullptr, ms->stream);
+  if (rc) return rc;
+  ms->dirty = false;
+  return MODGPU_OK;
+}
+
+int mg_modset_ensure_numbered(ModgpuModset *ms) { return ensure_numbered(ms); }
+void mg_modset_mark(ModgpuModset *ms, bool dirty, bool depthIsZero) { ms->dirty = dirty; ms->depthIsZero = depthIsZero; }
+cudaStream_t mg_modset_stream(ModgpuModset *ms) { return ms->stream; }
+void *mg_modset_kmers(ModgpuModset *ms) { return ms->kmers.p; }
+void *mg_modset_gpos(ModgpuModset *ms) { return ms->gpos.p; }
+
+extern "C" uint32_t modgpuModsetMax(ModgpuModset *ms)
+{
+  if (ensure_numbered(ms)) return 0xFFFFFFFFu;
+  return (uint32_t)mg_table_numbered(ms->table);
+}
+
+extern "C" int modgpuModsetExport(ModgpuModset *ms, uint64_t *value, uint16_t *depth, uint8_t *info)
+{
+  int rc = ensure_numbered(ms);
+  if (rc) return rc;
+  const uint64_t n = mg_table_numbered(ms->table);
+  if (!n) return MODGPU_OK;
+  cudaStream_t st = ms->stream;
+  if ((rc = ms->expo.ensure(n * 11 + 64))) return rc;
+  uint64_t *dV = (uint64_t *)ms->expo.p;
+  uint16_t *dD = (uint16_t *)(dV + n);
+  uint8_t *dI = (uint8_t *)(dD + n);
+  { ProfScope p(ms, MODGPU_T_OTHER, 1);
+    if ((rc = modgpuTableExport(ms->table, dV, dD, dI, nullptr, st))) return rc;
+  }
+  if (value) MG_CUDA(cudaMemcpyAsync(value, dV, n * 8, cudaMemcpyDeviceToHost, st));
+  if (depth)
+    { if (ms->depthIsZero) memset(depth, 0, n * 2);
+      else MG_CUDA(cudaMemcpyAsync(depth, dD, n * 2, cudaMemcpyDeviceToHost, st));
+    }
+  if (info) MG_CUDA(cudaMemcpyAsync(info, dI, n, cudaMemcpyDeviceToHost, st));
+  MG_CUDA(cudaStreamSynchronize(st));
+  return MODGPU_OK;
+}
+
+extern "C" int modgpuModsetHistogram(ModgpuModset *ms, uint32_t *bins65536)
+{
+  int rc = ensure_numbered(ms);
+  if (rc) return rc;
+  if ((rc = ms->expo.ensure(65536 * 4))) return rc;
+  if (ms->depthIsZero)
+    { memset(bins65536, 0, 65536 * 4); bins65536[0] = (uint32_t)mg_table_numbered(ms->table); return MODGPU_OK; }
+  { ProfScope p(ms, MODGPU_T_OTHER, 1);
+    if ((rc = modgpuTableHistogram(ms->table, (uint32_t *)ms->expo.p, ms->stream))) return rc;
+  }
+  MG_CUDA(cudaMemcpyAsync(bins65536, ms->expo.p, 65536 * 4, cudaMemcpyDeviceToHost, ms->stream));
+  MG_CUDA(cudaStreamSynchronize(ms->stream));
+  return MODGPU_OK;
+}
+
+// mode: 0 thresholds (-s), 1 copyM only (-sM), 2 exact multiplicity (modmap), 3 tally only
+static int classify(ModgpuModset *ms, int mode, int c1, int c2, int cM, uint32_t classCounts[4])
+{
+  int rc = ensure_numbered(ms);
+  if (rc) return rc;
+  uint32_t *dC = (uint32_t *)((char *)ms->misc.p + 256);
+  { ProfScope p(ms, MODGPU_T_OTHER, 1);
+    if ((rc = mg_table_classify(ms->table, mode, c1, c2, cM, ms->depthIsZero ? 1 : 0, dC, ms->stream))) return rc;
+  }
+  uint32_t *hC = (uint32_t *)((char *)ms->hMisc.p + 256);
+  MG_CUDA(cudaMemcpyAsync(hC, dC, 16, cudaMemcpyDeviceToHost, ms->stream));
+  MG_CUDA(cudaStreamSynchronize(ms->stream));
+  if (classCounts) memcpy(classCounts, hC, 16);
+  return MODGPU_OK;
+}
+
+int mg_modset_classify(ModgpuModset *ms, int mode, int c1, int c2, int cM, uint32_t classCounts[4])
+{ return classify(ms, mode, c1, c2, cM, classCounts); }
+
+extern "C" int modgpuModsetSetCopy(ModgpuModset *ms, int c1, int c2, int cM, uint32_t classCounts[4])
+{ return classify(ms, 0, c1, c2, cM, classCounts); }
+
+extern "C" int modgpuModsetSetCopyM(ModgpuModset *ms, int cM, uint32_t classCounts[4])
+{ return classify(ms, 1, 0, 0, cM, classCounts); }
+
+extern "C" int modgpuModsetFind(ModgpuModset *ms, const uint64_t *kmers, uint64_t n, uint32_t *index, uint8_t *copy)
+{
+  int rc = ensure_numbered(ms);
+  if (rc) return rc;
+  if (!n) return MODGPU_OK;
+  cudaStream_t st = ms->stream;
+  if ((rc = ms->kmers.ensure(n * 8)) || (rc = ms->slot.ensure(n * 4))) return rc;
+  MG_CUDA(cudaMemcpyAsync(ms->kmers.p, kmers, n * 8, cudaMemcpyHostToDevice, st));
+  { ProfScope p(ms, MODGPU_T_OTHER, 1);
+    if ((rc = mg_table_lookup_dev(ms->table, (const uint64_t *)ms->kmers.p, nullptr, n, (uint32_t *)ms->slot.p, st))) return rc;
+  }
+  std::vector<uint32_t> aux(n);
+  MG_CUDA(cudaMemcpyAsync(aux.data(), ms->slot.p, n * 4, cudaMemcpyDeviceToHost, st));
+  MG_CUDA(cudaStreamSynchronize(st));
+  for (uint64_t i = 0; i < n; ++i)
+    { if (index) index[i] = aux[i] >> 2;
+      if (copy) copy[i] = (uint8_t)(aux[i] & 3u);
+    }
+  return MODGPU_OK;
+}
+
+// modsetSummary (reference modset.c:130-153): the histogram and the class
+// tallies come from the device, only the printf stays here.  Keeps the
+// reference's 32-bit products (depth * binCount is U32 * U32 there).
+extern "C" int modgpuModsetSummary(ModgpuModset *ms, char *buf, int n)
+{
+  if (ensure_numbered(ms)) return -1;
+  const ModgpuHasher *h = &ms->hasher;
+  const uint32_t max = (uint32_t)mg_table_numbered(ms->table);
+  int o = 0;
+  o += snprintf(buf + o, (size_t)(n - o), "SH k %d  w/m %d  s %d\n", h->k, h->w, h->seed);
+  o += snprintf(buf + o, (size_t)(n - o), "MS table bits %d size %llu number of entries %u", ms->bits,
+                (unsigned long long)(1ull << ms->bits), max);
+  if (!max) { o += snprintf(buf + o, (size_t)(n - o), "\n"); return o; }
+  std::vector<uint32_t> bins(65536);
+  uint32_t copy[4];
+  if (modgpuModsetHistogram(ms, bins.data()) || classify(ms, 3, 0, 0, 0, copy)) return -1;
+  uint32_t top = 0;
+  for (uint32_t i = 0; i < 65536; ++i) if (bins[i]) top = i + 1;
+  uint64_t sum = 0, tot = 0;
+  for (uint32_t i = 0; i < top; ++i) { sum += bins[i]; tot += (uint32_t)(i * bins[i]); }
+  int64_t half = (int64_t)(tot / 2);
+  uint32_t n50;
+  for (n50 = 0; n50 < top; ++n50) { half -= (uint32_t)(n50 * bins[n50]); if (half < 0) break; }
+  o += snprintf(buf + o, (size_t)(n - o), " total count %llu\nMS average depth %.1f N50 depth %u",
+                (unsigned long long)tot, tot / (double)sum, n50);
+  if (copy[0] < max)
+    o += snprintf(buf + o, (size_t)(n - o), " copy0 %u copy1 %u copy2 %u copyM %u", copy[0], copy[1], copy[2], copy[3]);
+  o += snprintf(buf + o, (size_t)(n - o), "\n");
+  return o;
+}
+
+extern "C" int modgpuModsetImport(ModgpuModset *ms, const uint64_t *value, const uint16_t *depth,
+                                  const uint8_t *info, uint64_t n)
+{
+  int rc = ensure_numbered(ms);
+  if (rc) return rc;
+  if (!n) return MODGPU_OK;
+  cudaStream_t st = ms->stream;
+  if ((rc = ms->expo.ensure(n * 11 + 64))) return rc;
+  uint64_t *dV = (uint64_t *)ms->expo.p;
+  uint16_t *dD = (uint16_t *)(dV + n);
+  uint8_t *dI = (uint8_t *)(dD + n);
+  MG_CUDA(cudaMemcpyAsync(dV, value, n * 8, cudaMemcpyHostToDevice, st));
+  if (depth) MG_CUDA(cudaMemcpyAsync(dD, depth, n * 2, cudaMemcpyHostToDevice, st));
+  if (info) MG_CUDA(cudaMemcpyAsync(dI, info, n, cudaMemcpyHostToDevice, st));
+  { ProfScope p(ms, MODGPU_T_OTHER, 1);
+    if ((rc = modgpuTableImport(ms->table, dV, depth ? dD : nullptr, info ? dI : nullptr, n, st))) return rc;
+  }
+  if (modgpuTableEntries(ms->table, st) == 0xFFFFFFFFFFFFFFFFull) return MODGPU_EFULL;
+  return MODGPU_OK;
+}

@@ -1,0 +1,255 @@
+// hash_select.cu - K2: canonical k-mer hashing + hash % d == 0 selection.
+//
+// replaces: modRCiterator / modRCnext / advanceHashRC / hashRC of the
+// reference (seqhash.c:60-79,154-196) for a whole batch of sequences at once.
+//
+// What the reference's serial "rolling" iterator computes per window start p is
+// a pure function of the 2k-bit window, so positions are
+// independent.  Layout of the work:
+//   - a thread owns a RUN of 32 consecutive window starts = one packed word
+//     plus the next (k-1 <= 30 overlap bases); forward and reverse-complement
+//     k-mers of window i are constant-shift bit fields of two 128-bit registers
+//     (mg_run_fwd / mg_run_rc), no per-base extraction, no serial dependence;
+//   - a 256-thread tile = 8192 bases = 2 KiB packed + 1 KiB end flags, staged
+//     in shared memory by one TMA bulk copy per stream (cp.async.bulk +
+//     mbarrier, double buffered), so the next tile streams in while this one
+//     is hashed;
+//   - tiles are claimed through an atomic ticket; the selected list is written
+//     in input order with a decoupled look-back scan (ORDERED) or at an
+//     atomically reserved offset (count mode, order irrelevant);
+//   - when d = 2^t * odd with t >= 3 and 64-2k+t <= 32 (e.g. k=31 d=64, the
+//     modmap index configuration) a PREFILTER evaluates only the low product
+//     word of both strands (2 IMAD + 2 compares per base) and the full 64-bit
+//     canonical test runs on the ~2/2^t surviving candidates.
+//
+// Integer-issue bound, not HBM bound (0.25 + 8/d algorithmic bytes per base
+// against ~9-28 instructions per base) - see DESIGN.md for the roofline.
+#include "mg_device.cuh"
+
+#define MG_TILE_PACK_BYTES (MG_TILE_THREADS * 8 + 16)     // 256 words + overlap word, 16 B multiple
+#define MG_TILE_ENDS_BYTES (MG_TILE_THREADS * 4 + 16)
+
+struct SelectParams {
+  MgKHasher H;
+  const uint64_t *packed;
+  const uint32_t *ends;
+  uint64_t nBases;
+  uint32_t nTiles;
+  uint32_t strandBit;          // MODGPU_SEL_STRAND
+  uint64_t *outKmer;
+  uint32_t *outPos;            // nullable
+  uint64_t cap;
+  unsigned long long *count;   // device total
+  uint64_t *status;            // look-back descriptors [nTiles]
+  uint32_t *ticket;            // tile ticket
+};
+
+template <bool PREFILTER, bool ORDERED, bool TMA>
+__global__ void __launch_bounds__(MG_TILE_THREADS) hash_select_kernel(const SelectParams P)
+{
+  __shared__ __align__(128) uint64_t sPack[TMA ? 2 : 1][TMA ? (MG_TILE_PACK_BYTES / 8) : 2];
+  __shared__ __align__(128) uint32_t sEnds[TMA ? 2 : 1][TMA ? (MG_TILE_ENDS_BYTES / 4) : 4];
+  __shared__ __align__(8) uint64_t sBar[2];
+  __shared__ uint32_t sTile[2];
+  __shared__ uint32_t sWarp[MG_TILE_THREADS / 32];
+  __shared__ uint64_t sBase;
+
+  const MgKHasher &H = P.H;
+  const uint32_t tid = threadIdx.x;
+
+  if (tid == 0)
+    { if (TMA)
+        { mg_mbar_init(&sBar[0], 1);
+          mg_mbar_init(&sBar[1], 1);
+          mg_fence_barrier_init();
+        }
+      uint32_t t0 = atomicAdd(P.ticket, 1u);
+      sTile[0] = t0;
+      if (TMA && t0 < P.nTiles)
+        { mg_mbar_expect_tx(&sBar[0], MG_TILE_PACK_BYTES + MG_TILE_ENDS_BYTES);
+          mg_tma_load_1d(sPack[0], P.packed + (uint64_t)t0 * MG_TILE_THREADS, MG_TILE_PACK_BYTES, &sBar[0]);
+          mg_tma_load_1d(sEnds[0], P.ends + (uint64_t)t0 * MG_TILE_THREADS, MG_TILE_ENDS_BYTES, &sBar[0]);
+        }
+    }
+
+  for (uint32_t it = 0;; ++it)
+    { const uint32_t stage = it & 1;
+      __syncthreads();               // sTile[stage] visible; everyone is done with buffer stage^1
+      const uint32_t tile = sTile[stage];
+      if (tile >= P.nTiles) break;
+
+      if (tid == 0)
+        { uint32_t tn = atomicAdd(P.ticket, 1u);
+          sTile[stage ^ 1] = tn;
+          if (TMA && tn < P.nTiles)
+            { mg_mbar_expect_tx(&sBar[stage ^ 1], MG_TILE_PACK_BYTES + MG_TILE_ENDS_BYTES);
+              mg_tma_load_1d(sPack[stage ^ 1], P.packed + (uint64_t)tn * MG_TILE_THREADS, MG_TILE_PACK_BYTES, &sBar[stage ^ 1]);
+              mg_tma_load_1d(sEnds[stage ^ 1], P.ends + (uint64_t)tn * MG_TILE_THREADS, MG_TILE_ENDS_BYTES, &sBar[stage ^ 1]);
+            }
+        }
+
+      // ---- this thread's run: 64 bases of sequence, 64 end flags
+      const uint64_t word = (uint64_t)tile * MG_TILE_THREADS + tid;
+      uint64_t w0, w1, eflags;
+      if (TMA)
+        { mg_mbar_wait(&sBar[stage], (it >> 1) & 1);
+          w0 = sPack[stage][tid];
+          w1 = sPack[stage][tid + 1];
+          eflags = (uint64_t)sEnds[stage][tid] | ((uint64_t)sEnds[stage][tid + 1] << 32);
+        }
+      else
+        { w0 = __ldg(P.packed + word);
+          w1 = __ldg(P.packed + word + 1);
+          eflags = (uint64_t)__ldg(P.ends + word) | ((uint64_t)__ldg(P.ends + word + 1) << 32);
+        }
+      const uint64_t p0 = word * MG_RUN;                   // global offset of window 0
+      const uint32_t usable = mg_run_usable(eflags, H.k, p0, P.nBases);
+
+      const MgRun R = mg_run_prepare(w0, w1, H.k);
+
+      // ---- selection mask over the 32 window starts
+      uint32_t sel = 0;
+      if (PREFILTER)
+        { uint32_t cand = 0;
+#pragma unroll
+          for (int i = 0; i < MG_RUN; ++i)
+            cand |= (mg_prefilter_candidate(H, R, i) ? 1u : 0u) << i;
+          cand &= usable;
+          while (cand)
+            { uint32_t i = __ffs(cand) - 1; cand &= cand - 1;
+              uint64_t km; bool isF;
+              if (mg_eval_window(H, R, i, &km, &isF)) sel |= 1u << i;
+            }
+        }
+      else
+        {
+#pragma unroll
+          for (int i = 0; i < MG_RUN; ++i)
+            { uint64_t km; bool isF;
+              bool ok = mg_eval_window(H, R, i, &km, &isF);
+              sel |= (ok ? 1u : 0u) << i;
+            }
+          sel &= usable;
+        }
+
+      // ---- where do this tile's results go
+      uint32_t total;
+      uint32_t off = mg_block_excl_scan256(__popc(sel), sWarp, &total);
+      if (tid < 32)
+        { if (ORDERED)
+            { uint32_t excl = mg_lookback(P.status, tile, total);
+              if (tid == 0)
+                { sBase = excl;
+                  if (tile == P.nTiles - 1) *P.count = (unsigned long long)excl + total;
+                }
+            }
+          else if (tid == 0)
+            sBase = total ? atomicAdd(P.count, (unsigned long long)total) : 0ull;
+        }
+      __syncthreads();
+      uint64_t dst = sBase + off;
+
+      // ---- write the selected k-mers (winning strand, seqhash.c:183)
+      while (sel)
+        { uint32_t i = __ffs(sel) - 1; sel &= sel - 1;
+          uint64_t km; bool isF;
+          mg_eval_window(H, R, i, &km, &isF);
+          if (dst < P.cap)
+            { if (P.strandBit && isF) km |= 1ull << 63;
+              P.outKmer[dst] = km;
+              if (P.outPos) P.outPos[dst] = (uint32_t)(p0 + i);
+            }
+          ++dst;
+        }
+    }
+}
+
+// ------------------------------------------------------------------- host
+extern "C" uint64_t modgpuHashSelectWorkspace(uint64_t nBases)
+{
+  uint64_t words = (nBases + 31) / 32;
+  uint64_t tiles = (words + MG_TILE_THREADS - 1) / MG_TILE_THREADS;
+  return 64 + tiles * sizeof(uint64_t);          // ticket (+pad) then descriptors
+}
+
+MgKHasher mg_khasher_from(const ModgpuHasher *h) { return mg_make_khasher(h->k, h->w, h->factor1); }
+
+template <bool PF, bool ORD, bool TMA>
+static int launch_select(const SelectParams &P, cudaStream_t st)
+{
+  static int blocksPerSm = 0;
+  if (!blocksPerSm)
+    { MG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, hash_select_kernel<PF, ORD, TMA>, MG_TILE_THREADS, 0));
+      if (blocksPerSm < 1) blocksPerSm = 1;
+    }
+  uint64_t grid = (uint64_t)mg_num_sms() * blocksPerSm;
+  if (grid > P.nTiles) grid = P.nTiles;
+  hash_select_kernel<PF, ORD, TMA><<<(unsigned)grid, MG_TILE_THREADS, 0, st>>>(P);
+  MG_LAUNCH_CHECK("hash_select");
+  return MODGPU_OK;
+}
+
+extern "C" int modgpuHashSelect(const ModgpuHasher *h, const uint64_t *d_packed, const uint32_t *d_ends,
+                                uint64_t nBases, uint64_t *d_kmers, uint32_t *d_gpos, uint64_t cap,
+                                uint64_t *d_count, void *d_workspace, int flags, void *stream)
+{
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!h || h->k < 1 || h->k > 31 || h->w < 1) { mg_set_error("modgpuHashSelect: bad hasher"); return MODGPU_EINVAL; }
+  if (nBases >= (1ull << 32)) { mg_set_error("modgpuHashSelect: batch of %llu bases exceeds 2^32-1", (unsigned long long)nBases); return MODGPU_EINVAL; }
+  MG_CUDA(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
+  if (!nBases) return MODGPU_OK;
+  SelectParams P;
+  P.H = mg_khasher_from(h);
+  P.packed = d_packed; P.ends = d_ends; P.nBases = nBases;
+  uint64_t words = (nBases + 31) / 32;
+  P.nTiles = (uint32_t)((words + MG_TILE_THREADS - 1) / MG_TILE_THREADS);
+  P.strandBit = (flags & MODGPU_SEL_STRAND) ? 1u : 0u;
+  P.outKmer = d_kmers; P.outPos = d_gpos; P.cap = cap;
+  P.count = (unsigned long long *)d_count;
+  P.ticket = (uint32_t *)d_workspace;
+  P.status = (uint64_t *)((char *)d_workspace + 64);
+  MG_CUDA(cudaMemsetAsync(d_workspace, 0, modgpuHashSelectWorkspace(nBases), st));
+  const bool pf = P.H.prefilter && !(flags & MODGPU_SEL_NOPREFILTER);
+  const bool ord = (flags & MODGPU_SEL_ORDERED) != 0;
+  const bool tma = !(flags & MODGPU_SEL_NOTMA);
+#define MG_SEL_CASE(a, b, c) if (pf == a && ord == b && tma == c) return launch_select<a, b, c>(P, st);
+  MG_SEL_CASE(true, true, true) MG_SEL_CASE(true, true, false)
+  MG_SEL_CASE(true, false, true) MG_SEL_CASE(true, false, false)
+  MG_SEL_CASE(false, true, true) MG_SEL_CASE(false, true, false)
+  MG_SEL_CASE(false, false, true) MG_SEL_CASE(false, false, false)
+#undef MG_SEL_CASE
+  return MODGPU_EINVAL;
+}
+
+// ---------------------------------------------------------------- locate --
+// global offset -> (sequence id, offset in sequence): the id/offset columns
+// the reference fills at modmap.c:113-116.  Binary search over the offsets.
+__global__ void __launch_bounds__(256) locate_kernel(const uint32_t *__restrict__ gpos, uint64_t n,
+                                                     const uint64_t *__restrict__ offs, uint64_t nSeq,
+                                                     uint32_t *__restrict__ id, uint32_t *__restrict__ pos)
+{
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    { uint64_t g = gpos[i];
+      uint64_t lo = 0, hi = nSeq;                     // last r with offs[r] <= g
+      while (hi - lo > 1)
+        { uint64_t mid = (lo + hi) >> 1;
+          if (__ldg(offs + mid) <= g) lo = mid; else hi = mid;
+        }
+      if (id) id[i] = (uint32_t)lo;
+      if (pos) pos[i] = (uint32_t)(g - __ldg(offs + lo));
+    }
+}
+
+extern "C" int modgpuLocate(const uint32_t *d_gpos, uint64_t n, const uint64_t *d_offs, uint64_t nSeq,
+                            uint32_t *d_id, uint32_t *d_pos, void *stream)
+{
+  if (!n) return MODGPU_OK;
+  if (!nSeq) { mg_set_error("modgpuLocate: no sequences"); return MODGPU_EINVAL; }
+  uint64_t blocks = (n + 255) / 256;
+  uint64_t maxBlocks = (uint64_t)mg_num_sms() * 8;
+  if (blocks > maxBlocks) blocks = maxBlocks;
+  locate_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_gpos, n, d_offs, nSeq, d_id, d_pos);
+  MG_LAUNCH_CHECK("locate");
+  return MODGPU_OK;
+}

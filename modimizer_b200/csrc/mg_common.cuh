@@ -1,0 +1,246 @@
+// mg_common.cuh - shared types and arithmetic of libmodgpu (sm_100a).
+//
+// The arithmetic in this header is __host__ __device__ on purpose: tests/ compiles
+// it with the host compiler and checks it against the oracle position by
+// position (tests/test_math_host.py), so that what the kernels compute per base
+// is verified even on a box without a GPU.  The product never runs it on the
+// CPU: every public entry point launches kernels or fails.
+#pragma once
+
+#include <stdint.h>
+#include <stddef.h>
+
+#if defined(__CUDACC__)
+#define MGHD __host__ __device__ __forceinline__
+#define MGD __device__ __forceinline__
+#else
+#define MGHD static inline
+#define MGD static inline
+#endif
+
+// ----------------------------------------------------------------- geometry
+// One thread owns a RUN of 32 consecutive window starts (= one packed word),
+// one warp 1024, one 256-thread tile 8192 bases = 2 KiB of packed sequence.
+#define MG_RUN 32
+#define MG_TILE_THREADS 256
+#define MG_TILE_BASES (MG_RUN * MG_TILE_THREADS)
+// slack words readable past the last tile (thread t also reads word t+1)
+#define MG_PACK_SLACK_WORDS 8
+
+// ------------------------------------------------------------ kernel hasher
+// Device view of the reference Seqhash (seqhash.h:15-23) plus precomputed
+// constants of the divisibility test and of the power-of-two prefilter.
+struct MgKHasher {
+  uint64_t factor;      // factor1
+  uint64_t mask;        // 2k low bits
+  uint64_t oddInv;      // inverse of the odd part of d modulo 2^64
+  uint64_t oddLim;      // floor((2^64-1) / odd part)
+  uint32_t k;
+  uint32_t shift;       // 64 - 2k
+  uint32_t d;           // modulus (reference w)
+  uint32_t tz;          // d = 2^tz * odd
+  uint32_t prefilter;   // 1: low-word candidate filter usable (tz >= 3, shift + tz <= 32)
+  uint32_t pfMul;       // (uint32) factor << (32 - shift - tz)
+  uint32_t pfLim;       // 1 << (32 - tz)
+  uint32_t pad_;
+};
+
+MGHD uint64_t mg_mulinv64(uint64_t a)   // a odd: Newton iteration, 5 steps double the bits 5->64
+{
+  uint64_t x = a;                       // correct to 3 bits (a*a = 1 mod 8)
+  for (int i = 0; i < 6; ++i) x *= 2 - a * x;
+  return x;
+}
+
+MGHD MgKHasher mg_make_khasher(int k, int d, uint64_t factor1)
+{
+  MgKHasher H;
+  H.factor = factor1;
+  H.k = (uint32_t)k;
+  H.shift = (uint32_t)(64 - 2 * k);
+  H.mask = (((uint64_t)1) << (2 * k)) - 1;
+  H.d = (uint32_t)d;
+  uint32_t tz = 0, odd = (uint32_t)d;
+  while (!(odd & 1)) { odd >>= 1; ++tz; }
+  H.tz = tz;
+  H.oddInv = mg_mulinv64(odd);
+  H.oddLim = 0xFFFFFFFFFFFFFFFFull / odd;
+  H.prefilter = (tz >= 3 && H.shift + tz <= 32) ? 1u : 0u;
+  H.pfMul = H.prefilter ? (uint32_t)(factor1 << (32 - H.shift - tz)) : 0u;
+  H.pfLim = H.prefilter ? (1u << (32 - tz)) : 0u;
+  H.pad_ = 0;
+  return H;
+}
+
+// seqhash() of the reference (seqhash.h:58)
+MGHD uint64_t mg_hash(const MgKHasher &H, uint64_t kmer) { return (kmer * H.factor) >> H.shift; }
+
+// hash % d == 0 without a division (the reference spends most of its 10 ns/base
+// in this `%`, seqhash.c:171,190): low tz bits zero, and exact-division test
+// for the odd part: n divisible by odd  <=>  n * inv(odd) mod 2^64 <= (2^64-1)/odd
+MGHD bool mg_divisible(const MgKHasher &H, uint64_t hash)
+{
+  if (hash & ((1ull << H.tz) - 1)) return false;
+  return (hash >> H.tz) * H.oddInv <= H.oddLim;
+}
+
+// canonical choice of hashRC (seqhash.c:60-68): forward only if strictly smaller
+MGHD bool mg_canonical_select(const MgKHasher &H, uint64_t fwd, uint64_t rc, bool *isF)
+{
+  uint64_t hf = mg_hash(H, fwd), hr = mg_hash(H, rc);
+  bool f = hf < hr;
+  *isF = f;
+  return mg_divisible(H, f ? hf : hr);
+}
+
+// ------------------------------------------------------------- 2-bit windows
+// A run's view of the packed stream: two consecutive words w0:w1 = 64 bases,
+// base j at bits [126-2j, 127-2j] of the 128-bit value (first base on top).
+// The reverse-complement stream keeps base j at bits [2j, 2j+1], complemented,
+// so that the rc k-mer of window i is again a plain bit field (seqhash.c:74:
+// rc rolls in at the top, i.e. base p+m of the window sits at bits 2m).
+struct MgRun {
+  uint64_t yhi, ylo;    // (w0:w1) >> (64 - 2k): forward k-mer i = (y >> (64-2i)) & mask
+  uint64_t rhi, rlo;    // ~pairreverse(w0:w1):  rc k-mer i      = (r >> 2i) & mask
+};
+
+MGHD uint64_t mg_pairrev64(uint64_t x)
+{
+#if defined(__CUDA_ARCH__)
+  uint64_t y = __brevll(x);
+#else
+  uint64_t y = x;
+  y = ((y >> 1) & 0x5555555555555555ull) | ((y & 0x5555555555555555ull) << 1);
+  y = ((y >> 2) & 0x3333333333333333ull) | ((y & 0x3333333333333333ull) << 2);
+  y = ((y >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((y & 0x0F0F0F0F0F0F0F0Full) << 4);
+  y = ((y >> 8) & 0x00FF00FF00FF00FFull) | ((y & 0x00FF00FF00FF00FFull) << 8);
+  y = ((y >> 16) & 0x0000FFFF0000FFFFull) | ((y & 0x0000FFFF0000FFFFull) << 16);
+  y = (y >> 32) | (y << 32);
+#endif
+  // full bit reversal also swapped the two bits inside every base: swap back
+  return ((y >> 1) & 0x5555555555555555ull) | ((y & 0x5555555555555555ull) << 1);
+}
+
+MGHD MgRun mg_run_prepare(uint64_t w0, uint64_t w1, uint32_t k)
+{
+  MgRun R;
+  uint32_t s = 64 - 2 * k;                   // 2..62
+  R.yhi = w0 >> s;
+  R.ylo = (w0 << (64 - s)) | (w1 >> s);
+  R.rlo = ~mg_pairrev64(w0);
+  R.rhi = ~mg_pairrev64(w1);
+  return R;
+}
+
+// forward / reverse-complement k-mer of window i (0..31) of a run
+MGHD uint64_t mg_run_fwd(const MgRun &R, uint32_t i, uint64_t mask)
+{
+  uint64_t v = i ? ((R.yhi << (2 * i)) | (R.ylo >> (64 - 2 * i))) : R.yhi;
+  return v & mask;
+}
+
+MGHD uint64_t mg_run_rc(const MgRun &R, uint32_t i, uint64_t mask)
+{
+  uint64_t v = i ? ((R.rlo >> (2 * i)) | (R.rhi << (64 - 2 * i))) : R.rlo;
+  return v & mask;
+}
+
+// Window starts of a run that may NOT be used: a k-mer must not span two
+// sequences (modRCiterator is per sequence, seqhash.c:154-177).  `ends` = end
+// flags of the 64 bases starting at the run (bit j = base j is the last base of
+// a sequence).  Start i is blocked iff a flag sits on one of the window's first
+// k-1 bases, i.e. bits i .. i+k-2.  Returns the 32-bit blocked mask.
+MGHD uint32_t mg_blocked_mask(uint64_t ends, uint32_t k)
+{
+  uint32_t L = k - 1;                       // window of flags to OR, 0..30
+  if (L == 0) return 0u;
+  uint64_t s = ends;                        // OR over 1 flag
+  uint32_t have = 1;
+  while (have * 2 <= L) { s |= s >> have; have *= 2; }   // OR over `have` flags, have = 2^m <= L
+  s |= s >> (L - have);                     // OR over exactly L flags
+  return (uint32_t)s;
+}
+
+// full canonical evaluation of window i of a run: hashRC (seqhash.c:60-68)
+// followed by the `% w` of modRCiterator/modRCnext (seqhash.c:171,190)
+MGHD bool mg_eval_window(const MgKHasher &H, const MgRun &R, uint32_t i, uint64_t *kmer, bool *isF)
+{
+  uint64_t f = mg_run_fwd(R, i, H.mask), r = mg_run_rc(R, i, H.mask);
+  uint64_t hf = mg_hash(H, f), hr = mg_hash(H, r);
+  bool fw = hf < hr;
+  uint64_t hv = fw ? hf : hr;
+  *kmer = fw ? f : r;
+  *isF = fw;
+  bool lowOk = (hv & ((1ull << H.tz) - 1)) == 0;
+  bool oddOk = (hv >> H.tz) * H.oddInv <= H.oddLim;
+  return lowOk && oddOk;
+}
+
+// power-of-two prefilter (H.prefilter): a window can only be selected if the tz
+// low bits of hash(fwd) or of hash(rc) are zero, and with 64-2k+tz <= 32 those
+// bits live in the LOW 32-bit word of the product, which depends only on the low
+// word of the k-mer: (lo * factor) >> shift & (2^tz - 1) == 0
+//   <=>  lo * (factor << (32-shift-tz))  <  2^(32-tz)        (mod 2^32)
+MGHD bool mg_prefilter_candidate(const MgKHasher &H, const MgRun &R, uint32_t i)
+{
+  uint32_t flo = i ? (uint32_t)((R.yhi << (2 * i)) | (R.ylo >> (64 - 2 * i))) : (uint32_t)R.yhi;
+  uint32_t rlo = i ? (uint32_t)((R.rlo >> (2 * i)) | (R.rhi << (64 - 2 * i))) : (uint32_t)R.rlo;
+  return (flo * H.pfMul < H.pfLim) | (rlo * H.pfMul < H.pfLim);
+}
+
+// window starts of the run at global offset p0 that may be selected at all
+MGHD uint32_t mg_run_usable(uint64_t eflags, uint32_t k, uint64_t p0, uint64_t nBases)
+{
+  uint32_t usable = ~mg_blocked_mask(eflags, k);
+  if (p0 + MG_RUN > nBases)
+    usable &= (p0 >= nBases) ? 0u : ((1u << (uint32_t)(nBases - p0)) - 1u);
+  return usable;
+}
+
+// ---- K1 arithmetic: four bytes -> four 2-bit codes, first byte in the top two
+// bits of the 8-bit result.  ASCII: ((c>>1)^(c>>2))&3 maps A,a->0 C,c->1 G,g->2
+// T,t->3 and N,n->0 (dna2indexConv with the N patch, seqio.c:643-652, modutils.c:39)
+MGHD uint32_t mg_pack4(uint32_t v, bool ascii)
+{
+  uint32_t c = ascii ? (((v >> 1) ^ (v >> 2)) & 0x03030303u) : (v & 0x03030303u);
+  return (c * 0x40100401u) >> 24;      // gather: byte0 -> bits 7:6 ... byte3 -> bits 1:0
+}
+
+MGHD uint64_t mg_pack32(const uint32_t v[8], bool ascii)
+{
+  uint32_t hi = (mg_pack4(v[0], ascii) << 24) | (mg_pack4(v[1], ascii) << 16) | (mg_pack4(v[2], ascii) << 8) | mg_pack4(v[3], ascii);
+  uint32_t lo = (mg_pack4(v[4], ascii) << 24) | (mg_pack4(v[5], ascii) << 16) | (mg_pack4(v[6], ascii) << 8) | mg_pack4(v[7], ascii);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+MGHD uint32_t mg_code_of(uint32_t ch, bool ascii) { return ascii ? (((ch >> 1) ^ (ch >> 2)) & 3u) : (ch & 3u); }
+
+// ------------------------------------------------------------------- table
+// 16-byte slot, one 32-byte sector holds two: a probe costs one sector.
+struct __attribute__((aligned(16))) MgSlot {
+  uint64_t key;        // k-mer (< 2^62) or MG_EMPTY
+  uint32_t count;      // occurrences (reference depth, clamped to 65535 on export)
+  uint32_t aux;        // see MG_AUX_*
+};
+
+#define MG_EMPTY 0xFFFFFFFFFFFFFFFFull
+// aux word:  < MG_AUX_ORD : (dense index << 2) | copy class      (numbered entry)
+//           >= MG_AUX_ORD : not numbered yet; MG_AUX_ORD + ordinal of the first
+//                           occurrence in the current exact-order batch, or
+//                           MG_AUX_FRESH when no ordinal was recorded
+#define MG_AUX_ORD 0xC0000000u
+#define MG_AUX_FRESH 0xFFFFFFFFu
+#define MG_MAX_INDEX ((MG_AUX_ORD >> 2) - 1)
+
+MGHD uint64_t mg_slot_hash(uint64_t kmer, uint32_t slotBits)
+{
+  return (kmer * 0x9E3779B97F4A7C15ull) >> (64 - slotBits);
+}
+
+// owner GPU of a k-mer in the hash-sharded multi-GPU table: an independent
+// multiplicative hash mapped uniformly onto [0, nOwners)
+MGHD uint32_t mg_owner(uint64_t kmer, uint32_t nOwners)
+{
+  uint64_t h = (kmer * 0xD6E8FEB86659FD93ull) >> 32;
+  return (uint32_t)((h * nOwners) >> 32);
+}

@@ -1,0 +1,347 @@
+// refmap.cu - the modmap side of the hot path on the device.
+//
+//   modgpuReferenceBuild == referenceFastaRead's insert loop + classification
+//                           + modsetPack + referencePack (reference
+//                           modmap.c:93-134, 74-91): per selected reference
+//                           k-mer the triple (index, offset, id), per index the
+//                           multiplicity, loc[] = exclusive prefix sum of the
+//                           multiplicities, rev[] = occurrences grouped by index.
+//   modgpuReferenceQuery == the seed loop of queryProcess (modmap.c:196-231):
+//                           lookup of every read modimizer, the Q-line
+//                           counters and the reference hits of copy-1/2 seeds.
+//
+// Index numbering is the reference's (first occurrence, modset.c:57), so the
+// arrays are identical to the reference's, not merely isomorphic.
+// rev[] needs a stable sort of the occurrence list by index; that one step uses
+// cub::DeviceRadixSort (header-only, ships with the toolkit) - it is outside the
+// north-star hot path; everything else here is hand-written.
+#include <vector>
+#include <string.h>
+#include <cub/device/device_radix_sort.cuh>
+#include "mg_device.cuh"
+#include "mg_scan.cuh"
+
+struct ModgpuModset;
+int mg_modset_select_chunk(ModgpuModset *ms, const uint8_t *d_bases, const uint64_t *d_offs,
+                           uint64_t nSeq, uint64_t nBases, int isAscii, bool wantPos, int extraFlags,
+                           uint64_t *nSelected);
+int mg_table_insert_dev(ModgpuTable *t, const uint64_t *d_kmers, const uint64_t *d_n, uint64_t nMax,
+                        uint32_t *d_slot, int exactOrder, cudaStream_t st);
+int mg_table_lookup_dev(const ModgpuTable *t, const uint64_t *d_kmers, const uint64_t *d_n, uint64_t nMax,
+                        uint32_t *d_out, cudaStream_t st);
+uint64_t mg_table_numbered(const ModgpuTable *t);
+int mg_modset_classify(ModgpuModset *ms, int mode, int c1, int c2, int cM, uint32_t classCounts[4]);
+int mg_modset_ensure_numbered(ModgpuModset *ms);
+void mg_modset_mark(ModgpuModset *ms, bool dirty, bool depthIsZero);
+cudaStream_t mg_modset_stream(ModgpuModset *ms);
+// scratch of the modset object (api.cu)
+void *mg_modset_kmers(ModgpuModset *ms);
+void *mg_modset_gpos(ModgpuModset *ms);
+
+static const uint64_t MG_REF_CHUNK = 1ull << 31;
+static const uint32_t MG_REF_CAP = 1u << 26;      // modmap.c:363: referenceCreate(ms, 1 << 26)
+
+struct RBuf {
+  void *p = nullptr; size_t cap = 0;
+  int ensure(size_t bytes, cudaStream_t st, bool keep = false)
+  {
+    if (bytes <= cap) return MODGPU_OK;
+    void *q = nullptr;
+    size_t want = bytes + bytes / 4 + 256;
+    MG_CUDA(cudaMalloc(&q, want));
+    if (p && keep) MG_CUDA(cudaMemcpyAsync(q, p, cap, cudaMemcpyDeviceToDevice, st));
+    if (p) { MG_CUDA(cudaStreamSynchronize(st)); cudaFree(p); }
+    p = q; cap = want;
+    return MODGPU_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct ModgpuReference {
+  ModgpuModset *ms = nullptr;
+  uint32_t max = 0;                      // number of reference hits (ref->max)
+  RBuf index, offset, id;                // per hit                      modmap.c:38-41
+  RBuf depth, loc;                       // per modset index, max+1      modmap.c:42,44
+  RBuf rev;                              // per hit, grouped by index    modmap.c:43
+  RBuf tmp, tmp2, sortTmp, slot, bases, offs, misc;
+  void *hPinned = nullptr;
+};
+
+// ------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(256) add_const_kernel(uint32_t *a, uint64_t n, uint32_t c)
+{
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a[i] += c;
+}
+
+__global__ void __launch_bounds__(256) iota_kernel(uint32_t *a, uint64_t n)
+{
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a[i] = (uint32_t)i;
+}
+
+// loc[i] = sum of depth[0..i-1]  (modmap.c:84-86; depth[0] = 0)
+struct LocScan {
+  const uint32_t *depth; uint32_t *loc;
+  __device__ uint32_t value(uint64_t i) const { return depth[i]; }
+  __device__ void emit(uint64_t i, uint32_t prefix, uint32_t) const { loc[i] = prefix; }
+};
+
+// per seed: counters of the Q line and the reference hits of the -v lines
+__global__ void __launch_bounds__(256) query_resolve_kernel(const uint32_t *__restrict__ aux, uint64_t n,
+                                                            const uint32_t *__restrict__ readId,
+                                                            const uint32_t *__restrict__ loc, const uint32_t *__restrict__ rev,
+                                                            const uint32_t *__restrict__ refId, const uint32_t *__restrict__ refOffset,
+                                                            uint32_t *__restrict__ seedIndex, uint32_t *__restrict__ hitId,
+                                                            uint32_t *__restrict__ hitOffset, int32_t *counters)
+{
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    { uint32_t a = aux[i];
+      uint32_t ix = a >> 2, cls = a & 3u;
+      seedIndex[i] = ix;
+      uint32_t h0 = 0xFFFFFFFFu, o0 = 0xFFFFFFFFu, h1 = 0xFFFFFFFFu, o1 = 0xFFFFFFFFu;
+      if (!ix) atomicAdd(&counters[4 * (uint64_t)readId[i]], 1);               // miss         modmap.c:207
+      else
+        { if (cls) atomicAdd(&counters[4 * (uint64_t)readId[i] + cls], 1);     // ++copy[msCopy], modmap.c:206
+          if (cls != 3)                                                        // modmap.c:217
+            { uint32_t l = rev[loc[ix]];                                       // modmap.c:219
+              h0 = refId[l]; o0 = refOffset[l];
+              if (cls != 1) { uint32_t l2 = rev[loc[ix] + 1]; h1 = refId[l2]; o1 = refOffset[l2]; }   // modmap.c:226
+            }
+        }
+      hitId[2 * i] = h0; hitId[2 * i + 1] = h1;
+      hitOffset[2 * i] = o0; hitOffset[2 * i + 1] = o1;
+    }
+}
+
+// seedOff[r] = number of seeds whose read id is < r (ids are non-decreasing)
+__global__ void __launch_bounds__(256) seed_offsets_kernel(const uint32_t *__restrict__ readId, uint64_t n,
+                                                           uint64_t nSeq, uint64_t base, uint64_t *seedOff)
+{
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r <= nSeq; r += stride)
+    { uint64_t lo = 0, hi = n;                       // first i with readId[i] >= r
+      while (lo < hi)
+        { uint64_t mid = (lo + hi) >> 1;
+          if (readId[mid] < r) lo = mid + 1; else hi = mid;
+        }
+      seedOff[r] = base + lo;
+    }
+}
+
+static unsigned rgrid(uint64_t n)
+{
+  uint64_t blocks = (n + 255) / 256;
+  uint64_t maxBlocks = (uint64_t)mg_num_sms() * 16;
+  if (blocks > maxBlocks) blocks = maxBlocks;
+  if (!blocks) blocks = 1;
+  return (unsigned)blocks;
+}
+
+// ------------------------------------------------------------------- build
+static void plan(const uint64_t *offs, uint64_t nSeq, uint64_t limit, std::vector<uint64_t> &cuts)
+{
+  cuts.clear(); cuts.push_back(0);
+  uint64_t r = 0;
+  while (r < nSeq)
+    { uint64_t r1 = r + 1;
+      while (r1 < nSeq && offs[r1 + 1] - offs[r] <= limit) ++r1;
+      cuts.push_back(r1); r = r1;
+    }
+}
+
+static int stage(ModgpuReference *R, const char *bases, const uint64_t *offs, uint64_t r0, uint64_t r1, cudaStream_t st)
+{
+  const uint64_t nb = offs[r1] - offs[r0], ns = r1 - r0;
+  int rc;
+  if ((rc = R->bases.ensure(nb + 64, st)) || (rc = R->offs.ensure((ns + 1) * 8, st))) return rc;
+  std::vector<uint64_t> local(ns + 1);
+  for (uint64_t r = 0; r <= ns; ++r) local[r] = offs[r0 + r] - offs[r0];
+  if (nb) MG_CUDA(cudaMemcpyAsync(R->bases.p, bases + offs[r0], nb, cudaMemcpyHostToDevice, st));
+  MG_CUDA(cudaMemcpyAsync(R->offs.p, local.data(), (ns + 1) * 8, cudaMemcpyHostToDevice, st));
+  MG_CUDA(cudaStreamSynchronize(st));              // `local` dies with this scope
+  return MODGPU_OK;
+}
+
+extern "C" void modgpuReferenceDestroy(ModgpuReference *R)
+{
+  if (!R) return;
+  RBuf *all[] = { &R->index, &R->offset, &R->id, &R->depth, &R->loc, &R->rev, &R->tmp, &R->tmp2, &R->sortTmp,
+                  &R->slot, &R->bases, &R->offs, &R->misc };
+  for (RBuf *b : all) b->release();
+  if (R->hPinned) cudaFreeHost(R->hPinned);
+  if (R->ms) modgpuModsetDestroy(R->ms);
+  delete R;
+}
+
+extern "C" ModgpuReference *modgpuReferenceBuild(int bits, int k, int w, int seed, const char *bases,
+                                                 const uint64_t *offs, uint64_t nSeq, int isAscii, uint32_t counts[4])
+{
+  ModgpuModset *ms = modgpuModsetCreate(bits, k, w, seed);
+  if (!ms) return nullptr;
+  ModgpuReference *R = new ModgpuReference();
+  R->ms = ms;
+  modgpuModsetSetExactOrder(ms, 1);                  // first-occurrence numbering, ordered selection
+  cudaStream_t st = mg_modset_stream(ms);
+  ModgpuTable *t = modgpuModsetTable(ms);
+#define RB_FAIL() do { modgpuReferenceDestroy(R); return nullptr; } while (0)
+  if (mg_check_cuda(cudaMallocHost(&R->hPinned, 256), "cudaMallocHost", __FILE__, __LINE__)) RB_FAIL();
+  if (!offs || offs[0] != 0) { mg_set_error("offsets must start at 0"); RB_FAIL(); }
+  for (uint64_t r = 0; r < nSeq; ++r)
+    if (offs[r + 1] < offs[r] || offs[r + 1] - offs[r] > 0x7FFFFFFFull)
+      { mg_set_error("bad length of reference sequence %llu", (unsigned long long)r); RB_FAIL(); }
+
+  std::vector<uint64_t> cuts;
+  plan(offs, nSeq, MG_REF_CHUNK, cuts);
+  uint64_t nHits = 0;
+  for (size_t c = 0; c + 1 < cuts.size(); ++c)
+    { const uint64_t r0 = cuts[c], r1 = cuts[c + 1], nb = offs[r1] - offs[r0], ns = r1 - r0;
+      if (nb >= (1ull << 32)) { mg_set_error("reference sequence group exceeds 2^32-1 bases"); RB_FAIL(); }
+      if (stage(R, bases, offs, r0, r1, st)) RB_FAIL();
+      uint64_t n = 0;
+      if (mg_modset_select_chunk(ms, (const uint8_t *)R->bases.p, (const uint64_t *)R->offs.p, ns, nb, isAscii, true,
+                                 MODGPU_SEL_ORDERED, &n))
+        RB_FAIL();
+      if (!n) continue;
+      if (nHits + n + 1 >= MG_REF_CAP)               // modmap.c:111: die ("reference size overflow")
+        { mg_set_error("reference size overflow (%llu hits, capacity 2^26)", (unsigned long long)(nHits + n)); RB_FAIL(); }
+      if (R->slot.ensure(n * 4, st) || R->index.ensure((nHits + n) * 4, st, true) ||
+          R->offset.ensure((nHits + n) * 4, st, true) || R->id.ensure((nHits + n) * 4, st, true))
+        RB_FAIL();
+      uint32_t *dIndex = (uint32_t *)R->index.p + nHits, *dOffset = (uint32_t *)R->offset.p + nHits, *dId = (uint32_t *)R->id.p + nHits;
+      // find-or-insert with the multiplicity in the slot count (++ref->depth[index], modmap.c:113)
+      if (mg_table_insert_dev(t, (const uint64_t *)mg_modset_kmers(ms), nullptr, n, (uint32_t *)R->slot.p, 1, st)) RB_FAIL();
+      if (modgpuTableNumber(t, (const uint32_t *)R->slot.p, n, dIndex, st)) RB_FAIL();
+      if (modgpuLocate((const uint32_t *)mg_modset_gpos(ms), n, (const uint64_t *)R->offs.p, ns, dId, dOffset, st)) RB_FAIL();
+      if (r0)
+        { add_const_kernel<<<rgrid(n), 256, 0, st>>>(dId, n, (uint32_t)r0);
+          if (mg_check_cuda(cudaGetLastError(), "add_const", __FILE__, __LINE__)) RB_FAIL();
+        }
+      nHits += n;
+    }
+  if (modgpuTableEntries(t, st) == 0xFFFFFFFFFFFFFFFFull) RB_FAIL();
+  R->max = (uint32_t)nHits;
+  mg_modset_mark(ms, false, true);                   // numbered; ms->depth stays 0 in modmap
+
+  // classes by exact multiplicity (modmap.c:125-129)
+  uint32_t cls[4] = { 0, 0, 0, 0 };
+  if (mg_modset_classify(ms, 2, 0, 0, 0, cls)) RB_FAIL();
+  if (counts) { counts[0] = R->max; counts[1] = cls[1]; counts[2] = cls[2]; counts[3] = cls[3]; }
+
+  // referencePack (modmap.c:74-91)
+  const uint64_t m = mg_table_numbered(t) + 1;
+  if (R->depth.ensure(m * 4, st) || R->loc.ensure(m * 4, st) || R->rev.ensure((nHits + 1) * 4, st) ||
+      R->misc.ensure(((m + MG_CP_CHUNK - 1) / MG_CP_CHUNK + 16) * 4 + 64, st))
+    RB_FAIL();
+  if (mg_check_cuda(cudaMemsetAsync(R->depth.p, 0, 4, st), "memset", __FILE__, __LINE__)) RB_FAIL();
+  if (modgpuTableExport(t, nullptr, nullptr, nullptr, (uint32_t *)R->depth.p + 1, st)) RB_FAIL();
+  { LocScan f; f.depth = (const uint32_t *)R->depth.p; f.loc = (uint32_t *)R->loc.p;
+    unsigned long long *dTotal = (unsigned long long *)R->misc.p;
+    if (mg_ordered_scan(f, m, (uint32_t *)((char *)R->misc.p + 64), dTotal, st)) RB_FAIL();
+  }
+  if (nHits)
+    { // stable sort of hit ordinals by modset index == the counting sort of modmap.c:88-90
+      if (R->tmp.ensure(nHits * 4, st) || R->tmp2.ensure(nHits * 4, st)) RB_FAIL();
+      iota_kernel<<<rgrid(nHits), 256, 0, st>>>((uint32_t *)R->tmp.p, nHits);
+      if (mg_check_cuda(cudaGetLastError(), "iota", __FILE__, __LINE__)) RB_FAIL();
+      int endBit = 1;
+      while (endBit < 32 && (m >> endBit)) ++endBit;
+      size_t tmpBytes = 0;
+      if (mg_check_cuda(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, (const uint32_t *)R->index.p, (uint32_t *)R->tmp2.p,
+                                                        (const uint32_t *)R->tmp.p, (uint32_t *)R->rev.p, (uint64_t)nHits, 0, endBit, st),
+                        "cub sort size", __FILE__, __LINE__))
+        RB_FAIL();
+      if (R->sortTmp.ensure(tmpBytes + 16, st)) RB_FAIL();
+      if (mg_check_cuda(cub::DeviceRadixSort::SortPairs(R->sortTmp.p, tmpBytes, (const uint32_t *)R->index.p, (uint32_t *)R->tmp2.p,
+                                                        (const uint32_t *)R->tmp.p, (uint32_t *)R->rev.p, (uint64_t)nHits, 0, endBit, st),
+                        "cub sort", __FILE__, __LINE__))
+        RB_FAIL();
+    }
+  if (mg_check_cuda(cudaStreamSynchronize(st), "sync", __FILE__, __LINE__)) RB_FAIL();
+  R->bases.release(); R->tmp.release(); R->tmp2.release(); R->sortTmp.release(); R->slot.release();
+#undef RB_FAIL
+  return R;
+}
+
+extern "C" ModgpuModset *modgpuReferenceModset(ModgpuReference *R) { return R->ms; }
+extern "C" uint32_t modgpuReferenceMax(ModgpuReference *R) { return R->max; }
+
+extern "C" int modgpuReferenceExport(ModgpuReference *R, uint32_t *index, uint32_t *offset, uint32_t *id,
+                                     uint32_t *depth, uint32_t *rev, uint32_t *loc)
+{
+  cudaStream_t st = mg_modset_stream(R->ms);
+  const uint64_t n = R->max, m = mg_table_numbered(modgpuModsetTable(R->ms)) + 1;
+  if (n)
+    { if (index) MG_CUDA(cudaMemcpyAsync(index, R->index.p, n * 4, cudaMemcpyDeviceToHost, st));
+      if (offset) MG_CUDA(cudaMemcpyAsync(offset, R->offset.p, n * 4, cudaMemcpyDeviceToHost, st));
+      if (id) MG_CUDA(cudaMemcpyAsync(id, R->id.p, n * 4, cudaMemcpyDeviceToHost, st));
+      if (rev) MG_CUDA(cudaMemcpyAsync(rev, R->rev.p, n * 4, cudaMemcpyDeviceToHost, st));
+    }
+  if (depth) MG_CUDA(cudaMemcpyAsync(depth, R->depth.p, m * 4, cudaMemcpyDeviceToHost, st));
+  if (loc) MG_CUDA(cudaMemcpyAsync(loc, R->loc.p, m * 4, cudaMemcpyDeviceToHost, st));
+  MG_CUDA(cudaStreamSynchronize(st));
+  return MODGPU_OK;
+}
+
+// ------------------------------------------------------------------- query
+extern "C" uint64_t modgpuReferenceQuery(ModgpuReference *R, const char *bases, const uint64_t *offs,
+                                         uint64_t nSeq, int isAscii, uint64_t *seedOff,
+                                         uint32_t *seedIndex, uint32_t *seedPos,
+                                         uint32_t *hitId, uint32_t *hitOffset,
+                                         int32_t *counters, uint64_t cap)
+{
+  const uint64_t FAIL = 0xFFFFFFFFFFFFFFFFull;
+  ModgpuModset *ms = R->ms;
+  cudaStream_t st = mg_modset_stream(ms);
+  ModgpuTable *t = modgpuModsetTable(ms);
+  if (!offs || offs[0] != 0) { mg_set_error("offsets must start at 0"); return FAIL; }
+  for (uint64_t r = 0; r < nSeq; ++r)
+    if (offs[r + 1] < offs[r] || offs[r + 1] - offs[r] > 0x7FFFFFFFull)
+      { mg_set_error("bad length of query sequence %llu", (unsigned long long)r); return FAIL; }
+  std::vector<uint64_t> cuts;
+  plan(offs, nSeq, 1ull << 30, cuts);
+  uint64_t total = 0;
+  seedOff[0] = 0;
+  for (size_t c = 0; c + 1 < cuts.size(); ++c)
+    { const uint64_t r0 = cuts[c], r1 = cuts[c + 1], nb = offs[r1] - offs[r0], ns = r1 - r0;
+      if (nb >= (1ull << 32)) { mg_set_error("query sequence group exceeds 2^32-1 bases"); return FAIL; }
+      if (stage(R, bases, offs, r0, r1, st)) return FAIL;
+      uint64_t n = 0;
+      if (mg_modset_select_chunk(ms, (const uint8_t *)R->bases.p, (const uint64_t *)R->offs.p, ns, nb, isAscii, true,
+                                 MODGPU_SEL_ORDERED, &n))
+        return FAIL;
+      // device scratch: aux, readId, pos, seedIndex, hitId[2], hitOffset[2] per seed; counters, seedOff per read
+      const size_t perSeed = 4 * 8, need = n * perSeed + (ns + 1) * (16 + 8) + 256;
+      if (R->tmp.ensure(need, st)) return FAIL;
+      uint32_t *dAux = (uint32_t *)R->tmp.p, *dRead = dAux + n, *dPos = dRead + n, *dIdx = dPos + n;
+      uint32_t *dHitId = dIdx + n, *dHitOff = dHitId + 2 * n;
+      uint64_t *dSeedOff = (uint64_t *)(((uintptr_t)(dHitOff + 2 * n) + 15) & ~(uintptr_t)15);
+      int32_t *dCtr = (int32_t *)(dSeedOff + ns + 1);
+      if (mg_check_cuda(cudaMemsetAsync(dCtr, 0, ns * 16, st), "memset", __FILE__, __LINE__)) return FAIL;
+      if (n)
+        { if (mg_table_lookup_dev(t, (const uint64_t *)mg_modset_kmers(ms), nullptr, n, dAux, st)) return FAIL;
+          if (modgpuLocate((const uint32_t *)mg_modset_gpos(ms), n, (const uint64_t *)R->offs.p, ns, dRead, dPos, st)) return FAIL;
+          query_resolve_kernel<<<rgrid(n), 256, 0, st>>>(dAux, n, dRead, (const uint32_t *)R->loc.p, (const uint32_t *)R->rev.p,
+                                                         (const uint32_t *)R->id.p, (const uint32_t *)R->offset.p, dIdx, dHitId, dHitOff, dCtr);
+          if (mg_check_cuda(cudaGetLastError(), "query_resolve", __FILE__, __LINE__)) return FAIL;
+        }
+      seed_offsets_kernel<<<rgrid(ns + 1), 256, 0, st>>>(dRead, n, ns, total, dSeedOff);
+      if (mg_check_cuda(cudaGetLastError(), "seed_offsets", __FILE__, __LINE__)) return FAIL;
+      // results back to the caller (clipped to cap)
+      uint64_t room = total < cap ? cap - total : 0, take = n < room ? n : room;
+      if (take)
+        { if (mg_check_cuda(cudaMemcpyAsync(seedIndex + total, dIdx, take * 4, cudaMemcpyDeviceToHost, st), "d2h", __FILE__, __LINE__) ||
+              mg_check_cuda(cudaMemcpyAsync(seedPos + total, dPos, take * 4, cudaMemcpyDeviceToHost, st), "d2h", __FILE__, __LINE__) ||
+              mg_check_cuda(cudaMemcpyAsync(hitId + 2 * total, dHitId, take * 8, cudaMemcpyDeviceToHost, st), "d2h", __FILE__, __LINE__) ||
+              mg_check_cuda(cudaMemcpyAsync(hitOffset + 2 * total, dHitOff, take * 8, cudaMemcpyDeviceToHost, st), "d2h", __FILE__, __LINE__))
+            return FAIL;
+        }
+      if (mg_check_cuda(cudaMemcpyAsync(seedOff + r0, dSeedOff, (ns + 1) * 8, cudaMemcpyDeviceToHost, st), "d2h", __FILE__, __LINE__) ||
+          mg_check_cuda(cudaMemcpyAsync(counters + 4 * r0, dCtr, ns * 16, cudaMemcpyDeviceToHost, st), "d2h", __FILE__, __LINE__) ||
+          mg_check_cuda(cudaStreamSynchronize(st), "sync", __FILE__, __LINE__))
+        return FAIL;
+      total += n;
+    }
+  return total;
+}

@@ -1,0 +1,432 @@
+// table.cu - K3..K6: the modset as an open-addressing table in HBM.
+//
+// replaces: Modset / modsetCreate / modsetIndexFind (reference modset.h:17-28,
+// modset.c:15-62), the saturating ++depth of addSequence (modutils.c:26),
+// depthHistogram (modutils.c:53-63), the -s / -sM classification
+// (modutils.c:205-219), modmap's multiplicity classes (modmap.c:125-129) and
+// the dense arrays modsetPack leaves behind (modset.c:36-43).
+//
+// Layout: 2^(bits-1) slots of 16 bytes {kmer u64, count u32, aux u32}; two
+// slots per 32-byte sector so find-or-insert + count touches ONE sector.
+// Insert = read key, atomicCAS on EMPTY, RED.ADD on the count (+ RED.MIN of the
+// input ordinal when the reference's first-occurrence numbering is wanted).
+// Bound by random-sector L2/HBM atomic throughput, not by streaming bandwidth:
+// 20 algorithmic bytes per selected k-mer.
+#include "mg_device.cuh"
+#include "mg_scan.cuh"
+
+struct ModgpuTable {
+  MgSlot *slots;
+  int bits;                  // reference tableBits
+  uint32_t slotBits;         // bits - 1
+  uint64_t nSlots;
+  uint64_t maxEntries;       // reference: max must stay < size = 2^(bits-2) - 1   (modset.c:24-26,58)
+  unsigned long long *dEntries;   // device: distinct entries
+  uint32_t *dError;          // device: probe overflow flag
+  uint32_t *dScratch;        // block counts for the ordered compactions
+  uint64_t scratchWords;
+  uint64_t numbered;         // host: highest dense index handed out
+  unsigned long long *hPinned;    // pinned readback word(s)
+};
+
+// ------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(256) table_clear_kernel(MgSlot *slots, uint64_t nSlots)
+{
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint4 e;
+  e.x = 0xFFFFFFFFu; e.y = 0xFFFFFFFFu; e.z = 0u; e.w = MG_AUX_FRESH;
+  uint4 *p = reinterpret_cast<uint4 *>(slots);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nSlots; i += stride) p[i] = e;
+}
+
+// find-or-insert; returns the slot or UINT64_MAX when the table is full
+__device__ __forceinline__ uint64_t probe_insert(MgSlot *slots, uint32_t slotBits, uint64_t key, bool *isNew)
+{
+  const uint64_t maskS = (1ull << slotBits) - 1;
+  uint64_t s = mg_slot_hash(key, slotBits);
+  *isNew = false;
+  for (uint64_t probes = 0; probes <= maskS; ++probes, s = (s + 1) & maskS)
+    { unsigned long long *kp = reinterpret_cast<unsigned long long *>(&slots[s].key);
+      unsigned long long cur = __ldcg(kp);
+      if (cur == key) return s;
+      if (cur == MG_EMPTY)
+        { unsigned long long old = atomicCAS(kp, MG_EMPTY, (unsigned long long)key);
+          if (old == MG_EMPTY) { *isNew = true; return s; }
+          if (old == key) return s;
+        }
+    }
+  return 0xFFFFFFFFFFFFFFFFull;
+}
+
+__device__ __forceinline__ uint64_t probe_find(const MgSlot *slots, uint32_t slotBits, uint64_t key)
+{
+  const uint64_t maskS = (1ull << slotBits) - 1;
+  uint64_t s = mg_slot_hash(key, slotBits);
+  for (uint64_t probes = 0; probes <= maskS; ++probes, s = (s + 1) & maskS)
+    { unsigned long long cur = __ldcg(reinterpret_cast<const unsigned long long *>(&slots[s].key));
+      if (cur == key) return s;
+      if (cur == MG_EMPTY) break;
+    }
+  return 0xFFFFFFFFFFFFFFFFull;
+}
+
+// n is read from device memory (the count hash_select just produced) so that no
+// host round trip sits between select and insert; nHost bounds it (the cap).
+template <bool EXACT>
+__global__ void __launch_bounds__(256) table_insert_kernel(MgSlot *slots, uint32_t slotBits,
+                                                           const uint64_t *__restrict__ kmers,
+                                                           const unsigned long long *__restrict__ nDev, uint64_t nHost,
+                                                           uint32_t *__restrict__ slotOut,
+                                                           unsigned long long *entries, uint32_t *error)
+{
+  uint64_t n = nDev ? (uint64_t)*nDev : nHost;
+  if (n > nHost) n = nHost;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint32_t fresh = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    { uint64_t key = kmers[i] & 0x3FFFFFFFFFFFFFFFull;       // drop the optional strand bit
+      bool isNew;
+      uint64_t s = probe_insert(slots, slotBits, key, &isNew);
+      if (s == 0xFFFFFFFFFFFFFFFFull) { atomicExch(error, 1u); if (slotOut) slotOut[i] = 0xFFFFFFFFu; continue; }
+      fresh += isNew ? 1u : 0u;
+      atomicAdd(&slots[s].count, 1u);
+      if (EXACT) atomicMin(&slots[s].aux, MG_AUX_ORD + (uint32_t)i);
+      if (slotOut) slotOut[i] = (uint32_t)s;
+    }
+  fresh = mg_warp_sum(fresh);
+  if (mg_lane() == 0 && fresh) atomicAdd(entries, (unsigned long long)fresh);
+}
+
+__global__ void __launch_bounds__(256) table_lookup_kernel(const MgSlot *slots, uint32_t slotBits,
+                                                           const uint64_t *__restrict__ kmers,
+                                                           const unsigned long long *__restrict__ nDev, uint64_t nHost,
+                                                           uint32_t *__restrict__ out)
+{
+  uint64_t n = nDev ? (uint64_t)*nDev : nHost;
+  if (n > nHost) n = nHost;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    { uint64_t key = kmers[i] & 0x3FFFFFFFFFFFFFFFull;
+      uint64_t s = probe_find(slots, slotBits, key);
+      out[i] = (s == 0xFFFFFFFFFFFFFFFFull) ? 0u : __ldcg(&slots[s].aux);
+    }
+}
+
+// ---- numbering: rank the not-yet-numbered entries (mg_scan.cuh) ------------
+struct FlagNewSlot {         // entries inserted but not numbered yet, in slot order
+  MgSlot *slots;
+  uint64_t base;             // indices already handed out
+  __device__ uint32_t value(uint64_t i) const { return (slots[i].key != MG_EMPTY && slots[i].aux >= MG_AUX_ORD) ? 1u : 0u; }
+  __device__ void emit(uint64_t i, uint32_t rank, uint32_t v) const { if (v) slots[i].aux = (uint32_t)((base + rank + 1) << 2); }
+};
+
+struct FlagFirstOccurrence { // list elements that were the first occurrence of a new entry
+  MgSlot *slots;
+  const uint32_t *slotOf;
+  uint64_t base;
+  __device__ uint32_t value(uint64_t i) const
+  { uint32_t s = slotOf[i]; return (s != 0xFFFFFFFFu && slots[s].aux == MG_AUX_ORD + (uint32_t)i) ? 1u : 0u; }
+  __device__ void emit(uint64_t i, uint32_t rank, uint32_t v) const
+  { if (v) slots[slotOf[i]].aux = (uint32_t)((base + rank + 1) << 2); }
+};
+
+__global__ void __launch_bounds__(256) gather_index_kernel(const MgSlot *slots, const uint32_t *__restrict__ slotOf,
+                                                           uint64_t n, uint32_t *__restrict__ index)
+{
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    { uint32_t s = slotOf[i];
+      index[i] = (s == 0xFFFFFFFFu) ? 0u : (__ldcg(&slots[s].aux) >> 2);
+    }
+}
+
+// depth = count clamped to 65535: the reference's ++ saturates (modutils.c:26)
+__device__ __forceinline__ uint32_t clamp16(uint32_t c) { return c > 65535u ? 65535u : c; }
+
+#define MG_HIST_SMEM 4096
+__global__ void __launch_bounds__(256) table_hist_kernel(const MgSlot *slots, uint64_t nSlots, uint32_t *bins)
+{
+  __shared__ uint32_t sBins[MG_HIST_SMEM];
+  for (int i = threadIdx.x; i < MG_HIST_SMEM; i += 256) sBins[i] = 0;
+  __syncthreads();
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nSlots; i += stride)
+    { uint4 v = __ldcs(reinterpret_cast<const uint4 *>(slots) + i);
+      if ((v.x & v.y) == 0xFFFFFFFFu) continue;          // EMPTY key
+      uint32_t d = clamp16(v.z);
+      if (d < MG_HIST_SMEM) atomicAdd(&sBins[d], 1u); else atomicAdd(&bins[d], 1u);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < MG_HIST_SMEM; i += 256)
+    { uint32_t c = sBins[i]; if (c) atomicAdd(&bins[i], c); }
+}
+
+// mode 0: -s   depth<c1 -> 0, <c2 -> 1, <cM -> 2, else 3      (modutils.c:205-214)
+// mode 1: -sM  depth>=cM -> 3, others unchanged                (modutils.c:215-219)
+// mode 2: exact multiplicity 1 -> 1, 2 -> 2, else 3            (modmap.c:125-129)
+// mode 3: tally the current classes only                      (modsetSummary, modset.c:149-150)
+__global__ void __launch_bounds__(256) table_classify_kernel(MgSlot *slots, uint64_t nSlots, int mode,
+                                                             int c1, int c2, int cM, int zeroDepth, uint32_t *classCounts)
+{
+  uint32_t tally[4] = { 0, 0, 0, 0 };
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nSlots; i += stride)
+    { uint4 v = reinterpret_cast<const uint4 *>(slots)[i];
+      if ((v.x & v.y) == 0xFFFFFFFFu) continue;
+      if (v.w >= MG_AUX_ORD) continue;                   // not numbered: not part of the set yet
+      int d = zeroDepth ? 0 : (int)clamp16(v.z);            // modmap-built sets keep ms->depth at 0
+      uint32_t cls = v.w & 3u;
+      if (mode == 0) cls = d < c1 ? 0u : d < c2 ? 1u : d < cM ? 2u : 3u;
+      else if (mode == 1) { if (d >= cM) cls = 3u; }
+      else if (mode == 2) cls = (v.z == 1u) ? 1u : (v.z == 2u) ? 2u : 3u;
+      if (mode != 3) slots[i].aux = (v.w & ~3u) | cls;
+      ++tally[cls];
+    }
+  if (classCounts)
+    {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        { uint32_t t = mg_warp_sum(tally[c]);
+          if (mg_lane() == 0 && t) atomicAdd(&classCounts[c], t);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) table_export_kernel(const MgSlot *slots, uint64_t nSlots,
+                                                           uint64_t *value, uint16_t *depth, uint8_t *info, uint32_t *count32)
+{
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nSlots; i += stride)
+    { uint4 v = __ldcs(reinterpret_cast<const uint4 *>(slots) + i);
+      if ((v.x & v.y) == 0xFFFFFFFFu || v.w >= MG_AUX_ORD) continue;
+      uint32_t ix = (v.w >> 2) - 1;                      // reference indices are 1-based
+      if (value) value[ix] = ((uint64_t)v.y << 32) | v.x;
+      if (depth) depth[ix] = (uint16_t)clamp16(v.z);
+      if (info) info[ix] = (uint8_t)(v.w & 3u);
+      if (count32) count32[ix] = v.z;
+    }
+}
+
+__global__ void __launch_bounds__(256) table_import_kernel(MgSlot *slots, uint32_t slotBits,
+                                                           const uint64_t *__restrict__ value,
+                                                           const uint16_t *__restrict__ depth,
+                                                           const uint8_t *__restrict__ info, uint64_t n, uint64_t indexBase,
+                                                           unsigned long long *entries, uint32_t *error)
+{
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint32_t fresh = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    { bool isNew;
+      uint64_t s = probe_insert(slots, slotBits, value[i], &isNew);
+      if (s == 0xFFFFFFFFFFFFFFFFull || !isNew) { atomicExch(error, s == 0xFFFFFFFFFFFFFFFFull ? 1u : 2u); continue; }
+      ++fresh;
+      slots[s].count = depth ? (uint32_t)depth[i] : 0u;
+      slots[s].aux = (uint32_t)((indexBase + i + 1) << 2) | (info ? (info[i] & 3u) : 0u);
+    }
+  fresh = mg_warp_sum(fresh);
+  if (mg_lane() == 0 && fresh) atomicAdd(entries, (unsigned long long)fresh);
+}
+
+// ------------------------------------------------------------------- host
+static unsigned grid_for(uint64_t n, int perSm)
+{
+  uint64_t blocks = (n + 255) / 256;
+  uint64_t maxBlocks = (uint64_t)mg_num_sms() * perSm;
+  if (blocks > maxBlocks) blocks = maxBlocks;
+  if (!blocks) blocks = 1;
+  return (unsigned)blocks;
+}
+
+extern "C" ModgpuTable *modgpuTableCreate(int bits, void *stream)
+{
+  if (bits < 20 || bits > 34)                            // modset.c:17
+    { mg_set_error("table bits %d must be between 20 and 34", bits); return nullptr; }
+  ModgpuTable *t = new ModgpuTable();
+  t->bits = bits;
+  t->slotBits = (uint32_t)(bits - 1);
+  t->nSlots = 1ull << t->slotBits;
+  t->maxEntries = (1ull << (bits - 2)) - 2;              // reference dies when max >= size = 2^(bits-2)-1
+  if (t->maxEntries > MG_MAX_INDEX) t->maxEntries = MG_MAX_INDEX;
+  t->numbered = 0;
+  t->slots = nullptr; t->dEntries = nullptr; t->dError = nullptr; t->dScratch = nullptr; t->hPinned = nullptr;
+  t->scratchWords = t->nSlots / MG_CP_CHUNK + 1024;
+  if (mg_check_cuda(cudaMalloc(&t->slots, t->nSlots * sizeof(MgSlot)), "cudaMalloc(table)", __FILE__, __LINE__) ||
+      mg_check_cuda(cudaMalloc(&t->dEntries, 64), "cudaMalloc", __FILE__, __LINE__) ||
+      mg_check_cuda(cudaMalloc(&t->dScratch, t->scratchWords * sizeof(uint32_t)), "cudaMalloc", __FILE__, __LINE__) ||
+      mg_check_cuda(cudaMallocHost(&t->hPinned, 64), "cudaMallocHost", __FILE__, __LINE__))
+    { modgpuTableDestroy(t); return nullptr; }
+  t->dError = reinterpret_cast<uint32_t *>(t->dEntries + 1);
+  if (modgpuTableClear(t, stream)) { modgpuTableDestroy(t); return nullptr; }
+  return t;
+}
+
+extern "C" void modgpuTableDestroy(ModgpuTable *t)
+{
+  if (!t) return;
+  if (t->slots) cudaFree(t->slots);
+  if (t->dEntries) cudaFree(t->dEntries);
+  if (t->dScratch) cudaFree(t->dScratch);
+  if (t->hPinned) cudaFreeHost(t->hPinned);
+  delete t;
+}
+
+extern "C" int modgpuTableClear(ModgpuTable *t, void *stream)
+{
+  cudaStream_t st = (cudaStream_t)stream;
+  table_clear_kernel<<<grid_for(t->nSlots, 16), 256, 0, st>>>(t->slots, t->nSlots);
+  MG_LAUNCH_CHECK("table_clear");
+  MG_CUDA(cudaMemsetAsync(t->dEntries, 0, 64, st));
+  t->numbered = 0;
+  return MODGPU_OK;
+}
+
+extern "C" uint64_t modgpuTableSlots(const ModgpuTable *t) { return t->nSlots; }
+extern "C" void *modgpuTableDevicePtr(const ModgpuTable *t) { return t->slots; }
+
+// internal: insert with the element count taken from device memory
+int mg_table_insert_dev(ModgpuTable *t, const uint64_t *d_kmers, const uint64_t *d_n, uint64_t nMax,
+                        uint32_t *d_slot, int exactOrder, cudaStream_t st)
+{
+  if (!nMax) return MODGPU_OK;
+  if (exactOrder && nMax >= (1ull << 30) - 2)
+    { mg_set_error("exact-order insert batch of %llu exceeds 2^30", (unsigned long long)nMax); return MODGPU_EINVAL; }
+  unsigned grid = grid_for(nMax, 16);
+  if (exactOrder)
+    table_insert_kernel<true><<<grid, 256, 0, st>>>(t->slots, t->slotBits, d_kmers, (const unsigned long long *)d_n, nMax, d_slot, t->dEntries, t->dError);
+  else
+    table_insert_kernel<false><<<grid, 256, 0, st>>>(t->slots, t->slotBits, d_kmers, (const unsigned long long *)d_n, nMax, d_slot, t->dEntries, t->dError);
+  MG_LAUNCH_CHECK("table_insert");
+  return MODGPU_OK;
+}
+
+extern "C" int modgpuTableInsert(ModgpuTable *t, const uint64_t *d_kmers, uint64_t n, uint32_t *d_slot,
+                                 int exactOrder, void *stream)
+{
+  return mg_table_insert_dev(t, d_kmers, nullptr, n, d_slot, exactOrder, (cudaStream_t)stream);
+}
+
+extern "C" uint64_t modgpuTableEntries(ModgpuTable *t, void *stream)
+{
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mg_check_cuda(cudaMemcpyAsync(t->hPinned, t->dEntries, 16, cudaMemcpyDeviceToHost, st), "entries readback", __FILE__, __LINE__) ||
+      mg_check_cuda(cudaStreamSynchronize(st), "cudaStreamSynchronize", __FILE__, __LINE__))
+    return 0xFFFFFFFFFFFFFFFFull;
+  uint64_t entries = t->hPinned[0];
+  uint32_t err = (uint32_t)(t->hPinned[1] & 0xFFFFFFFFu);
+  if (err || entries > t->maxEntries)
+    { // reference: die("hashTableSize %u is too small for %u"), modset.c:58
+      mg_set_error("hashTableSize %llu is too small for %llu (table bits %d)%s",
+                   (unsigned long long)(t->maxEntries + 1), (unsigned long long)entries, t->bits,
+                   err == 2 ? " [duplicate key on import]" : "");
+      return 0xFFFFFFFFFFFFFFFFull;
+    }
+  return entries;
+}
+
+template <class F>
+static int run_compaction(ModgpuTable *t, F f, uint64_t n, uint64_t *totalOut, cudaStream_t st)
+{
+  uint64_t chunks = (n + MG_CP_CHUNK - 1) / MG_CP_CHUNK;
+  if (chunks > t->scratchWords)
+    { if (t->dScratch) cudaFree(t->dScratch);
+      t->dScratch = nullptr;
+      t->scratchWords = chunks + 1024;
+      MG_CUDA(cudaMalloc(&t->dScratch, t->scratchWords * sizeof(uint32_t)));
+    }
+  unsigned long long *dTotal = t->dEntries + 2;
+  int rc = mg_ordered_scan(f, n, t->dScratch, dTotal, st);
+  if (rc) return rc;
+  MG_CUDA(cudaMemcpyAsync(t->hPinned + 2, dTotal, 8, cudaMemcpyDeviceToHost, st));
+  MG_CUDA(cudaStreamSynchronize(st));
+  *totalOut = t->hPinned[2];
+  return MODGPU_OK;
+}
+
+extern "C" int modgpuTableNumber(ModgpuTable *t, const uint32_t *d_slot, uint64_t n, uint32_t *d_index, void *stream)
+{
+  cudaStream_t st = (cudaStream_t)stream;
+  uint64_t added = 0;
+  if (d_slot)
+    { if (n)
+        { FlagFirstOccurrence f; f.slots = t->slots; f.slotOf = d_slot; f.base = t->numbered;
+          int rc = run_compaction(t, f, n, &added, st);
+          if (rc) return rc;
+        }
+    }
+  else
+    { FlagNewSlot f; f.slots = t->slots; f.base = t->numbered;
+      int rc = run_compaction(t, f, t->nSlots, &added, st);
+      if (rc) return rc;
+    }
+  t->numbered += added;
+  if (t->numbered > t->maxEntries)
+    { mg_set_error("hashTableSize %llu is too small for %llu (table bits %d)",
+                   (unsigned long long)(t->maxEntries + 1), (unsigned long long)t->numbered, t->bits);
+      return MODGPU_EFULL;
+    }
+  if (d_slot && d_index && n)
+    { gather_index_kernel<<<grid_for(n, 16), 256, 0, st>>>(t->slots, d_slot, n, d_index);
+      MG_LAUNCH_CHECK("gather_index");
+    }
+  return MODGPU_OK;
+}
+
+uint64_t mg_table_numbered(const ModgpuTable *t) { return t->numbered; }
+
+int mg_table_lookup_dev(const ModgpuTable *t, const uint64_t *d_kmers, const uint64_t *d_n, uint64_t nMax,
+                        uint32_t *d_out, cudaStream_t st)
+{
+  if (!nMax) return MODGPU_OK;
+  table_lookup_kernel<<<grid_for(nMax, 16), 256, 0, st>>>(t->slots, t->slotBits, d_kmers, (const unsigned long long *)d_n, nMax, d_out);
+  MG_LAUNCH_CHECK("table_lookup");
+  return MODGPU_OK;
+}
+
+extern "C" int modgpuTableLookup(const ModgpuTable *t, const uint64_t *d_kmers, uint64_t n, uint32_t *d_out, void *stream)
+{
+  return mg_table_lookup_dev(t, d_kmers, nullptr, n, d_out, (cudaStream_t)stream);
+}
+
+extern "C" int modgpuTableHistogram(const ModgpuTable *t, uint32_t *d_bins65536, void *stream)
+{
+  cudaStream_t st = (cudaStream_t)stream;
+  MG_CUDA(cudaMemsetAsync(d_bins65536, 0, 65536 * sizeof(uint32_t), st));
+  table_hist_kernel<<<grid_for(t->nSlots, 8), 256, 0, st>>>(t->slots, t->nSlots, d_bins65536);
+  MG_LAUNCH_CHECK("table_hist");
+  return MODGPU_OK;
+}
+
+// mode: 0 thresholds (-s), 1 copyM only (-sM), 2 exact multiplicity (modmap), 3 tally only
+int mg_table_classify(ModgpuTable *t, int mode, int c1, int c2, int cM, int zeroDepth, uint32_t *d_classCounts, cudaStream_t st)
+{
+  if (d_classCounts) MG_CUDA(cudaMemsetAsync(d_classCounts, 0, 4 * sizeof(uint32_t), st));
+  table_classify_kernel<<<grid_for(t->nSlots, 8), 256, 0, st>>>(t->slots, t->nSlots, mode, c1, c2, cM, zeroDepth, d_classCounts);
+  MG_LAUNCH_CHECK("table_classify");
+  return MODGPU_OK;
+}
+
+extern "C" int modgpuTableClassify(ModgpuTable *t, int c1, int c2, int cM, int exact, uint32_t *d_classCounts, void *stream)
+{
+  int mode = exact ? 2 : (c1 < 0 && c2 < 0) ? 1 : 0;
+  return mg_table_classify(t, mode, c1, c2, cM, 0, d_classCounts, (cudaStream_t)stream);
+}
+
+extern "C" int modgpuTableExport(ModgpuTable *t, uint64_t *d_value, uint16_t *d_depth, uint8_t *d_info,
+                                 uint32_t *d_count32, void *stream)
+{
+  table_export_kernel<<<grid_for(t->nSlots, 8), 256, 0, (cudaStream_t)stream>>>(t->slots, t->nSlots, d_value, d_depth, d_info, d_count32);
+  MG_LAUNCH_CHECK("table_export");
+  return MODGPU_OK;
+}
+
+extern "C" int modgpuTableImport(ModgpuTable *t, const uint64_t *d_value, const uint16_t *d_depth,
+                                 const uint8_t *d_info, uint64_t n, void *stream)
+{
+  if (!n) return MODGPU_OK;
+  if (t->numbered + n > t->maxEntries)
+    { mg_set_error("Modset size %llu is too big for %d bits", (unsigned long long)(t->numbered + n), t->bits); return MODGPU_EFULL; }
+  table_import_kernel<<<grid_for(n, 16), 256, 0, (cudaStream_t)stream>>>(t->slots, t->slotBits, d_value, d_depth, d_info, n, t->numbered, t->dEntries, t->dError);
+  MG_LAUNCH_CHECK("table_import");
+  t->numbered += n;
+  return MODGPU_OK;
+}

@@ -1,0 +1,105 @@
+// host_emul.cpp - TEST INFRASTRUCTURE: drives the __host__ __device__ arithmetic
+// of modimizer_b200/csrc/mg_common.cuh on the CPU, run by run, exactly as the
+// kernels pack.cu / hash_select.cu do per thread, so that the per-base math is
+// checked against the oracle on boxes without a GPU (tests/test_math_host.py).
+// It is compiled only by the test suite and is not part of libmodgpu.
+#include <stdint.h>
+#include <string.h>
+#include <vector>
+#include "../../modimizer_b200/csrc/mg_common.cuh"
+
+extern "C" {
+
+void hm_khasher(int k, int d, uint64_t factor1, uint64_t out[8])
+{
+  MgKHasher H = mg_make_khasher(k, d, factor1);
+  out[0] = H.mask; out[1] = H.shift; out[2] = H.tz; out[3] = H.oddInv; out[4] = H.oddLim;
+  out[5] = H.prefilter; out[6] = H.pfMul; out[7] = H.pfLim;
+}
+
+int hm_divisible(int d, uint64_t hash)
+{
+  MgKHasher H = mg_make_khasher(19, d, 1);
+  return mg_divisible(H, hash) ? 1 : 0;
+}
+
+// K1: same word layout and SWAR path as pack2bit_kernel
+void hm_pack(const uint8_t *bytes, uint64_t nBases, int ascii, uint64_t *words, uint64_t nWords)
+{
+  for (uint64_t w = 0; w < nWords; ++w)
+    { uint64_t b0 = w * 32, word = 0;
+      if (b0 + 32 <= nBases)
+        { uint32_t v[8];
+          memcpy(v, bytes + b0, 32);
+          word = mg_pack32(v, ascii != 0);
+        }
+      else if (b0 < nBases)
+        for (uint64_t j = 0; b0 + j < nBases; ++j) word |= (uint64_t)mg_code_of(bytes[b0 + j], ascii != 0) << (62 - 2 * j);
+      words[w] = word;
+    }
+}
+
+// K2 per-thread logic over every run; usePrefilter: -1 = as the kernel decides
+int64_t hm_select(int k, int d, uint64_t factor1, const uint8_t *bytes, uint64_t nBases, int ascii,
+                  const uint64_t *offs, uint64_t nSeq, int usePrefilter,
+                  uint64_t *kmer, uint32_t *gpos, uint8_t *isF, int64_t cap)
+{
+  MgKHasher H = mg_make_khasher(k, d, factor1);
+  bool pf = usePrefilter < 0 ? (H.prefilter != 0) : (usePrefilter != 0 && H.prefilter);
+  uint64_t nWords = (nBases + 31) / 32 + 2;
+  std::vector<uint64_t> words(nWords, 0);
+  std::vector<uint32_t> ends(nWords + 1, 0);
+  hm_pack(bytes, nBases, ascii, words.data(), nWords);
+  for (uint64_t r = 0; r < nSeq; ++r)
+    if (offs[r + 1] > offs[r]) { uint64_t g = offs[r + 1] - 1; ends[g >> 5] |= 1u << (g & 31); }
+  int64_t n = 0;
+  for (uint64_t T = 0; T * 32 < nBases; ++T)
+    { uint64_t eflags = (uint64_t)ends[T] | ((uint64_t)ends[T + 1] << 32);
+      uint64_t p0 = T * 32;
+      uint32_t usable = mg_run_usable(eflags, H.k, p0, nBases);
+      MgRun R = mg_run_prepare(words[T], words[T + 1], H.k);
+      uint32_t sel = 0;
+      if (pf)
+        { uint32_t cand = 0;
+          for (uint32_t i = 0; i < 32; ++i) cand |= (mg_prefilter_candidate(H, R, i) ? 1u : 0u) << i;
+          cand &= usable;
+          for (uint32_t i = 0; i < 32; ++i)
+            if (cand >> i & 1) { uint64_t km; bool f; if (mg_eval_window(H, R, i, &km, &f)) sel |= 1u << i; }
+        }
+      else
+        { for (uint32_t i = 0; i < 32; ++i) { uint64_t km; bool f; if (mg_eval_window(H, R, i, &km, &f)) sel |= 1u << i; }
+          sel &= usable;
+        }
+      for (uint32_t i = 0; i < 32; ++i)
+        if (sel >> i & 1)
+          { uint64_t km; bool f;
+            mg_eval_window(H, R, i, &km, &f);
+            if (n < cap) { kmer[n] = km; gpos[n] = (uint32_t)(p0 + i); isF[n] = f ? 1 : 0; }
+            ++n;
+          }
+    }
+  return n;
+}
+
+uint64_t hm_slot_hash(uint64_t kmer, uint32_t bits) { return mg_slot_hash(kmer, bits); }
+uint32_t hm_owner(uint64_t kmer, uint32_t n) { return mg_owner(kmer, n); }
+
+}  // extern "C"
+
+// ---- synthetic inputs on the host: the same header the device generators use
+#include "../../include/modgpu_synth.h"
+extern "C" {
+void hs_genome(uint64_t seed, uint64_t start, uint64_t n, int dupMode, uint8_t *out)
+{ for (uint64_t i = 0; i < n; ++i) out[i] = mg_genome_base(seed, start + i, dupMode); }
+
+void hs_reads(const MgReadSpec *sp, uint64_t firstRead, uint64_t nReads, int ont, uint8_t *out)
+{
+  for (uint64_t rr = 0; rr < nReads; ++rr)
+    { uint64_t r = firstRead + rr;
+      if (ont) { mg_ont_read(sp, r, out + rr * sp->readLen); continue; }
+      uint64_t start; int rev;
+      mg_read_layout(sp, r, &start, &rev);
+      for (uint32_t j = 0; j < sp->readLen; ++j) out[rr * sp->readLen + j] = mg_read_base(sp, r, j, start, rev);
+    }
+}
+}

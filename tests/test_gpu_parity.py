@@ -1,0 +1,370 @@
+"""GPU parity tests: the CUDA path through the C ABI (libmodgpu.so) against the
+oracle (oracle/liboracle.so) on the same seeded inputs.  Bit-exact everywhere:
+the path is integer/byte work, there is no tolerance.
+
+Run on the B200 box:  python -m pytest tests -m gpu -x -q
+"""
+import numpy as np
+import pytest
+
+import harness as H
+import hostemul as he
+
+pytestmark = pytest.mark.gpu
+
+KAT_SEQ = ("ACGTTGCATGCCGATAGCTAGCTAGGATCGATCGTACGATCGTAGCTAGCTAGCTGATCGATGCATGCATCGATCGTAGCTAGCTAGCTAGCATCGATGCATGCAAATTTGGGCCCATATCGCGATATCGC")
+
+
+@pytest.fixture(scope="module")
+def mg():
+    import modimizer_b200 as m
+    m.require_device()
+    return m
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+# --------------------------------------------------------------- helpers --
+def gpu_select(mg, torch, k, d, seed, data, offs, flags=1, is_ascii=0):
+    """device-level K1 + K2 through the C ABI; returns (kmers, gpos) as numpy"""
+    import ctypes as C
+    from modimizer_b200 import _lib
+    lib = _lib.load()
+    h = _lib.Hasher()
+    _lib.check(lib.modgpuHasherInit(C.byref(h), k, d, seed))
+    data = np.ascontiguousarray(data, np.uint8)
+    offs = np.ascontiguousarray(offs, np.uint64)
+    n = int(offs[-1])
+    dev = torch.device("cuda:0")
+    d_bases = torch.from_numpy(data if n else np.zeros(1, np.uint8)).to(dev)
+    d_offs = torch.from_numpy(offs.view(np.int64)).to(dev)
+    words = lib.modgpuPackedWords(n)
+    d_packed = torch.zeros(words, dtype=torch.int64, device=dev)
+    d_ends = torch.zeros(words, dtype=torch.int32, device=dev)
+    cap = max(n, 1)
+    d_k = torch.zeros(cap, dtype=torch.int64, device=dev)
+    d_p = torch.zeros(cap, dtype=torch.int32, device=dev)
+    d_cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    d_ws = torch.zeros(lib.modgpuHashSelectWorkspace(n) // 8 + 8, dtype=torch.int64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.modgpuPack2bit(d_bases.data_ptr(), n, is_ascii, d_packed.data_ptr(), st), "pack")
+    _lib.check(lib.modgpuMarkEnds(d_offs.data_ptr(), len(offs) - 1, n, d_ends.data_ptr(), st), "ends")
+    _lib.check(lib.modgpuHashSelect(C.byref(h), d_packed.data_ptr(), d_ends.data_ptr(), n, d_k.data_ptr(), d_p.data_ptr(),
+                                    cap, d_cnt.data_ptr(), d_ws.data_ptr(), flags, st), "select")
+    torch.cuda.synchronize()
+    cnt = int(d_cnt.item())
+    km = d_k[:cnt].cpu().numpy().view(np.uint64)
+    gp = d_p[:cnt].cpu().numpy().view(np.uint32)
+    return km, gp, d_packed.cpu().numpy().view(np.uint64)
+
+
+def oracle_select(orc, k, d, seed, data, offs):
+    ks, ps, fs = [], [], []
+    for r in range(len(offs) - 1):
+        a, b = int(offs[r]), int(offs[r + 1])
+        kk, pp, ff = orc.mod_scan(k, d, seed, data[a:b])
+        ks.append(kk); ps.append(pp.astype(np.int64) + a); fs.append(ff)
+    if not ks:
+        return np.zeros(0, np.uint64), np.zeros(0, np.int64), np.zeros(0, np.uint8)
+    return np.concatenate(ks), np.concatenate(ps), np.concatenate(fs)
+
+
+def random_batch(rng, nseq, maxlen, mode="random"):
+    lens = rng.integers(0, maxlen, nseq)
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    n = int(offs[-1])
+    if mode == "polyA":
+        data = np.zeros(max(n, 1), np.uint8)
+    elif mode == "AT":
+        data = np.tile(np.array([0, 3], np.uint8), n // 2 + 1)[:max(n, 1)].copy()
+    else:
+        data = rng.integers(0, 4, max(n, 1)).astype(np.uint8)
+    return data[:n] if n else np.zeros(0, np.uint8), offs
+
+
+# ------------------------------------------------------------------ K1 K2 --
+def test_kat_survey_vectors(mg, torch_cuda, orc):
+    """the known-answer vectors of SURVEY section 4 (generated from the reference)"""
+    codes = H.codes_from_ascii(KAT_SEQ)
+    offs = np.array([0, len(codes)], np.uint64)
+    km, gp, _ = gpu_select(mg, torch_cuda, 19, 31, 17, codes, offs, flags=1 | 2)
+    assert [int(x) for x in gp] == [3, 41, 49, 84]
+    assert [hex(int(x) & ((1 << 62) - 1)) for x in km] == ["0x3e4e58c9c9", "0x2c9c9c9e36", "0x24e4d8d272", "0x1393639c9c"]
+    assert [int(x) >> 63 for x in km] == [1, 1, 0, 0]                      # isF
+    # len < k -> nothing
+    km, gp, _ = gpu_select(mg, torch_cuda, 19, 31, 17, codes[:18], np.array([0, 18], np.uint64))
+    assert len(km) == 0
+    # ASCII input gives the same answer as codes
+    asc = np.frombuffer(KAT_SEQ.encode(), np.uint8)
+    km2, gp2, _ = gpu_select(mg, torch_cuda, 19, 31, 17, asc, offs, flags=1, is_ascii=1)
+    assert [int(x) for x in gp2] == [3, 41, 49, 84]
+
+
+def test_pack_layout(mg, torch_cuda):
+    rng = np.random.default_rng(5)
+    for n in (1, 31, 32, 33, 1000, 8192, 8193, 100003):
+        codes = rng.integers(0, 4, n).astype(np.uint8)
+        offs = np.array([0, n], np.uint64)
+        _, _, packed = gpu_select(mg, torch_cuda, 5, 1, 17, codes, offs)
+        nw = (n + 31) // 32
+        exp = np.zeros(nw, np.uint64)
+        he.lib().hm_pack(codes, n, 0, exp, nw)
+        assert np.array_equal(packed[:nw], exp), n
+        assert not packed[nw:].any()
+        # ASCII, mixed case and N
+        asc = np.frombuffer(b"ACGTacgtNn", np.uint8)[rng.integers(0, 10, n)]
+        _, _, packed2 = gpu_select(mg, torch_cuda, 5, 1, 17, asc, offs, is_ascii=1)
+        exp2 = np.zeros(nw, np.uint64)
+        he.lib().hm_pack(H.codes_from_ascii(asc.tobytes()), n, 0, exp2, nw)
+        assert np.array_equal(packed2[:nw], exp2), n
+
+
+@pytest.mark.parametrize("flags", [1, 0, 1 | 4, 4, 1 | 8, 8 | 4])
+def test_select_random_params(mg, torch_cuda, orc, flags):
+    """property test: GPU selected list == the serial iterator's list, in order
+    (ORDERED) or as a multiset (count mode), for random k, d, seed, ragged batches"""
+    rng = np.random.default_rng(100 + flags)
+    ds = [1, 2, 3, 7, 8, 16, 31, 32, 48, 62, 64, 128, 1000, 4096]
+    for trial in range(40):
+        k = int(rng.integers(1, 32))
+        d = int(rng.choice(ds))
+        seed = int(rng.integers(0, 50))
+        mode = ["random", "random", "random", "polyA", "AT"][trial % 5]
+        data, offs = random_batch(rng, int(rng.integers(1, 40)), 40 if trial % 4 == 0 else 3000, mode)
+        ek, ep, ef = oracle_select(orc, k, d, seed, data, offs)
+        km, gp, _ = gpu_select(mg, torch_cuda, k, d, seed, data, offs, flags=flags | 2)
+        assert len(km) == len(ek), (k, d, seed, trial)
+        kk = km & np.uint64((1 << 62) - 1)
+        ff = (km >> np.uint64(63)).astype(np.uint8)
+        if flags & 1:
+            assert np.array_equal(kk, ek) and np.array_equal(gp.astype(np.int64), ep) and np.array_equal(ff, ef), (k, d, seed, trial)
+        else:
+            o1 = np.lexsort((kk, gp)); o2 = np.lexsort((ek, ep))
+            assert np.array_equal(kk[o1], ek[o2]) and np.array_equal(gp[o1].astype(np.int64), ep[o2]), (k, d, seed, trial)
+
+
+def test_select_large_multi_tile(mg, torch_cuda, orc):
+    """many tiles, reads that start at arbitrary (non word-aligned) offsets, both
+    headline parameter sets, TMA and plain loads, prefilter and generic"""
+    rng = np.random.default_rng(77)
+    lens = np.concatenate([rng.integers(100, 20000, 300), [0, 1, 18, 19, 30, 31, 32, 33, 0, 0, 150, 150]])
+    rng.shuffle(lens)
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    data = rng.integers(0, 4, int(offs[-1])).astype(np.uint8)
+    for (k, d) in ((19, 31), (31, 64), (16, 64), (17, 32), (31, 31)):
+        ek, ep, ef = oracle_select(orc, k, d, 17, data, offs)
+        for flags in (1, 1 | 4, 1 | 8):
+            km, gp, _ = gpu_select(mg, torch_cuda, k, d, 17, data, offs, flags=flags)
+            assert np.array_equal(km, ek) and np.array_equal(gp.astype(np.int64), ep), (k, d, flags)
+        km, gp, _ = gpu_select(mg, torch_cuda, k, d, 17, data, offs, flags=0)
+        assert np.array_equal(np.sort(km), np.sort(ek)), (k, d)
+
+
+# ------------------------------------------------------------------ modset --
+def _check_modset(mg, orc, bits, k, d, seed, data, offs, exact):
+    ms = mg.Modset(bits, k, d, seed, exact_order=exact)
+    oms = orc.modset_new(bits, k, d, seed)
+    try:
+        tot = ms.add(data, offs, is_ascii=0)
+        otot = orc.modset_add(oms, data, offs)
+        assert tot == otot
+        assert ms.max == orc._modset_max(oms)
+        gv, gd, gi = ms.sorted_dump()
+        ov, od, oi = orc.modset_sorted(oms)
+        assert np.array_equal(gv, ov) and np.array_equal(gd, od) and np.array_equal(gi, oi)
+        if exact:                                            # identical index numbering
+            v, dd, ii = ms.export()
+            ov2, od2, oi2 = orc.modset_export(oms)
+            assert np.array_equal(v, ov2) and np.array_equal(dd, od2)
+        assert np.array_equal(ms.histogram(), orc.modset_hist(oms))
+        assert ms.summary() == orc.modset_summary(oms)
+        return ms, oms
+    except Exception:
+        ms.close(); orc._modset_free(oms)
+        raise
+
+
+@pytest.mark.parametrize("exact", [False, True])
+def test_modset_build_count(mg, orc, exact):
+    """config-1 shape, scaled: reads sampled from a genome, both strands, ~30x"""
+    glen, rlen, nreads = 200000, 5000, 1200
+    sp = he.read_spec(12345, glen, 99, rlen)
+    data = he.reads(sp, 0, nreads)
+    offs = (np.arange(nreads + 1, dtype=np.uint64) * np.uint64(rlen))
+    ms, oms = _check_modset(mg, orc, 22, 19, 31, 17, data, offs, exact)
+    try:
+        # classification -s and -sM (modutils.c:205-219) + summary tallies
+        c = ms.set_copy(10, 45, 75)
+        orc._modset_setcopy(oms, 10, 45, 75)
+        gv, gd, gi = ms.sorted_dump(); ov, od, oi = orc.modset_sorted(oms)
+        assert np.array_equal(gi, oi)
+        assert list(c) == [int((oi == j).sum()) for j in range(4)]
+        assert ms.summary() == orc.modset_summary(oms)
+        ms.set_copy_m(40)
+        orc._modset_setcopyM(oms, 40)
+        assert np.array_equal(ms.sorted_dump()[2], orc.modset_sorted(oms)[2])
+        assert ms.summary() == orc.modset_summary(oms)
+        # a second batch accumulates into the same table
+        data2 = he.reads(sp, nreads, 300)
+        offs2 = (np.arange(301, dtype=np.uint64) * np.uint64(rlen))
+        assert ms.add(data2, offs2, is_ascii=0) == orc.modset_add(oms, data2, offs2)
+        gv, gd, gi = ms.sorted_dump(); ov, od, oi = orc.modset_sorted(oms)
+        assert np.array_equal(gv, ov) and np.array_equal(gd, od)
+        # lookups (modsetIndexFind(..,false))
+        probe = np.concatenate([ov[:1000], ov[:1000] ^ np.uint64(1)])
+        gidx, gcp = ms.find(probe)
+        oidx = np.array([orc._modset_find(oms, int(x)) for x in probe])
+        assert np.array_equal(gidx != 0, oidx != 0)
+        if exact:
+            assert np.array_equal(gidx, oidx)
+    finally:
+        ms.close(); orc._modset_free(oms)
+
+
+def test_modset_edge_cases(mg, orc):
+    rng = np.random.default_rng(3)
+    # empty batch, empty reads, len<k, len==k, palindromes, d = 1 (every k-mer), k = 1
+    for (k, d, mode) in ((19, 31, "random"), (5, 1, "random"), (1, 1, "random"), (4, 3, "AT"), (31, 64, "polyA"), (12, 8, "AT")):
+        data, offs = random_batch(rng, 30, 200, mode)
+        ms, oms = _check_modset(mg, orc, 20, k, d, 17, data, offs, True)
+        ms.close(); orc._modset_free(oms)
+    ms = mg.Modset(20, 19, 31, 17)
+    assert ms.add(np.zeros(0, np.uint8), np.array([0], np.uint64)) == 0
+    assert ms.add(np.zeros(0, np.uint8), np.array([0, 0, 0], np.uint64)) == 0
+    assert ms.max == 0
+    ms.close()
+
+
+def test_depth_saturation(mg, orc):
+    """depth is U16 saturating at 65535 (modutils.c:26): poly-A read, d = 1"""
+    n = 70000 + 18
+    data = np.zeros(n, np.uint8)
+    offs = np.array([0, n], np.uint64)
+    ms = mg.Modset(20, 19, 1, 17)
+    oms = orc.modset_new(20, 19, 1, 17)
+    assert ms.add(data, offs, is_ascii=0) == orc.modset_add(oms, data, offs) == 70000
+    gv, gd, gi = ms.sorted_dump(); ov, od, oi = orc.modset_sorted(oms)
+    assert np.array_equal(gv, ov) and np.array_equal(gd, od) and int(gd[0]) == 65535
+    assert np.array_equal(ms.histogram(), orc.modset_hist(oms))
+    ms.close(); orc._modset_free(oms)
+
+
+def test_table_overflow_is_an_error(mg):
+    """the reference dies when max >= size (modset.c:58); we raise"""
+    rng = np.random.default_rng(9)
+    n = 400000
+    data = rng.integers(0, 4, n).astype(np.uint8)
+    ms = mg.Modset(20, 19, 1, 17)          # capacity 2^18 - 2 entries
+    with pytest.raises(mg.ModgpuError):
+        ms.add(data, np.array([0, n], np.uint64), is_ascii=0)
+    ms.close()
+
+
+# ------------------------------------------------------------------ modmap --
+def test_reference_build_and_query(mg, orc):
+    """config-2/5 shape, scaled: genome with duplicated segments (copy2 / multi
+    classes), reads with errors looked up; every Reference array identical"""
+    seqlens = [300000, 150000, 0, 70000, 19, 18]
+    total = sum(seqlens)
+    genome = he.genome(4242, 0, total, 1)
+    # plant small-scale duplicates so that copy2 / multi classes are populated
+    genome[150000:160000] = genome[10000:20000]
+    genome[310000:312000] = genome[10000:12000]
+    genome[400000:405000] = genome[100000:105000]
+    offs = np.concatenate([[0], np.cumsum(seqlens)]).astype(np.uint64)
+    for (k, d) in ((31, 64), (19, 31)):
+        R = mg.Reference(24, k, d, 17, genome, offs, is_ascii=0)
+        oref, ocounts = orc.ref_build(24, k, d, 17, genome, offs)
+        try:
+            assert list(R.counts) == list(ocounts), (k, d)
+            assert ocounts[2] > 0 and ocounts[3] > 0
+            g = R.export(); o = orc.ref_export(oref)
+            for key in ("index", "offset", "id", "depth", "loc", "rev"):
+                assert np.array_equal(g[key], o[key]), (k, d, key)
+            gv, gd, gi = R.ms.export()
+            ov, od, oi = orc.modset_export(orc._ref_modset(oref))
+            assert np.array_equal(gv, ov) and np.array_equal(gd, od) and np.array_equal(gi, oi)
+            # reads: error-free, 1% and 10% substitution/indel
+            for (sub, ins, dele, ont) in ((0, 0, 0, False), (10000, 0, 0, False), (30000, 30000, 40000, True)):
+                sp = he.read_spec(4242, 300000, 5, 2000, sub, ins, dele, dup_mode=1)
+                reads = he.reads(sp, 0, 200, ont)
+                roffs = np.arange(201, dtype=np.uint64) * np.uint64(2000)
+                gq = R.query(reads, roffs, is_ascii=0)
+                oq = orc.ref_query(oref, reads, roffs)
+                for key in ("seedOff", "index", "pos", "hitId", "hitOffset", "counters"):
+                    assert np.array_equal(gq[key], oq[key]), (k, d, key, sub)
+                assert oq["counters"][:, 1].sum() > 0
+        finally:
+            R.close(); orc._ref_free(oref)
+
+
+def test_import_export_roundtrip(mg, orc):
+    """sync-to-host / upload: export -> import into a fresh table -> identical set and lookups"""
+    rng = np.random.default_rng(21)
+    data = rng.integers(0, 4, 300000).astype(np.uint8)
+    offs = np.array([0, 100000, 300000], np.uint64)
+    ms = mg.Modset(22, 19, 31, 17, exact_order=True)
+    ms.add(data, offs, is_ascii=0)
+    ms.set_copy(1, 2, 3)
+    v, d, i = ms.export()
+    ms2 = mg.Modset(22, 19, 31, 17)
+    ms2.import_entries(v, d, i)
+    v2, d2, i2 = ms2.export()
+    assert np.array_equal(v, v2) and np.array_equal(d, d2) and np.array_equal(i, i2)
+    idx, cp = ms2.find(v[::7])
+    assert np.array_equal(idx, np.arange(1, len(v) + 1, dtype=np.uint32)[::7]) and np.array_equal(cp, i[::7] & 3)
+    ms.close(); ms2.close()
+
+
+def test_device_synth_matches_host(mg, torch_cuda):
+    """the device generators produce the bytes the host generator (oracle side) does"""
+    from modimizer_b200 import synth
+    dev = torch_cuda.device("cuda:0")
+    buf = torch_cuda.zeros(200000, dtype=torch_cuda.uint8, device=dev)
+    synth.genome_device(12345, 64, 200000, 1, buf.data_ptr())
+    torch_cuda.cuda.synchronize()
+    assert np.array_equal(buf.cpu().numpy(), he.genome(12345, 64, 200000, 1))
+    synth.genome_device(12345, 7, 1999, 0, buf.data_ptr() + 1)
+    torch_cuda.cuda.synchronize()
+    assert np.array_equal(buf[1:2000].cpu().numpy(), he.genome(12345, 7, 1999, 0))
+    for (spec, ont) in ((synth.read_spec(12345, 100000, 7, 150, 5000, frag_len=400, pair_mode=1), False),
+                        (synth.read_spec(12345, 100000, 7, 1001, 1000), False),
+                        (synth.read_spec(12345, 100000, 7, 500, 30000, 30000, 40000), True)):
+        n = 64
+        synth.reads_device(spec, 3, n, ont, buf.data_ptr())
+        torch_cuda.cuda.synchronize()
+        hs = he.read_spec(spec.genomeSeed, spec.genomeLen, spec.readSeed, spec.readLen, spec.subPPM, spec.insPPM,
+                          spec.delPPM, spec.fragLen, spec.pairMode, spec.dupMode)
+        assert np.array_equal(buf[:n * spec.readLen].cpu().numpy(), he.reads(hs, 3, n, ont))
+
+
+def test_large_batch_properties(mg, torch_cuda):
+    """size-independent properties at a multi-chunk size (no oracle): adding the
+    same batch twice doubles every depth and keeps the set; the histogram
+    counts every entry once; total hashes = sum of depths (below saturation)."""
+    from modimizer_b200 import synth
+    n = (1 << 28) + 12345                    # > one host chunk
+    dev = torch_cuda.device("cuda:0")
+    buf = torch_cuda.zeros(n, dtype=torch_cuda.uint8, device=dev)
+    synth.genome_device(777, 0, n, 0, buf.data_ptr())
+    nseq = 50
+    cuts = np.linspace(0, n, nseq + 1).astype(np.uint64)
+    d_offs = torch_cuda.from_numpy(cuts.view(np.int64)).to(dev)
+    ms = mg.Modset(26, 31, 64, 17)
+    t1 = ms.add_device(buf.data_ptr(), d_offs.data_ptr(), nseq, n)
+    v1, d1, _ = ms.sorted_dump()
+    assert int(d1.astype(np.int64).sum()) == t1
+    assert abs(t1 - n / 64) < 0.02 * n / 64
+    host = buf.cpu().numpy()
+    t2 = ms.add(host, cuts, is_ascii=0)      # same data through the host path, chunked + pipelined
+    assert t2 == t1
+    v2, d2, _ = ms.sorted_dump()
+    assert np.array_equal(v1, v2) and np.array_equal(d2, 2 * d1)
+    h = ms.histogram()
+    assert int(h.sum()) == ms.max == len(v1)
+    ms.close()
