@@ -168,7 +168,8 @@ const ModgpuHasher *modgpuModsetHasher(const ModgpuModset *ms);
 ModgpuTable *modgpuModsetTable(ModgpuModset *ms);
 /* use the caller's stream (e.g. torch's current stream) for all work */
 int modgpuModsetSetStream(ModgpuModset *ms, void *stream);
-/* MODGPU_SEL_* flags forwarded to the hash/select kernel (tuning, A/B tests) */
+/* MODGPU_SEL_* flags forwarded to the hash/select kernel (tuning, A/B tests);
+ * bits 8..15 = insert-locality override + 1: 0 auto, 1 off, v = 2^(v-1) table regions */
 int modgpuModsetSetFlags(ModgpuModset *ms, int flags);
 /* exactOrder != 0: keep the reference's first-occurrence index numbering */
 int modgpuModsetSetExactOrder(ModgpuModset *ms, int exactOrder);

@@ -22,6 +22,8 @@ int mg_table_insert_dev(ModgpuTable *t, const uint64_t *d_kmers, const uint64_t 
 int mg_table_lookup_dev(const ModgpuTable *t, const uint64_t *d_kmers, const uint64_t *d_n, uint64_t nMax,
                         uint32_t *d_out, cudaStream_t st);
 uint64_t mg_table_numbered(const ModgpuTable *t);
+int mg_slot_partition(const uint64_t *d_kmers, uint64_t n, uint32_t slotBits, uint32_t bucketBits,
+                      uint64_t *d_out, uint64_t *d_scratch, cudaStream_t st);
 int mg_table_classify(ModgpuTable *t, int mode, int c1, int c2, int cM, int zeroDepth, uint32_t *d_classCounts, cudaStream_t st);
 
 // bases per pipelined chunk when the batch comes from host memory / is resident
@@ -72,7 +74,8 @@ struct ModgpuModset {
   int exactOrder = 0;
   bool depthIsZero = false;         // modmap-built sets keep ms->depth at 0
   bool dirty = false;               // entries inserted since the last numbering
-  DevBuf bases[2], offs[2], packed, ends, kmers, gpos, slot, work, misc, expo;
+  DevBuf bases[2], offs[2], packed, ends, kmers, kmers2, gpos, slot, work, misc, expo;
+  int regionBits = -1;              // -1 auto: partition inserts by table region when the table exceeds L2
   PinBuf hOffs[2], hMisc;
   cudaEvent_t evCopied[2] = { nullptr, nullptr }, evFree[2] = { nullptr, nullptr };
   uint64_t totalHashes = 0;
@@ -140,7 +143,7 @@ extern "C" ModgpuModset *modgpuModsetCreate(int bits, int k, int w, int seed)
     }
   ms->table = modgpuTableCreate(bits, ms->stream);
   if (!ms->table) { modgpuModsetDestroy(ms); return nullptr; }
-  if (ms->misc.ensure(4096) || ms->hMisc.ensure(4096)) { modgpuModsetDestroy(ms); return nullptr; }
+  if (ms->misc.ensure(16384) || ms->hMisc.ensure(4096)) { modgpuModsetDestroy(ms); return nullptr; }
   return ms;
 }
 
@@ -156,7 +159,7 @@ extern "C" void modgpuModsetDestroy(ModgpuModset *ms)
       if (ms->evCopied[i]) cudaEventDestroy(ms->evCopied[i]);
       if (ms->evFree[i]) cudaEventDestroy(ms->evFree[i]);
     }
-  ms->packed.release(); ms->ends.release(); ms->kmers.release(); ms->gpos.release(); ms->slot.release();
+  ms->packed.release(); ms->ends.release(); ms->kmers.release(); ms->kmers2.release(); ms->gpos.release(); ms->slot.release();
   ms->work.release(); ms->misc.release(); ms->expo.release(); ms->hMisc.release();
   if (ms->table) modgpuTableDestroy(ms->table);
   if (ms->ownStream && ms->stream) cudaStreamDestroy(ms->stream);
@@ -176,7 +179,14 @@ extern "C" int modgpuModsetSetStream(ModgpuModset *ms, void *stream)
   return MODGPU_OK;
 }
 
-extern "C" int modgpuModsetSetFlags(ModgpuModset *ms, int flags) { ms->selFlags = flags; return MODGPU_OK; }
+extern "C" int modgpuModsetSetFlags(ModgpuModset *ms, int flags)
+{
+  ms->selFlags = flags & 0xFF;
+  // bits 8..15: insert locality override + 1 (0 = auto): 1 = off, 2.. = 2^(v-1) regions
+  const int v = (flags >> 8) & 0xFF;
+  ms->regionBits = v ? v - 1 : -1;
+  return MODGPU_OK;
+}
 extern "C" int modgpuModsetSetExactOrder(ModgpuModset *ms, int e) { ms->exactOrder = e ? 1 : 0; return MODGPU_OK; }
 
 extern "C" int modgpuModsetProfile(ModgpuModset *ms, int enable)
@@ -240,6 +250,34 @@ int mg_modset_select_chunk(ModgpuModset *ms, const uint8_t *d_bases, const uint6
   return MODGPU_OK;
 }
 
+// K3 with locality: when the table is much larger than L2 and the list is long,
+// group the k-mers by table region first (2 streaming passes over 8 B each) so
+// that the random probes of one region hit L2; order of insertion is free in
+// count mode.  Exact-order inserts keep the input order (ordinals matter).
+static int insert_list(ModgpuModset *ms, const uint64_t *d_kmers, uint64_t n, uint32_t *dSlot)
+{
+  int rc;
+  const uint64_t tableBytes = modgpuTableSlots(ms->table) * sizeof(MgSlot);
+  uint32_t slotBits = 0;
+  while ((1ull << slotBits) < modgpuTableSlots(ms->table)) ++slotBits;
+  int rb = ms->regionBits;
+  if (rb < 0)
+    { rb = 0;
+      if (!ms->exactOrder && tableBytes > (64ull << 20) && n >= (1ull << 20))
+        while ((tableBytes >> rb) > (8ull << 20) && rb < 8) ++rb;        // regions of <= 8 MiB (measured best)
+    }
+  if (rb > 0 && !ms->exactOrder)
+    { if ((rc = ms->kmers2.ensure(n * 8))) return rc;
+      uint64_t *scratch = (uint64_t *)((char *)ms->misc.p + 512);
+      { ProfScope p(ms, MODGPU_T_INSERT, 3);
+        if ((rc = mg_slot_partition(d_kmers, n, slotBits, (uint32_t)rb, (uint64_t *)ms->kmers2.p, scratch, ms->stream))) return rc;
+      }
+      d_kmers = (const uint64_t *)ms->kmers2.p;
+    }
+  ProfScope p(ms, MODGPU_T_INSERT, 1);
+  return mg_table_insert_dev(ms->table, d_kmers, nullptr, n, dSlot, ms->exactOrder, ms->stream);
+}
+
 static int add_chunk_device(ModgpuModset *ms, const uint8_t *d_bases, const uint64_t *d_offs, uint64_t nSeq,
                             uint64_t nBases, int isAscii, uint64_t *nHashes)
 {
@@ -253,9 +291,7 @@ static int add_chunk_device(ModgpuModset *ms, const uint8_t *d_bases, const uint
     { if ((rc = ms->slot.ensure(n * 4))) return rc;
       dSlot = (uint32_t *)ms->slot.p;
     }
-  { ProfScope p(ms, MODGPU_T_INSERT, 1);
-    if ((rc = mg_table_insert_dev(ms->table, (const uint64_t *)ms->kmers.p, nullptr, n, dSlot, ms->exactOrder, ms->stream))) return rc;
-  }
+  if ((rc = insert_list(ms, (const uint64_t *)ms->kmers.p, n, dSlot))) return rc;
   if (ms->exactOrder)
     { ProfScope p(ms, MODGPU_T_OTHER, 3);
       if ((rc = modgpuTableNumber(ms->table, dSlot, n, nullptr, ms->stream))) return rc;
@@ -408,8 +444,10 @@ extern "C" int modgpuModsetSelectHost(ModgpuModset *ms, const char *bases, const
 extern "C" int modgpuModsetInsertDevice(ModgpuModset *ms, const uint64_t *d_kmers, uint64_t n)
 {
   if (!n) return MODGPU_OK;
-  { ProfScope p(ms, MODGPU_T_INSERT, 1);
-    int rc = mg_table_insert_dev(ms->table, d_kmers, nullptr, n, nullptr, 0, ms->stream);
+  { const int keep = ms->exactOrder;
+    ms->exactOrder = 0;
+    int rc = insert_list(ms, d_kmers, n, nullptr);
+    ms->exactOrder = keep;
     if (rc) return rc;
   }
   ms->dirty = true;
@@ -443,8 +481,11 @@ void *mg_modset_gpos(ModgpuModset *ms) { return ms->gpos.p; }
 
 extern "C" uint32_t modgpuModsetMax(ModgpuModset *ms)
 {
-  if (ensure_numbered(ms)) return 0xFFFFFFFFu;
-  return (uint32_t)mg_table_numbered(ms->table);
+  // ms->max is the number of distinct entries: the device counter has it without
+  // numbering the entries (numbering is only needed to export or look up)
+  uint64_t e = modgpuTableEntries(ms->table, ms->stream);
+  if (e == 0xFFFFFFFFFFFFFFFFull) return 0xFFFFFFFFu;
+  return (uint32_t)e;
 }
 
 extern "C" int modgpuModsetExport(ModgpuModset *ms, uint64_t *value, uint16_t *depth, uint8_t *info)

@@ -26,7 +26,7 @@
 // against ~9-28 instructions per base) - see DESIGN.md for the roofline.
 #include "mg_device.cuh"
 
-#define MG_TILE_PACK_BYTES (MG_TILE_THREADS * 8 + 16)     // 256 words + overlap word, 16 B multiple
+#define MG_TILE_PACK_BYTES (MG_TILE_THREADS * 8 + 16)     // 256 words + overlap word, 16 B multiple (258 words)
 #define MG_TILE_ENDS_BYTES (MG_TILE_THREADS * 4 + 16)
 
 struct SelectParams {
@@ -44,24 +44,51 @@ struct SelectParams {
   uint32_t *ticket;            // tile ticket
 };
 
+// Phase 2 helper: evaluate queue entry e = (source thread << 5 | window) of the
+// current tile from the shared-memory copy of the packed words.
+__device__ __forceinline__ bool eval_entry(const MgKHasher &H, const uint64_t *sWords, uint32_t e,
+                                           uint64_t *km, bool *isF)
+{
+  const uint32_t src = e >> 5, bit = e & 31u;
+  const MgRun R = mg_run_prepare(sWords[src], sWords[src + 1], H.k);
+  return mg_eval_window(H, R, bit, km, isF);
+}
+
+// One tile in three phases:
+//  1. every thread scans its run of 32 window starts into a bit mask: with the
+//     PREFILTER the candidates (cheap low-word test), otherwise the windows
+//     that are selected (full canonical test);
+//  2. the set bits of the whole tile are compacted into a shared-memory queue
+//     in position order (one block scan), so that
+//  3. the expensive part - full 64-bit evaluation of a candidate, extraction
+//     of the winning strand's k-mer, the store - is spread evenly over the 256
+//     threads whatever the distribution of hits among the runs (a per-thread
+//     loop over its own hits costs max-over-lanes iterations per warp: measured
+//     2/3 of all issued instructions in the first version of this kernel).
 template <bool PREFILTER, bool ORDERED, bool TMA>
 __global__ void __launch_bounds__(MG_TILE_THREADS) hash_select_kernel(const SelectParams P)
 {
-  __shared__ __align__(128) uint64_t sPack[TMA ? 2 : 1][TMA ? (MG_TILE_PACK_BYTES / 8) : 2];
+  constexpr int NBUF = TMA ? 2 : 1;
+  __shared__ __align__(128) uint64_t sPack[NBUF][MG_TILE_PACK_BYTES / 8];
   __shared__ __align__(128) uint32_t sEnds[TMA ? 2 : 1][TMA ? (MG_TILE_ENDS_BYTES / 4) : 4];
   __shared__ __align__(8) uint64_t sBar[2];
+  __shared__ uint16_t sQueue[MG_TILE_BASES];
+  __shared__ uint32_t sSel[ORDERED ? MG_TILE_THREADS : 1];     // ORDERED: selected windows per run
+  __shared__ uint32_t sDst[ORDERED ? MG_TILE_THREADS : 1];     // ORDERED: output offset of each run
   __shared__ uint32_t sTile[2];
   __shared__ uint32_t sWarp[MG_TILE_THREADS / 32];
   __shared__ uint64_t sBase;
 
   const MgKHasher &H = P.H;
   const uint32_t tid = threadIdx.x;
+  const uint32_t lane = tid & 31;
 
   if (tid == 0)
     { if (TMA)
         { mg_mbar_init(&sBar[0], 1);
           mg_mbar_init(&sBar[1], 1);
           mg_fence_barrier_init();
+          mg_fence_proxy_async();
         }
       uint32_t t0 = atomicAdd(P.ticket, 1u);
       sTile[0] = t0;
@@ -74,7 +101,8 @@ __global__ void __launch_bounds__(MG_TILE_THREADS) hash_select_kernel(const Sele
 
   for (uint32_t it = 0;; ++it)
     { const uint32_t stage = it & 1;
-      __syncthreads();               // sTile[stage] visible; everyone is done with buffer stage^1
+      const uint32_t buf = TMA ? stage : 0;
+      __syncthreads();               // sTile[stage] visible; everyone is done with the other buffer and the queue
       const uint32_t tile = sTile[stage];
       if (tile >= P.nTiles) break;
 
@@ -93,32 +121,32 @@ __global__ void __launch_bounds__(MG_TILE_THREADS) hash_select_kernel(const Sele
       uint64_t w0, w1, eflags;
       if (TMA)
         { mg_mbar_wait(&sBar[stage], (it >> 1) & 1);
-          w0 = sPack[stage][tid];
-          w1 = sPack[stage][tid + 1];
-          eflags = (uint64_t)sEnds[stage][tid] | ((uint64_t)sEnds[stage][tid + 1] << 32);
+          w0 = sPack[buf][tid];
+          w1 = sPack[buf][tid + 1];
+          eflags = (uint64_t)sEnds[buf][tid] | ((uint64_t)sEnds[buf][tid + 1] << 32);
         }
       else
         { w0 = __ldg(P.packed + word);
           w1 = __ldg(P.packed + word + 1);
           eflags = (uint64_t)__ldg(P.ends + word) | ((uint64_t)__ldg(P.ends + word + 1) << 32);
+          sPack[0][tid] = w0;                              // phase 3 reads the tile from shared memory
+          if (tid == MG_TILE_THREADS - 1) sPack[0][MG_TILE_THREADS] = w1;
         }
-      const uint64_t p0 = word * MG_RUN;                   // global offset of window 0
-      const uint32_t usable = mg_run_usable(eflags, H.k, p0, P.nBases);
-
+      const uint64_t tileBase = (uint64_t)tile * MG_TILE_BASES;
+      const uint32_t usable = mg_run_usable(eflags, H.k, tileBase + (uint64_t)tid * MG_RUN, P.nBases);
       const MgRun R = mg_run_prepare(w0, w1, H.k);
 
-      // ---- selection mask over the 32 window starts
-      uint32_t sel = 0;
+      // ---- phase 1: mask over the 32 window starts of the run
+      uint32_t m = 0;
       if (PREFILTER)
-        { uint32_t cand = 0;
+        {
 #pragma unroll
           for (int i = 0; i < MG_RUN; ++i)
-            cand |= (mg_prefilter_candidate(H, R, i) ? 1u : 0u) << i;
-          cand &= usable;
-          while (cand)
-            { uint32_t i = __ffs(cand) - 1; cand &= cand - 1;
-              uint64_t km; bool isF;
-              if (mg_eval_window(H, R, i, &km, &isF)) sel |= 1u << i;
+            { // candidate <=> min(low product word of fwd, of rc) < pfLim; one predicated OR per window
+              const uint32_t pf = mg_run_fwd_lo(R, i) * H.pfMul, pr = mg_run_rc_lo(R, i) * H.pfMul;
+              const uint32_t mn = min(pf, pr);
+              asm("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}"
+                  : "+r"(m) : "r"(mn), "r"(H.pfLim), "r"(1u << i));
             }
         }
       else
@@ -126,40 +154,93 @@ __global__ void __launch_bounds__(MG_TILE_THREADS) hash_select_kernel(const Sele
 #pragma unroll
           for (int i = 0; i < MG_RUN; ++i)
             { uint64_t km; bool isF;
-              bool ok = mg_eval_window(H, R, i, &km, &isF);
-              sel |= (ok ? 1u : 0u) << i;
+              if (mg_eval_window(H, R, i, &km, &isF)) m |= 1u << i;
             }
-          sel &= usable;
         }
+      m &= usable;
 
-      // ---- where do this tile's results go
-      uint32_t total;
-      uint32_t off = mg_block_excl_scan256(__popc(sel), sWarp, &total);
-      if (tid < 32)
-        { if (ORDERED)
+      // ---- phase 2: queue of (run, window) in position order
+      uint32_t nQueue;
+      uint32_t qoff = mg_block_excl_scan256(__popc(m), sWarp, &nQueue);
+      if (ORDERED) sSel[tid] = 0;
+      while (m)
+        { uint32_t i = __ffs(m) - 1; m &= m - 1;
+          sQueue[qoff++] = (uint16_t)((tid << 5) | i);
+        }
+      __syncthreads();
+
+      // ---- phase 3: balanced evaluation and output
+      const uint64_t *sWords = sPack[buf];
+      if (!ORDERED)
+        { // count mode: order is irrelevant, reserve output space per warp
+          for (uint32_t base = 0; base < nQueue; base += MG_TILE_THREADS)
+            { const uint32_t q = base + tid;
+              uint64_t km = 0; bool isF = false, ok = false;
+              uint32_t e = 0;
+              if (q < nQueue)
+                { e = sQueue[q];
+                  ok = eval_entry(H, sWords, e, &km, &isF);
+                }
+              const uint32_t ballot = __ballot_sync(0xffffffffu, ok);
+              if (!ballot) continue;
+              unsigned long long wbase = 0;
+              if (lane == 0) wbase = atomicAdd(P.count, (unsigned long long)__popc(ballot));
+              wbase = __shfl_sync(0xffffffffu, wbase, 0);
+              if (ok)
+                { const uint64_t dst = wbase + __popc(ballot & ((1u << lane) - 1u));
+                  if (dst < P.cap)
+                    { if (P.strandBit && isF) km |= 1ull << 63;
+                      P.outKmer[dst] = km;
+                      if (P.outPos) P.outPos[dst] = (uint32_t)(tileBase + e);   // e = run*32 + window
+                    }
+                }
+            }
+        }
+      else
+        { // input order: pass 1 marks the selected windows of every run ...
+          if (PREFILTER)
+            { for (uint32_t q = tid; q < nQueue; q += MG_TILE_THREADS)
+                { const uint32_t e = sQueue[q];
+                  uint64_t km; bool isF;
+                  if (eval_entry(H, sWords, e, &km, &isF)) atomicOr(&sSel[e >> 5], 1u << (e & 31u));
+                }
+            }
+          else
+            { for (uint32_t q = tid; q < nQueue; q += MG_TILE_THREADS)
+                { const uint32_t e = sQueue[q];
+                  atomicOr(&sSel[e >> 5], 1u << (e & 31u));          // the queue already holds the selected windows
+                }
+            }
+          __syncthreads();
+          // ... a scan over the runs + the look-back over the tiles place them ...
+          uint32_t total;
+          const uint32_t mySel = sSel[tid];
+          const uint32_t off = mg_block_excl_scan256(__popc(mySel), sWarp, &total);
+          sDst[tid] = off;
+          if (tid < 32)
             { uint32_t excl = mg_lookback(P.status, tile, total);
               if (tid == 0)
                 { sBase = excl;
                   if (tile == P.nTiles - 1) *P.count = (unsigned long long)excl + total;
                 }
             }
-          else if (tid == 0)
-            sBase = total ? atomicAdd(P.count, (unsigned long long)total) : 0ull;
-        }
-      __syncthreads();
-      uint64_t dst = sBase + off;
-
-      // ---- write the selected k-mers (winning strand, seqhash.c:183)
-      while (sel)
-        { uint32_t i = __ffs(sel) - 1; sel &= sel - 1;
-          uint64_t km; bool isF;
-          mg_eval_window(H, R, i, &km, &isF);
-          if (dst < P.cap)
-            { if (P.strandBit && isF) km |= 1ull << 63;
-              P.outKmer[dst] = km;
-              if (P.outPos) P.outPos[dst] = (uint32_t)(p0 + i);
+          __syncthreads();
+          const uint64_t outBase = sBase;
+          // ... pass 2 writes them, again spread over all threads
+          for (uint32_t q = tid; q < nQueue; q += MG_TILE_THREADS)
+            { const uint32_t e = sQueue[q];
+              const uint32_t src = e >> 5, bit = e & 31u;
+              const uint32_t selBits = sSel[src];
+              if (!((selBits >> bit) & 1u)) continue;
+              uint64_t km; bool isF;
+              eval_entry(H, sWords, e, &km, &isF);
+              const uint64_t dst = outBase + sDst[src] + __popc(selBits & ((1u << bit) - 1u));
+              if (dst < P.cap)
+                { if (P.strandBit && isF) km |= 1ull << 63;
+                  P.outKmer[dst] = km;
+                  if (P.outPos) P.outPos[dst] = (uint32_t)(tileBase + e);
+                }
             }
-          ++dst;
         }
     }
 }

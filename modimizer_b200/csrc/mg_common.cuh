@@ -181,11 +181,47 @@ MGHD bool mg_eval_window(const MgKHasher &H, const MgRun &R, uint32_t i, uint64_
 // bits live in the LOW 32-bit word of the product, which depends only on the low
 // word of the k-mer: (lo * factor) >> shift & (2^tz - 1) == 0
 //   <=>  lo * (factor << (32-shift-tz))  <  2^(32-tz)        (mod 2^32)
+// low 32 bits of the forward / reverse-complement window i, one funnel shift each
+MGHD uint32_t mg_funnel_l(uint32_t lo, uint32_t hi, uint32_t s)   // high word of (hi:lo) << s, 0 < s < 32
+{
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_l(lo, hi, s);
+#else
+  return (hi << s) | (lo >> (32 - s));
+#endif
+}
+
+MGHD uint32_t mg_funnel_r(uint32_t lo, uint32_t hi, uint32_t s)   // low word of (hi:lo) >> s, 0 < s < 32
+{
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(lo, hi, s);
+#else
+  return (lo >> s) | (hi << (32 - s));
+#endif
+}
+
+MGHD uint32_t mg_run_fwd_lo(const MgRun &R, uint32_t i)
+{
+  const uint32_t yhl = (uint32_t)R.yhi, ylh = (uint32_t)(R.ylo >> 32), yll = (uint32_t)R.ylo;
+  if (i == 0) return yhl;
+  if (i < 16) return mg_funnel_l(ylh, yhl, 2 * i);
+  if (i == 16) return ylh;
+  return mg_funnel_r(yll, ylh, 64 - 2 * i);
+}
+
+MGHD uint32_t mg_run_rc_lo(const MgRun &R, uint32_t i)
+{
+  const uint32_t rll = (uint32_t)R.rlo, rlh = (uint32_t)(R.rlo >> 32), rhl = (uint32_t)R.rhi;
+  if (i == 0) return rll;
+  if (i < 16) return mg_funnel_r(rll, rlh, 2 * i);
+  if (i == 16) return rlh;
+  return mg_funnel_r(rlh, rhl, 2 * i - 32);
+}
+
 MGHD bool mg_prefilter_candidate(const MgKHasher &H, const MgRun &R, uint32_t i)
 {
-  uint32_t flo = i ? (uint32_t)((R.yhi << (2 * i)) | (R.ylo >> (64 - 2 * i))) : (uint32_t)R.yhi;
-  uint32_t rlo = i ? (uint32_t)((R.rlo >> (2 * i)) | (R.rhi << (64 - 2 * i))) : (uint32_t)R.rlo;
-  return (flo * H.pfMul < H.pfLim) | (rlo * H.pfMul < H.pfLim);
+  const uint32_t pf = mg_run_fwd_lo(R, i) * H.pfMul, pr = mg_run_rc_lo(R, i) * H.pfMul;
+  return (pf < pr ? pf : pr) < H.pfLim;
 }
 
 // window starts of the run at global offset p0 that may be selected at all

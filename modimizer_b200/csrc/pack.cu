@@ -10,20 +10,33 @@
 // contiguous), SWAR converts four bytes at a time.
 #include "mg_device.cuh"
 
-// nFull: words whose 32 bytes are all inside the input; nWords: words to write
-// (the tail is zero = 'a' padding, never selected thanks to the end flags).
-template <bool ASCII, bool ALIGNED>
+// nWords: words to write (the tail is zero = 'a' padding, never selected thanks
+// to the end flags).  MIS = misalignment of `in` modulo 16 in 4-byte words
+// (0..3) with `sh` = 8 * (misalignment modulo 4): a misaligned batch (a group
+// of records inside a larger resident buffer) is still read with aligned
+// 16-byte loads, three per thread, and realigned with funnel shifts.
+template <bool ASCII, int MIS>
 __global__ void __launch_bounds__(256) pack2bit_kernel(const uint8_t *__restrict__ in, uint64_t nBases,
-                                                       uint64_t *__restrict__ out, uint64_t nWords)
+                                                       uint64_t *__restrict__ out, uint64_t nWords, uint32_t sh)
 {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const bool aligned = (MIS == 0 && sh == 0);
   for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nWords; w += stride)
     { const uint64_t b0 = w * 32;
       uint64_t word = 0;
-      if (b0 + 32 <= nBases && ALIGNED)
+      if (aligned && b0 + 32 <= nBases)
         { const uint4 *p = reinterpret_cast<const uint4 *>(in + b0);
           uint4 a = __ldg(p), b = __ldg(p + 1);
           const uint32_t v[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+          word = mg_pack32(v, ASCII);
+        }
+      else if (!aligned && b0 + 64 <= nBases)
+        { const uint4 *p = reinterpret_cast<const uint4 *>(in + b0 - (MIS * 4 + sh / 8));
+          uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+          const uint32_t q[12] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w };
+          uint32_t v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __funnelshift_r(q[MIS + j], q[MIS + j + 1], sh);
           word = mg_pack32(v, ASCII);
         }
       else if (b0 < nBases)
@@ -59,23 +72,28 @@ extern "C" uint64_t modgpuPackedWords(uint64_t nBases)
 
 extern "C" uint64_t modgpuEndsWords(uint64_t nBases) { return modgpuPackedWords(nBases); }
 
+template <bool ASCII>
+static void launch_pack(const uint8_t *d_bases, uint64_t nBases, uint64_t *d_packed, uint64_t nWords, dim3 grid, cudaStream_t st)
+{
+  const uint32_t mis = (uint32_t)(((uintptr_t)d_bases) & 15), sh = 8 * (mis & 3);
+  switch (mis >> 2)
+    { case 0: pack2bit_kernel<ASCII, 0><<<grid, 256, 0, st>>>(d_bases, nBases, d_packed, nWords, sh); break;
+      case 1: pack2bit_kernel<ASCII, 1><<<grid, 256, 0, st>>>(d_bases, nBases, d_packed, nWords, sh); break;
+      case 2: pack2bit_kernel<ASCII, 2><<<grid, 256, 0, st>>>(d_bases, nBases, d_packed, nWords, sh); break;
+      default: pack2bit_kernel<ASCII, 3><<<grid, 256, 0, st>>>(d_bases, nBases, d_packed, nWords, sh); break;
+    }
+}
+
 extern "C" int modgpuPack2bit(const uint8_t *d_bases, uint64_t nBases, int isAscii, uint64_t *d_packed, void *stream)
 {
   cudaStream_t st = (cudaStream_t)stream;
   const uint64_t nWords = modgpuPackedWords(nBases);
-  const bool aligned = (((uintptr_t)d_bases) & 15) == 0;
   uint64_t blocks = (nWords + 255) / 256;
   uint64_t maxBlocks = (uint64_t)mg_num_sms() * 16;
   if (blocks > maxBlocks) blocks = maxBlocks;
-  dim3 grid((unsigned)blocks), block(256);
-  if (isAscii)
-    { if (aligned) pack2bit_kernel<true, true><<<grid, block, 0, st>>>(d_bases, nBases, d_packed, nWords);
-      else pack2bit_kernel<true, false><<<grid, block, 0, st>>>(d_bases, nBases, d_packed, nWords);
-    }
-  else
-    { if (aligned) pack2bit_kernel<false, true><<<grid, block, 0, st>>>(d_bases, nBases, d_packed, nWords);
-      else pack2bit_kernel<false, false><<<grid, block, 0, st>>>(d_bases, nBases, d_packed, nWords);
-    }
+  dim3 grid((unsigned)blocks);
+  if (isAscii) launch_pack<true>(d_bases, nBases, d_packed, nWords, grid, st);
+  else launch_pack<false>(d_bases, nBases, d_packed, nWords, grid, st);
   MG_LAUNCH_CHECK("pack2bit");
   return MODGPU_OK;
 }

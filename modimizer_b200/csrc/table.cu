@@ -12,6 +12,7 @@
 // input ordinal when the reference's first-occurrence numbering is wanted).
 // Bound by random-sector L2/HBM atomic throughput, not by streaming bandwidth:
 // 20 algorithmic bytes per selected k-mer.
+#include <stdlib.h>
 #include "mg_device.cuh"
 #include "mg_scan.cuh"
 
@@ -241,6 +242,12 @@ extern "C" ModgpuTable *modgpuTableCreate(int bits, void *stream)
 {
   if (bits < 20 || bits > 34)                            // modset.c:17
     { mg_set_error("table bits %d must be between 20 and 34", bits); return nullptr; }
+  // random 16-byte probes: ask L2 to fetch 32-byte sectors instead of whole lines
+  // (MODGPU_L2_FETCH=32|64|128 overrides; measured in profiles/)
+  { const char *g = getenv("MODGPU_L2_FETCH");
+    size_t gran = g ? (size_t)atoi(g) : 0;
+    if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+  }
   ModgpuTable *t = new ModgpuTable();
   t->bits = bits;
   t->slotBits = (uint32_t)(bits - 1);
@@ -290,6 +297,8 @@ int mg_table_insert_dev(ModgpuTable *t, const uint64_t *d_kmers, const uint64_t 
   if (!nMax) return MODGPU_OK;
   if (exactOrder && nMax >= (1ull << 30) - 2)
     { mg_set_error("exact-order insert batch of %llu exceeds 2^30", (unsigned long long)nMax); return MODGPU_EINVAL; }
+  // two waves of resident blocks measured faster than one on B200 for this
+  // latency-bound probe loop (profiles/README.md, insert sweep)
   unsigned grid = grid_for(nMax, 16);
   if (exactOrder)
     table_insert_kernel<true><<<grid, 256, 0, st>>>(t->slots, t->slotBits, d_kmers, (const unsigned long long *)d_n, nMax, d_slot, t->dEntries, t->dError);

@@ -124,6 +124,35 @@ def test_pack_layout(mg, torch_cuda):
         assert np.array_equal(packed2[:nw], exp2), n
 
 
+def test_pack_misaligned_pointer(mg, torch_cuda):
+    """a batch that starts anywhere inside a resident buffer (any pointer alignment)"""
+    import ctypes as C
+    from modimizer_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(6)
+    n = 70001
+    dev = torch_cuda.device("cuda:0")
+    host = rng.integers(0, 4, n + 64).astype(np.uint8)
+    d = torch_cuda.from_numpy(host).to(dev)
+    words = lib.modgpuPackedWords(n)
+    out = torch_cuda.zeros(words, dtype=torch_cuda.int64, device=dev)
+    for off in list(range(0, 18)) + [31, 33, 47]:
+        for ascii_ in (0, 1):
+            src = host[off:off + n]
+            if ascii_:
+                asc = np.frombuffer(b"ACGT", np.uint8)[src]
+                d2 = torch_cuda.from_numpy(np.concatenate([np.zeros(off, np.uint8), asc, np.zeros(64, np.uint8)])).to(dev)
+                ptr = d2.data_ptr() + off
+            else:
+                ptr = d.data_ptr() + off
+            _lib.check(lib.modgpuPack2bit(ptr, n, ascii_, out.data_ptr(), torch_cuda.cuda.current_stream().cuda_stream))
+            torch_cuda.cuda.synchronize()
+            nw = (n + 31) // 32
+            exp = np.zeros(nw, np.uint64)
+            he.lib().hm_pack(np.ascontiguousarray(src), n, 0, exp, nw)
+            assert np.array_equal(out.cpu().numpy().view(np.uint64)[:nw], exp), (off, ascii_)
+
+
 @pytest.mark.parametrize("flags", [1, 0, 1 | 4, 4, 1 | 8, 8 | 4])
 def test_select_random_params(mg, torch_cuda, orc, flags):
     """property test: GPU selected list == the serial iterator's list, in order
