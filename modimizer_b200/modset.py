@@ -339,8 +339,9 @@ class Reference:
             a, b = int(so[r]), int(so[r + 1])
             miss, c1, c2, cm = (int(x) for x in res["counters"][r])
             nseed = b - a
-            frac = (nseed - miss) / float(nseed) if nseed else float("nan")
-            out.append("Q\t%s\t%d\t%d miss, %d copy1, %d copy2, %d multi, %.2f hit\n" % (names[r], lengths[r], miss, c1, c2, cm, frac))
+            # 0 seeds: the reference divides 0 by 0.0, which glibc's printf shows as "-nan" on x86-64
+            frac = ("%.2f" % ((nseed - miss) / float(nseed))) if nseed else "-nan"
+            out.append("Q\t%s\t%d\t%d miss, %d copy1, %d copy2, %d multi, %s hit\n" % (names[r], lengths[r], miss, c1, c2, cm, frac))
             if verbose:
                 for s in range(a, b):
                     h0, h1 = res["hitId"][s]

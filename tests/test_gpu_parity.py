@@ -397,3 +397,75 @@ def test_large_batch_properties(mg, torch_cuda):
     h = ms.histogram()
     assert int(h.sum()) == ms.max == len(v1)
     ms.close()
+
+
+# ------------------------------------------------------------------ golden --
+def _golden_cases():
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden as G
+    return G
+
+
+@pytest.mark.parametrize("name", sorted(_golden_cases().cases()))
+def test_gpu_matches_golden(mg, name):
+    """the CUDA path against the vectors generated from the unmodified reference
+    (tests/golden/golden_v1.json): identical lists, identical index numbering,
+    identical histogram / summary text / Reference arrays / query results"""
+    import json, os
+    from gpu_checker import GpuChecker
+    G = _golden_cases()
+    golden = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.json")))
+    got = json.loads(json.dumps(G.evaluate(GpuChecker(), name, G.cases()[name])))
+    assert got == golden[name]
+
+
+# --------------------------------------------------------------- multi-GPU --
+def _sharded_worker(rank, world, port, tmpdir):
+    import os, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.dirname(here)); sys.path.insert(0, here)
+    import torch, torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from modimizer_b200 import _lib
+    from modimizer_b200.dist import ShardedModset
+    _lib.check(_lib.load().modgpuSetDevice(rank))
+    import hostemul as he
+    sp = he.read_spec(12345, 200000, 3, 5000)
+    per = 600 // world
+    data = he.reads(sp, rank * per, per)
+    offs = np.arange(per + 1, dtype=np.uint64) * np.uint64(5000)
+    sm = ShardedModset(22, 19, 31, 17)
+    n1 = sm.add(data, offs)                                   # host path
+    d_b = torch.from_numpy(data).cuda(); d_o = torch.from_numpy(offs.view(np.int64)).cuda()
+    n2 = sm.add_device(d_b.data_ptr(), d_o.data_ptr(), per, len(data))   # device path, same data again
+    assert n1 == n2
+    v, d, i = sm.gather_sorted_dump()
+    h = sm.histogram()
+    gmax = sm.global_max()
+    if rank == 0:
+        np.savez(os.path.join(tmpdir, "sharded.npz"), v=v, d=d, h=h, gmax=gmax, sel=n1)
+    sm.close()
+    dist.destroy_process_group()
+
+
+def test_sharded_modset_two_gpus(mg, torch_cuda, orc, tmp_path):
+    """hash-sharded table over 2 GPUs, NCCL all-to-all: union == single-GPU == oracle"""
+    if torch_cuda.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_sharded_worker, args=(world, 29800 + os.getpid() % 1000, str(tmp_path)), nprocs=world, join=True)
+    r = np.load(os.path.join(str(tmp_path), "sharded.npz"))
+    sp = he.read_spec(12345, 200000, 3, 5000)
+    data = he.reads(sp, 0, 600)
+    offs = np.arange(601, dtype=np.uint64) * np.uint64(5000)
+    oms = orc.modset_new(22, 19, 31, 17)
+    orc.modset_add(oms, data, offs); orc.modset_add(oms, data, offs)        # every rank added its chunk twice
+    ov, od, _ = orc.modset_sorted(oms)
+    assert np.array_equal(r["v"], ov) and np.array_equal(r["d"], od)
+    assert np.array_equal(r["h"], orc.modset_hist(oms)) and int(r["gmax"]) == len(ov)
+    orc._modset_free(oms)
