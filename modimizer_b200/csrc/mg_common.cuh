@@ -277,6 +277,10 @@ MGHD uint64_t mg_slot_hash(uint64_t kmer, uint32_t slotBits)
 // multiplicative hash mapped uniformly onto [0, nOwners)
 MGHD uint32_t mg_owner(uint64_t kmer, uint32_t nOwners)
 {
-  uint64_t h = (kmer * 0xD6E8FEB86659FD93ull) >> 32;
-  return (uint32_t)((h * nOwners) >> 32);
+  const uint32_t h = (uint32_t)((kmer * 0xD6E8FEB86659FD93ull) >> 32);
+#if defined(__CUDA_ARCH__)
+  return __umulhi(h, nOwners);               // floor(h * nOwners / 2^32), always < nOwners
+#else
+  return (uint32_t)(((uint64_t)h * nOwners) >> 32);
+#endif
 }

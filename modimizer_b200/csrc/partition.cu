@@ -32,7 +32,9 @@ __global__ void __launch_bounds__(256) owner_count_kernel(const uint64_t *__rest
   __syncthreads();
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    atomicAdd(&sC[bucket_of<MODE>(kmers[i], a, b)], 1u);
+    { const uint32_t o = bucket_of<MODE>(kmers[i], a, b);
+      if (o < MG_MAX_OWNERS) atomicAdd(&sC[o], 1u);
+    }
   __syncthreads();
   if (threadIdx.x < nOwners && sC[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)sC[threadIdx.x]);
 }
