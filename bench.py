@@ -244,7 +244,7 @@ def run_ours(args):
     groups = []
     r0 = 0
     for r in range(1, args.records + 1):
-        if r == args.records or offs[r + 1] - offs[r0] > (1 << 31):
+        if r == args.records or offs[r + 1] - offs[r0] > (1 << 32) - (1 << 20):
             groups.append((r0, r)); r0 = r
     d_goffs = [torch.from_numpy((offs[a:b + 1] - offs[a]).view(np.int64)).to(dev) for a, b in groups]
 

@@ -22,13 +22,23 @@ int mg_table_insert_dev(ModgpuTable *t, const uint64_t *d_kmers, const uint64_t 
 int mg_table_lookup_dev(const ModgpuTable *t, const uint64_t *d_kmers, const uint64_t *d_n, uint64_t nMax,
                         uint32_t *d_out, cudaStream_t st);
 uint64_t mg_table_numbered(const ModgpuTable *t);
+int mg_table_insert_bulk(ModgpuTable *t, const uint64_t *d_kmers, uint64_t n, cudaStream_t st);
+struct MgBulk { uint32_t slotBits, regionBits, nRegions, cap; uint32_t *cursors; uint64_t *buckets, *overflow; uint64_t overflowCap; };
+int mg_table_bulk_begin(ModgpuTable *t, uint64_t expectedN, uint64_t maxN, MgBulk *b, cudaStream_t st);
+const uint32_t *mg_table_bulk_overflow_count(const ModgpuTable *t);
+int mg_table_bulk_finish(ModgpuTable *t, const MgBulk *b, cudaStream_t st);
+int mg_hash_select_scatter(const ModgpuHasher *h, const uint64_t *d_packed, const uint32_t *d_ends, uint64_t nBases,
+                           uint64_t *d_count, void *d_workspace, int flags, uint32_t slotBits, uint32_t regionBits,
+                           uint32_t bucketCap, uint32_t *d_cursors, uint64_t *d_buckets, uint64_t *d_overflow,
+                           uint64_t overflowCap, cudaStream_t st);
+uint64_t mg_table_bulk_threshold(const ModgpuTable *t);
 int mg_slot_partition(const uint64_t *d_kmers, uint64_t n, uint32_t slotBits, uint32_t bucketBits,
                       uint64_t *d_out, uint64_t *d_scratch, cudaStream_t st);
 int mg_table_classify(ModgpuTable *t, int mode, int c1, int c2, int cM, int zeroDepth, uint32_t *d_classCounts, cudaStream_t st);
 
 // bases per pipelined chunk when the batch comes from host memory / is resident
 static const uint64_t MG_HOST_CHUNK = 1ull << 28;
-static const uint64_t MG_DEV_CHUNK = 1ull << 31;
+static const uint64_t MG_DEV_CHUNK = (1ull << 32) - (1ull << 20);   // global offsets are 32-bit
 
 struct DevBuf {
   void *p = nullptr;
@@ -250,24 +260,26 @@ int mg_modset_select_chunk(ModgpuModset *ms, const uint8_t *d_bases, const uint6
   return MODGPU_OK;
 }
 
-// K3 with locality: when the table is much larger than L2 and the list is long,
-// group the k-mers by table region first (2 streaming passes over 8 B each) so
-// that the random probes of one region hit L2; order of insertion is free in
-// count mode.  Exact-order inserts keep the input order (ordinals matter).
+// K3, three ways:
+//  - bulk (default for long lists in count mode): scatter into per-region buckets,
+//    build every region in shared memory, stream the table once (table.cu);
+//  - direct: one random HBM probe per k-mer (short lists, and exact-order lists,
+//    whose input ordinals matter);
+//  - region-partitioned direct (A/B only, MODGPU flags bits 8..15 = 2..): group
+//    the list by 2^rb table regions first so that the probes of one region hit L2.
 static int insert_list(ModgpuModset *ms, const uint64_t *d_kmers, uint64_t n, uint32_t *dSlot)
 {
   int rc;
-  const uint64_t tableBytes = modgpuTableSlots(ms->table) * sizeof(MgSlot);
-  uint32_t slotBits = 0;
-  while ((1ull << slotBits) < modgpuTableSlots(ms->table)) ++slotBits;
-  int rb = ms->regionBits;
-  if (rb < 0)
-    { rb = 0;
-      if (!ms->exactOrder && tableBytes > (64ull << 20) && n >= (1ull << 20))
-        while ((tableBytes >> rb) > (8ull << 20) && rb < 8) ++rb;        // regions of <= 8 MiB (measured best)
+  const int rb = ms->regionBits;                       // -1 auto, 0 direct, 1..8 partitioned direct, 254 bulk
+  const bool bulk = !ms->exactOrder && (rb == 254 || (rb < 0 && n >= mg_table_bulk_threshold(ms->table)));
+  if (bulk)
+    { ProfScope p(ms, MODGPU_T_INSERT, 3);
+      return mg_table_insert_bulk(ms->table, d_kmers, n, ms->stream);
     }
-  if (rb > 0 && !ms->exactOrder)
-    { if ((rc = ms->kmers2.ensure(n * 8))) return rc;
+  if (rb > 0 && rb <= 8 && !ms->exactOrder)
+    { uint32_t slotBits = 0;
+      while ((1ull << slotBits) < modgpuTableSlots(ms->table)) ++slotBits;
+      if ((rc = ms->kmers2.ensure(n * 8))) return rc;
       uint64_t *scratch = (uint64_t *)((char *)ms->misc.p + 512);
       { ProfScope p(ms, MODGPU_T_INSERT, 3);
         if ((rc = mg_slot_partition(d_kmers, n, slotBits, (uint32_t)rb, (uint64_t *)ms->kmers2.p, scratch, ms->stream))) return rc;
@@ -278,11 +290,59 @@ static int insert_list(ModgpuModset *ms, const uint64_t *d_kmers, uint64_t n, ui
   return mg_table_insert_dev(ms->table, d_kmers, nullptr, n, dSlot, ms->exactOrder, ms->stream);
 }
 
+// count mode, long batch: K1 -> K2 with the selected k-mers scattered straight
+// into the table's per-region buckets -> shared-memory region build.  No list.
+// Returns 1 when the batch turned out too skewed for the buckets (nothing was
+// applied to the table; the caller falls back to the list path).
+static int add_chunk_fused(ModgpuModset *ms, const uint8_t *d_bases, const uint64_t *d_offs, uint64_t nSeq,
+                           uint64_t nBases, int isAscii, uint64_t expected, uint64_t *nHashes)
+{
+  cudaStream_t st = ms->stream;
+  const uint64_t words = modgpuPackedWords(nBases);
+  int rc;
+  if ((rc = ms->packed.ensure(words * 8)) || (rc = ms->ends.ensure(words * 4)) ||
+      (rc = ms->work.ensure(modgpuHashSelectWorkspace(nBases))))
+    return rc;
+  { ProfScope p(ms, MODGPU_T_PACK, 2);
+    if ((rc = modgpuPack2bit(d_bases, nBases, isAscii, (uint64_t *)ms->packed.p, st))) return rc;
+    if ((rc = modgpuMarkEnds(d_offs, nSeq, nBases, (uint32_t *)ms->ends.p, st))) return rc;
+  }
+  MgBulk b;
+  if ((rc = mg_table_bulk_begin(ms->table, expected, 2 * expected + 65536, &b, st))) return rc;
+  uint64_t *dCount = (uint64_t *)ms->misc.p;
+  volatile uint64_t *hCount = (volatile uint64_t *)ms->hMisc.p;
+  { ProfScope p(ms, MODGPU_T_SELECT, 1);
+    if ((rc = mg_hash_select_scatter(&ms->hasher, (const uint64_t *)ms->packed.p, (const uint32_t *)ms->ends.p, nBases, dCount,
+                                     ms->work.p, ms->selFlags, b.slotBits, b.regionBits, b.cap, b.cursors, b.buckets,
+                                     b.overflow, b.overflowCap, st)))
+      return rc;
+  }
+  MG_CUDA(cudaMemcpyAsync((void *)hCount, dCount, 8, cudaMemcpyDeviceToHost, st));
+  MG_CUDA(cudaMemcpyAsync((void *)(hCount + 1), mg_table_bulk_overflow_count(ms->table), 4, cudaMemcpyDeviceToHost, st));
+  MG_CUDA(cudaStreamSynchronize(st));
+  const uint64_t overflowed = hCount[1] & 0xFFFFFFFFull;
+  if (overflowed > b.overflowCap) return 1;              // skewed batch: buckets and overflow list too small
+  *nHashes = hCount[0];
+  { ProfScope p(ms, MODGPU_T_INSERT, 2);
+    if ((rc = mg_table_bulk_finish(ms->table, &b, st))) return rc;
+  }
+  ms->dirty = true;
+  return MODGPU_OK;
+}
+
 static int add_chunk_device(ModgpuModset *ms, const uint8_t *d_bases, const uint64_t *d_offs, uint64_t nSeq,
                             uint64_t nBases, int isAscii, uint64_t *nHashes)
 {
   uint64_t n = 0;
-  int rc = mg_modset_select_chunk(ms, d_bases, d_offs, nSeq, nBases, isAscii, false, 0, &n);
+  int rc;
+  const uint64_t expected = nBases / (uint64_t)ms->hasher.w;
+  const bool fuse = !ms->exactOrder && ms->hasher.w >= 4 && !(ms->selFlags & 0x10) &&
+                    (ms->regionBits == 254 || (ms->regionBits < 0 && expected >= mg_table_bulk_threshold(ms->table)));
+  if (fuse)
+    { rc = add_chunk_fused(ms, d_bases, d_offs, nSeq, nBases, isAscii, expected, nHashes);
+      if (rc <= 0) return rc;
+    }
+  rc = mg_modset_select_chunk(ms, d_bases, d_offs, nSeq, nBases, isAscii, false, 0, &n);
   if (rc) return rc;
   *nHashes = n;
   if (!n) return MODGPU_OK;

@@ -24,6 +24,7 @@
 //
 // Integer-issue bound, not HBM bound (0.25 + 8/d algorithmic bytes per base
 // against ~9-28 instructions per base) - see DESIGN.md for the roofline.
+#include <string.h>
 #include "mg_device.cuh"
 
 #define MG_TILE_PACK_BYTES (MG_TILE_THREADS * 8 + 16)     // 256 words + overlap word, 16 B multiple (258 words)
@@ -42,6 +43,13 @@ struct SelectParams {
   unsigned long long *count;   // device total
   uint64_t *status;            // look-back descriptors [nTiles]
   uint32_t *ticket;            // tile ticket
+  // SCATTER: selected k-mers go straight into the table's per-region buckets
+  // (table.cu bulk insert) instead of a list
+  uint32_t slotBits, regionBits, nRegions, bucketCap;
+  uint32_t *cursors;           // [nRegions] fill counts, [nRegions] = overflow count
+  uint64_t *buckets;
+  uint64_t *overflow;
+  uint64_t overflowCap;
 };
 
 // Phase 2 helper: evaluate queue entry e = (source thread << 5 | window) of the
@@ -65,7 +73,7 @@ __device__ __forceinline__ bool eval_entry(const MgKHasher &H, const uint64_t *s
 //     threads whatever the distribution of hits among the runs (a per-thread
 //     loop over its own hits costs max-over-lanes iterations per warp: measured
 //     2/3 of all issued instructions in the first version of this kernel).
-template <bool PREFILTER, bool ORDERED, bool TMA>
+template <bool PREFILTER, bool ORDERED, bool TMA, bool SCATTER>
 __global__ void __launch_bounds__(MG_TILE_THREADS) hash_select_kernel(const SelectParams P)
 {
   constexpr int NBUF = TMA ? 2 : 1;
@@ -183,6 +191,20 @@ __global__ void __launch_bounds__(MG_TILE_THREADS) hash_select_kernel(const Sele
                 }
               const uint32_t ballot = __ballot_sync(0xffffffffu, ok);
               if (!ballot) continue;
+              if (SCATTER)
+                { // fused K2 -> K3a: the atomic's round trip hides behind the other warps' hashing
+                  if (lane == 0) atomicAdd(P.count, (unsigned long long)__popc(ballot));
+                  if (ok)
+                    { const uint32_t region = (uint32_t)(mg_slot_hash(km, P.slotBits) >> P.regionBits);
+                      const uint32_t pos = atomicAdd(&P.cursors[region], 1u);
+                      if (pos < P.bucketCap) P.buckets[(uint64_t)region * P.bucketCap + pos] = km;
+                      else
+                        { const uint32_t o = atomicAdd(&P.cursors[P.nRegions], 1u);
+                          if (o < P.overflowCap) P.overflow[o] = km;
+                        }
+                    }
+                  continue;
+                }
               unsigned long long wbase = 0;
               if (lane == 0) wbase = atomicAdd(P.count, (unsigned long long)__popc(ballot));
               wbase = __shfl_sync(0xffffffffu, wbase, 0);
@@ -255,17 +277,17 @@ extern "C" uint64_t modgpuHashSelectWorkspace(uint64_t nBases)
 
 MgKHasher mg_khasher_from(const ModgpuHasher *h) { return mg_make_khasher(h->k, h->w, h->factor1); }
 
-template <bool PF, bool ORD, bool TMA>
+template <bool PF, bool ORD, bool TMA, bool SC = false>
 static int launch_select(const SelectParams &P, cudaStream_t st)
 {
   static int blocksPerSm = 0;
   if (!blocksPerSm)
-    { MG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, hash_select_kernel<PF, ORD, TMA>, MG_TILE_THREADS, 0));
+    { MG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, hash_select_kernel<PF, ORD, TMA, SC>, MG_TILE_THREADS, 0));
       if (blocksPerSm < 1) blocksPerSm = 1;
     }
   uint64_t grid = (uint64_t)mg_num_sms() * blocksPerSm;
   if (grid > P.nTiles) grid = P.nTiles;
-  hash_select_kernel<PF, ORD, TMA><<<(unsigned)grid, MG_TILE_THREADS, 0, st>>>(P);
+  hash_select_kernel<PF, ORD, TMA, SC><<<(unsigned)grid, MG_TILE_THREADS, 0, st>>>(P);
   MG_LAUNCH_CHECK("hash_select");
   return MODGPU_OK;
 }
@@ -280,6 +302,7 @@ extern "C" int modgpuHashSelect(const ModgpuHasher *h, const uint64_t *d_packed,
   MG_CUDA(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
   if (!nBases) return MODGPU_OK;
   SelectParams P;
+  memset(&P, 0, sizeof(P));
   P.H = mg_khasher_from(h);
   P.packed = d_packed; P.ends = d_ends; P.nBases = nBases;
   uint64_t words = (nBases + 31) / 32;
@@ -300,6 +323,36 @@ extern "C" int modgpuHashSelect(const ModgpuHasher *h, const uint64_t *d_packed,
   MG_SEL_CASE(false, false, true) MG_SEL_CASE(false, false, false)
 #undef MG_SEL_CASE
   return MODGPU_EINVAL;
+}
+
+// K2 fused with the bucket scatter of the bulk insert (count mode): no list.
+// cursors must be zeroed by the caller; *d_count receives the number selected.
+int mg_hash_select_scatter(const ModgpuHasher *h, const uint64_t *d_packed, const uint32_t *d_ends, uint64_t nBases,
+                           uint64_t *d_count, void *d_workspace, int flags, uint32_t slotBits, uint32_t regionBits,
+                           uint32_t bucketCap, uint32_t *d_cursors, uint64_t *d_buckets, uint64_t *d_overflow,
+                           uint64_t overflowCap, cudaStream_t st)
+{
+  if (nBases >= (1ull << 32)) { mg_set_error("hash_select: batch of %llu bases exceeds 2^32-1", (unsigned long long)nBases); return MODGPU_EINVAL; }
+  MG_CUDA(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
+  if (!nBases) return MODGPU_OK;
+  SelectParams P;
+  memset(&P, 0, sizeof(P));
+  P.H = mg_khasher_from(h);
+  P.packed = d_packed; P.ends = d_ends; P.nBases = nBases;
+  uint64_t words = (nBases + 31) / 32;
+  P.nTiles = (uint32_t)((words + MG_TILE_THREADS - 1) / MG_TILE_THREADS);
+  P.count = (unsigned long long *)d_count;
+  P.ticket = (uint32_t *)d_workspace;
+  P.status = (uint64_t *)((char *)d_workspace + 64);
+  P.slotBits = slotBits; P.regionBits = regionBits; P.nRegions = 1u << (slotBits - regionBits); P.bucketCap = bucketCap;
+  P.cursors = d_cursors; P.buckets = d_buckets; P.overflow = d_overflow; P.overflowCap = overflowCap;
+  MG_CUDA(cudaMemsetAsync(d_workspace, 0, 64, st));
+  const bool pf = P.H.prefilter && !(flags & MODGPU_SEL_NOPREFILTER);
+  const bool tma = !(flags & MODGPU_SEL_NOTMA);
+  if (pf && tma) return launch_select<true, false, true, true>(P, st);
+  if (pf) return launch_select<true, false, false, true>(P, st);
+  if (tma) return launch_select<false, false, true, true>(P, st);
+  return launch_select<false, false, false, true>(P, st);
 }
 
 // ---------------------------------------------------------------- locate --

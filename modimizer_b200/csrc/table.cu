@@ -10,7 +10,13 @@
 // slots per 32-byte sector so find-or-insert + count touches ONE sector.
 // Insert = read key, atomicCAS on EMPTY, RED.ADD on the count (+ RED.MIN of the
 // input ordinal when the reference's first-occurrence numbering is wanted).
-// Bound by random-sector L2/HBM atomic throughput, not by streaming bandwidth:
+// Probing is linear but confined to an aligned REGION of 2048 slots (32 KiB), so
+// that a region is a self-contained sub-table: small batches insert straight
+// into HBM (one random sector per probe, bound by random-access throughput,
+// ~14 G inserts/s measured, profiles/atomic_roofline_r01.txt); large batches are
+// scattered into per-region buckets and every region is built in SHARED MEMORY
+// by one block and written back with coalesced 16-byte stores, which turns the
+// table traffic into two streaming passes (region_build_kernel).
 // 20 algorithmic bytes per selected k-mer.
 #include <stdlib.h>
 #include "mg_device.cuh"
@@ -28,7 +34,18 @@ struct ModgpuTable {
   uint64_t scratchWords;
   uint64_t numbered;         // host: highest dense index handed out
   unsigned long long *hPinned;    // pinned readback word(s)
+  bool clearPending;         // the table is logically empty but the slots were not rewritten yet
+  uint64_t *dBuckets;        // bulk insert: per-region buckets of k-mers
+  uint64_t bucketBytes;
+  uint32_t *dCursors;        // bulk insert: per-region fill counts (+ overflow count at [nRegions])
+  uint64_t *dOverflow;       // k-mers that did not fit their bucket
+  uint64_t overflowCap;
 };
+
+#define MG_REGION_BITS 11
+#define MG_REGION_SLOTS (1u << MG_REGION_BITS)
+__device__ __forceinline__ uint64_t next_slot(uint64_t s)
+{ return (s & ~(uint64_t)(MG_REGION_SLOTS - 1)) | ((s + 1) & (MG_REGION_SLOTS - 1)); }
 
 // ------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(256) table_clear_kernel(MgSlot *slots, uint64_t nSlots)
@@ -43,10 +60,9 @@ __global__ void __launch_bounds__(256) table_clear_kernel(MgSlot *slots, uint64_
 // find-or-insert; returns the slot or UINT64_MAX when the table is full
 __device__ __forceinline__ uint64_t probe_insert(MgSlot *slots, uint32_t slotBits, uint64_t key, bool *isNew)
 {
-  const uint64_t maskS = (1ull << slotBits) - 1;
   uint64_t s = mg_slot_hash(key, slotBits);
   *isNew = false;
-  for (uint64_t probes = 0; probes <= maskS; ++probes, s = (s + 1) & maskS)
+  for (uint32_t probes = 0; probes < MG_REGION_SLOTS; ++probes, s = next_slot(s))
     { unsigned long long *kp = reinterpret_cast<unsigned long long *>(&slots[s].key);
       unsigned long long cur = __ldcg(kp);
       if (cur == key) return s;
@@ -61,9 +77,8 @@ __device__ __forceinline__ uint64_t probe_insert(MgSlot *slots, uint32_t slotBit
 
 __device__ __forceinline__ uint64_t probe_find(const MgSlot *slots, uint32_t slotBits, uint64_t key)
 {
-  const uint64_t maskS = (1ull << slotBits) - 1;
   uint64_t s = mg_slot_hash(key, slotBits);
-  for (uint64_t probes = 0; probes <= maskS; ++probes, s = (s + 1) & maskS)
+  for (uint32_t probes = 0; probes < MG_REGION_SLOTS; ++probes, s = next_slot(s))
     { unsigned long long cur = __ldcg(reinterpret_cast<const unsigned long long *>(&slots[s].key));
       if (cur == key) return s;
       if (cur == MG_EMPTY) break;
@@ -111,6 +126,74 @@ __global__ void __launch_bounds__(256) table_lookup_kernel(const MgSlot *slots, 
       uint64_t s = probe_find(slots, slotBits, key);
       out[i] = (s == 0xFFFFFFFFFFFFFFFFull) ? 0u : __ldcg(&slots[s].aux);
     }
+}
+
+// ---- bulk insert: scatter into per-region buckets, build regions in smem ----
+// cursors[region] counts the k-mers aimed at the region; the first `cap` of them
+// land in its bucket, the rest in the overflow list (cursors[nRegions] counts it).
+__global__ void __launch_bounds__(256) bucket_scatter_kernel(const uint64_t *__restrict__ kmers, uint64_t n, uint32_t slotBits,
+                                                             uint32_t nRegions, uint32_t cap, uint32_t *cursors,
+                                                             uint64_t *__restrict__ buckets, uint64_t *__restrict__ overflow,
+                                                             uint64_t overflowCap, uint32_t *error)
+{
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    { const uint64_t key = kmers[i] & 0x3FFFFFFFFFFFFFFFull;
+      const uint32_t region = (uint32_t)(mg_slot_hash(key, slotBits) >> MG_REGION_BITS);
+      const uint32_t pos = atomicAdd(&cursors[region], 1u);
+      if (pos < cap) buckets[(uint64_t)region * cap + pos] = key;
+      else
+        { const uint32_t o = atomicAdd(&cursors[nRegions], 1u);
+          if (o < overflowCap) overflow[o] = key; else atomicExch(error, 1u);
+        }
+    }
+}
+
+// one block builds one region: load (or, for a logically empty table, create)
+// its 2048 slots in shared memory, insert + count the bucket with shared-memory
+// atomics, store the region back.  Streaming, coalesced, 16 bytes per thread.
+template <bool FRESH>
+__global__ void __launch_bounds__(256) region_build_kernel(MgSlot *slots, uint32_t slotBits, const uint64_t *__restrict__ buckets,
+                                                           const uint32_t *__restrict__ cursors, uint32_t cap,
+                                                           unsigned long long *entries, uint32_t *error)
+{
+  __shared__ uint4 sR[MG_REGION_SLOTS];
+  const uint32_t region = blockIdx.x;
+  uint4 *g = reinterpret_cast<uint4 *>(slots) + (uint64_t)region * MG_REGION_SLOTS;
+  uint32_t cnt = cursors[region];
+  if (cnt > cap) cnt = cap;
+  if (!FRESH && cnt == 0) return;                              // nothing to add: leave the region alone
+  uint4 e;
+  e.x = 0xFFFFFFFFu; e.y = 0xFFFFFFFFu; e.z = 0u; e.w = MG_AUX_FRESH;
+#pragma unroll
+  for (int i = 0; i < MG_REGION_SLOTS / 256; ++i)
+    sR[i * 256 + threadIdx.x] = FRESH ? e : __ldcs(g + i * 256 + threadIdx.x);
+  __syncthreads();
+  MgSlot *sS = reinterpret_cast<MgSlot *>(sR);
+  const uint64_t *b = buckets + (uint64_t)region * cap;
+  uint32_t fresh = 0;
+  for (uint32_t j = threadIdx.x; j < cnt; j += 256)
+    { const unsigned long long key = b[j];
+      uint32_t s = (uint32_t)mg_slot_hash(key, slotBits) & (MG_REGION_SLOTS - 1);
+      uint32_t probes = 0;
+      for (; probes < MG_REGION_SLOTS; ++probes, s = (s + 1) & (MG_REGION_SLOTS - 1))
+        { unsigned long long *kp = reinterpret_cast<unsigned long long *>(&sS[s].key);
+          unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(kp);
+          if (cur == key) break;
+          if (cur == MG_EMPTY)
+            { unsigned long long old = atomicCAS(kp, MG_EMPTY, key);
+              if (old == MG_EMPTY) { ++fresh; break; }
+              if (old == key) break;
+            }
+        }
+      if (probes == MG_REGION_SLOTS) { atomicExch(error, 1u); continue; }
+      atomicAdd(&sS[s].count, 1u);
+    }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < MG_REGION_SLOTS / 256; ++i) __stcs(g + i * 256 + threadIdx.x, sR[i * 256 + threadIdx.x]);
+  fresh = mg_warp_sum(fresh);
+  if (mg_lane() == 0 && fresh) atomicAdd(entries, (unsigned long long)fresh);
 }
 
 // ---- numbering: rank the not-yet-numbered entries (mg_scan.cuh) ------------
@@ -256,6 +339,7 @@ extern "C" ModgpuTable *modgpuTableCreate(int bits, void *stream)
   if (t->maxEntries > MG_MAX_INDEX) t->maxEntries = MG_MAX_INDEX;
   t->numbered = 0;
   t->slots = nullptr; t->dEntries = nullptr; t->dError = nullptr; t->dScratch = nullptr; t->hPinned = nullptr;
+  t->clearPending = false; t->dBuckets = nullptr; t->bucketBytes = 0; t->dCursors = nullptr; t->dOverflow = nullptr; t->overflowCap = 0;
   t->scratchWords = t->nSlots / MG_CP_CHUNK + 1024;
   if (mg_check_cuda(cudaMalloc(&t->slots, t->nSlots * sizeof(MgSlot)), "cudaMalloc(table)", __FILE__, __LINE__) ||
       mg_check_cuda(cudaMalloc(&t->dEntries, 64), "cudaMalloc", __FILE__, __LINE__) ||
@@ -274,27 +358,119 @@ extern "C" void modgpuTableDestroy(ModgpuTable *t)
   if (t->dEntries) cudaFree(t->dEntries);
   if (t->dScratch) cudaFree(t->dScratch);
   if (t->hPinned) cudaFreeHost(t->hPinned);
+  if (t->dBuckets) cudaFree(t->dBuckets);
+  if (t->dCursors) cudaFree(t->dCursors);
+  if (t->dOverflow) cudaFree(t->dOverflow);
   delete t;
+}
+
+// The clear is lazy: a bulk insert into a logically empty table creates every
+// region itself (region_build_kernel<true>), so the separate 16 B/slot clearing
+// pass only runs when something else touches the table first.
+static int ensure_cleared(ModgpuTable *t, cudaStream_t st)
+{
+  if (!t->clearPending) return MODGPU_OK;
+  table_clear_kernel<<<grid_for(t->nSlots, 16), 256, 0, st>>>(t->slots, t->nSlots);
+  MG_LAUNCH_CHECK("table_clear");
+  t->clearPending = false;
+  return MODGPU_OK;
 }
 
 extern "C" int modgpuTableClear(ModgpuTable *t, void *stream)
 {
   cudaStream_t st = (cudaStream_t)stream;
-  table_clear_kernel<<<grid_for(t->nSlots, 16), 256, 0, st>>>(t->slots, t->nSlots);
-  MG_LAUNCH_CHECK("table_clear");
   MG_CUDA(cudaMemsetAsync(t->dEntries, 0, 64, st));
   t->numbered = 0;
+  t->clearPending = true;
   return MODGPU_OK;
 }
 
+// ---- bulk insert in three steps, so that hash_select can do the scatter itself:
+//   mg_table_bulk_begin   size + zero the per-region buckets for ~expectedN k-mers
+//   (scatter)             bucket_scatter_kernel on a list, or hash_select<SCATTER>
+//   mg_table_bulk_finish  build every region in shared memory, then the overflow
+struct MgBulk { uint32_t slotBits, regionBits, nRegions, cap; uint32_t *cursors; uint64_t *buckets, *overflow; uint64_t overflowCap; };
+
+int mg_table_bulk_begin(ModgpuTable *t, uint64_t expectedN, uint64_t maxN, MgBulk *b, cudaStream_t st)
+{
+  const uint32_t nRegions = (uint32_t)(t->nSlots >> MG_REGION_BITS);
+  uint64_t cap64 = expectedN / nRegions + expectedN / (4ull * nRegions) + 64;
+  cap64 = (cap64 + 1) & ~1ull;
+  if (cap64 > 0x7FFFFFFFull) { mg_set_error("bulk insert: bucket capacity overflow"); return MODGPU_EINVAL; }
+  const uint64_t needBuckets = (uint64_t)nRegions * cap64 * sizeof(uint64_t);
+  if (needBuckets > t->bucketBytes)
+    { if (t->dBuckets) cudaFree(t->dBuckets);
+      t->dBuckets = nullptr; t->bucketBytes = 0;
+      MG_CUDA(cudaMalloc(&t->dBuckets, needBuckets + needBuckets / 8));
+      t->bucketBytes = needBuckets + needBuckets / 8;
+    }
+  if (!t->dCursors) MG_CUDA(cudaMalloc(&t->dCursors, ((size_t)nRegions + 16) * sizeof(uint32_t)));
+  const uint64_t needOvf = maxN + 1024;                  // a list of maxN can overflow entirely (one hot k-mer)
+  if (needOvf > t->overflowCap)
+    { if (t->dOverflow) cudaFree(t->dOverflow);
+      t->dOverflow = nullptr; t->overflowCap = 0;
+      MG_CUDA(cudaMalloc(&t->dOverflow, needOvf * sizeof(uint64_t)));
+      t->overflowCap = needOvf;
+    }
+  MG_CUDA(cudaMemsetAsync(t->dCursors, 0, ((size_t)nRegions + 16) * sizeof(uint32_t), st));
+  b->slotBits = t->slotBits; b->regionBits = MG_REGION_BITS; b->nRegions = nRegions; b->cap = (uint32_t)cap64;
+  b->cursors = t->dCursors; b->buckets = t->dBuckets; b->overflow = t->dOverflow; b->overflowCap = t->overflowCap;
+  return MODGPU_OK;
+}
+
+// number of k-mers that missed their bucket in the last scatter (device word, uint32)
+const uint32_t *mg_table_bulk_overflow_count(const ModgpuTable *t) { return t->dCursors + (t->nSlots >> MG_REGION_BITS); }
+
+int mg_table_bulk_finish(ModgpuTable *t, const MgBulk *b, cudaStream_t st)
+{
+  if (t->clearPending)
+    { region_build_kernel<true><<<b->nRegions, 256, 0, st>>>(t->slots, t->slotBits, b->buckets, b->cursors, b->cap, t->dEntries, t->dError);
+      t->clearPending = false;
+    }
+  else
+    region_build_kernel<false><<<b->nRegions, 256, 0, st>>>(t->slots, t->slotBits, b->buckets, b->cursors, b->cap, t->dEntries, t->dError);
+  MG_LAUNCH_CHECK("region_build");
+  // stragglers of over-full buckets go straight into HBM; their number is only known on the device:
+  // the insert kernel reads it as the 64-bit word {cursors[nRegions], cursors[nRegions+1] == 0}
+  table_insert_kernel<false><<<grid_for(65536, 4), 256, 0, st>>>(
+      t->slots, t->slotBits, b->overflow, reinterpret_cast<const unsigned long long *>(b->cursors + b->nRegions),
+      b->overflowCap, nullptr, t->dEntries, t->dError);
+  MG_LAUNCH_CHECK("overflow_insert");
+  return MODGPU_OK;
+}
+
+// Bulk find-or-insert + count of a long list (count mode, any order): 8 B read +
+// 8 B written per k-mer for the scatter, then one streaming pass over the table.
+int mg_table_insert_bulk(ModgpuTable *t, const uint64_t *d_kmers, uint64_t n, cudaStream_t st)
+{
+  if (!n) return MODGPU_OK;
+  MgBulk b;
+  int rc = mg_table_bulk_begin(t, n, n, &b, st);
+  if (rc) return rc;
+  bucket_scatter_kernel<<<grid_for(n, 16), 256, 0, st>>>(d_kmers, n, t->slotBits, b.nRegions, b.cap, b.cursors, b.buckets,
+                                                         b.overflow, b.overflowCap, t->dError);
+  MG_LAUNCH_CHECK("bucket_scatter");
+  return mg_table_bulk_finish(t, &b, st);
+}
+
+uint64_t mg_table_bulk_threshold(const ModgpuTable *t) { return t->nSlots / 8; }
+
 extern "C" uint64_t modgpuTableSlots(const ModgpuTable *t) { return t->nSlots; }
-extern "C" void *modgpuTableDevicePtr(const ModgpuTable *t) { return t->slots; }
+extern "C" void *modgpuTableDevicePtr(const ModgpuTable *t)
+{
+  if (t->clearPending)
+    { ensure_cleared(const_cast<ModgpuTable *>(t), 0);
+      cudaStreamSynchronize(0);
+    }
+  return t->slots;
+}
 
 // internal: insert with the element count taken from device memory
 int mg_table_insert_dev(ModgpuTable *t, const uint64_t *d_kmers, const uint64_t *d_n, uint64_t nMax,
                         uint32_t *d_slot, int exactOrder, cudaStream_t st)
 {
   if (!nMax) return MODGPU_OK;
+  { int rc = ensure_cleared(t, st); if (rc) return rc; }
   if (exactOrder && nMax >= (1ull << 30) - 2)
     { mg_set_error("exact-order insert batch of %llu exceeds 2^30", (unsigned long long)nMax); return MODGPU_EINVAL; }
   // two waves of resident blocks measured faster than one on B200 for this
@@ -354,6 +530,7 @@ static int run_compaction(ModgpuTable *t, F f, uint64_t n, uint64_t *totalOut, c
 extern "C" int modgpuTableNumber(ModgpuTable *t, const uint32_t *d_slot, uint64_t n, uint32_t *d_index, void *stream)
 {
   cudaStream_t st = (cudaStream_t)stream;
+  { int rc = ensure_cleared(t, st); if (rc) return rc; }
   uint64_t added = 0;
   if (d_slot)
     { if (n)
@@ -386,6 +563,7 @@ int mg_table_lookup_dev(const ModgpuTable *t, const uint64_t *d_kmers, const uin
                         uint32_t *d_out, cudaStream_t st)
 {
   if (!nMax) return MODGPU_OK;
+  { int rc = ensure_cleared(const_cast<ModgpuTable *>(t), st); if (rc) return rc; }
   table_lookup_kernel<<<grid_for(nMax, 16), 256, 0, st>>>(t->slots, t->slotBits, d_kmers, (const unsigned long long *)d_n, nMax, d_out);
   MG_LAUNCH_CHECK("table_lookup");
   return MODGPU_OK;
@@ -400,6 +578,7 @@ extern "C" int modgpuTableHistogram(const ModgpuTable *t, uint32_t *d_bins65536,
 {
   cudaStream_t st = (cudaStream_t)stream;
   MG_CUDA(cudaMemsetAsync(d_bins65536, 0, 65536 * sizeof(uint32_t), st));
+  { int rc = ensure_cleared(const_cast<ModgpuTable *>(t), st); if (rc) return rc; }
   table_hist_kernel<<<grid_for(t->nSlots, 8), 256, 0, st>>>(t->slots, t->nSlots, d_bins65536);
   MG_LAUNCH_CHECK("table_hist");
   return MODGPU_OK;
@@ -409,6 +588,7 @@ extern "C" int modgpuTableHistogram(const ModgpuTable *t, uint32_t *d_bins65536,
 int mg_table_classify(ModgpuTable *t, int mode, int c1, int c2, int cM, int zeroDepth, uint32_t *d_classCounts, cudaStream_t st)
 {
   if (d_classCounts) MG_CUDA(cudaMemsetAsync(d_classCounts, 0, 4 * sizeof(uint32_t), st));
+  { int rc = ensure_cleared(t, st); if (rc) return rc; }
   table_classify_kernel<<<grid_for(t->nSlots, 8), 256, 0, st>>>(t->slots, t->nSlots, mode, c1, c2, cM, zeroDepth, d_classCounts);
   MG_LAUNCH_CHECK("table_classify");
   return MODGPU_OK;
@@ -423,6 +603,7 @@ extern "C" int modgpuTableClassify(ModgpuTable *t, int c1, int c2, int cM, int e
 extern "C" int modgpuTableExport(ModgpuTable *t, uint64_t *d_value, uint16_t *d_depth, uint8_t *d_info,
                                  uint32_t *d_count32, void *stream)
 {
+  { int rc = ensure_cleared(t, (cudaStream_t)stream); if (rc) return rc; }
   table_export_kernel<<<grid_for(t->nSlots, 8), 256, 0, (cudaStream_t)stream>>>(t->slots, t->nSlots, d_value, d_depth, d_info, d_count32);
   MG_LAUNCH_CHECK("table_export");
   return MODGPU_OK;
@@ -434,6 +615,7 @@ extern "C" int modgpuTableImport(ModgpuTable *t, const uint64_t *d_value, const 
   if (!n) return MODGPU_OK;
   if (t->numbered + n > t->maxEntries)
     { mg_set_error("Modset size %llu is too big for %d bits", (unsigned long long)(t->numbered + n), t->bits); return MODGPU_EFULL; }
+  { int rc = ensure_cleared(t, (cudaStream_t)stream); if (rc) return rc; }
   table_import_kernel<<<grid_for(n, 16), 256, 0, (cudaStream_t)stream>>>(t->slots, t->slotBits, d_value, d_depth, d_info, n, t->numbered, t->dEntries, t->dError);
   MG_LAUNCH_CHECK("table_import");
   t->numbered += n;

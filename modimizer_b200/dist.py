@@ -82,6 +82,10 @@ class ShardedModset:
 
     def add_device(self, d_bases, d_offsets, nseq, nbases, is_ascii=0):
         """this rank's chunk, resident in device memory (< 2^32 bases per call)"""
+        if self.world == 1:                      # nothing to route: the single-GPU pipeline (fused select -> table)
+            n = self.local.add_device(d_bases, d_offsets, nseq, nbases, is_ascii)
+            self.total_selected += n
+            return n
         kptr = C.c_void_p()
         n = C.c_uint64()
         check(self._lib.modgpuModsetSelectDevice(self.local._p, C.c_void_p(d_bases), C.c_void_p(d_offsets), nseq, nbases,
@@ -95,6 +99,10 @@ class ShardedModset:
         return self.add_pointers(data.ctypes.data, offsets.ctypes.data, len(offsets) - 1, is_ascii)
 
     def add_pointers(self, host_ptr, offsets_ptr, nseq, is_ascii=0):
+        if self.world == 1:
+            n = self.local.add_pointers(host_ptr, offsets_ptr, nseq, is_ascii)
+            self.total_selected += n
+            return n
         kptr = C.c_void_p()
         n = C.c_uint64()
         check(self._lib.modgpuModsetSelectHost(self.local._p, C.c_void_p(host_ptr), C.c_void_p(offsets_ptr), nseq,

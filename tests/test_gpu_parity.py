@@ -255,6 +255,34 @@ def test_modset_build_count(mg, orc, exact):
         ms.close(); orc._modset_free(oms)
 
 
+@pytest.mark.parametrize("mode", ["bulk", "bulk_nofuse", "direct", "partitioned"])
+def test_insert_paths_agree(mg, orc, mode):
+    """the three insert strategies (shared-memory region build, direct HBM probes,
+    region-partitioned direct) give the oracle's modset: fresh table, repeated
+    adds into a populated table, heavy skew (bucket overflow), histogram"""
+    flags = {"bulk": 255 << 8, "bulk_nofuse": (255 << 8) | 16, "direct": 1 << 8, "partitioned": 7 << 8}[mode]
+    sp = he.read_spec(12345, 300000, 42, 3000, 2000)
+    nreads = 2500
+    data = he.reads(sp, 0, nreads)
+    offs = np.arange(nreads + 1, dtype=np.uint64) * np.uint64(3000)
+    skew = np.zeros(200000, np.uint8)                     # poly-A: one k-mer, 200k times
+    skew[100000:100050] = 1
+    ms = mg.Modset(22, 19, 4, 17)
+    ms.set_flags(flags)
+    oms = orc.modset_new(22, 19, 4, 17)
+    try:
+        for (d_, o_) in ((data, offs), (data[:3000 * 900], offs[:901]), (skew, np.array([0, 200000], np.uint64)), (data, offs)):
+            assert ms.add(d_, o_, is_ascii=0) == orc.modset_add(oms, d_, o_)
+            assert ms.max == orc._modset_max(oms)
+        gv, gd, gi = ms.sorted_dump(); ov, od, oi = orc.modset_sorted(oms)
+        assert np.array_equal(gv, ov) and np.array_equal(gd, od)
+        assert np.array_equal(ms.histogram(), orc.modset_hist(oms))
+        idx, _ = ms.find(np.concatenate([ov[::50], ov[::50] ^ np.uint64(3)]))
+        assert (idx[:len(ov[::50])] != 0).all()
+    finally:
+        ms.close(); orc._modset_free(oms)
+
+
 def test_modset_edge_cases(mg, orc):
     rng = np.random.default_rng(3)
     # empty batch, empty reads, len<k, len==k, palindromes, d = 1 (every k-mer), k = 1
