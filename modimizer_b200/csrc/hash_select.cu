@@ -58,38 +58,73 @@ __device__ __forceinline__ bool eval_entry(const MgKHasher &H, const uint64_t *s
                                            uint64_t *km, bool *isF)
 {
   const uint32_t src = e >> 5, bit = e & 31u;
-  const MgRun R = mg_run_prepare(sWords[src], sWords[src + 1], H.k);
-  return mg_eval_window(H, R, bit, km, isF);
+  return mg_eval_single(H, sWords[src], sWords[src + 1], bit, km, isF);
 }
 
-// One tile in three phases:
-//  1. every thread scans its run of 32 window starts into a bit mask: with the
-//     PREFILTER the candidates (cheap low-word test), otherwise the windows
-//     that are selected (full canonical test);
+// One tile (256 runs = 8192 window starts) in three phases, by 128 threads
+// owning two consecutive runs each (halves the per-run bookkeeping):
+//  1. every thread scans its runs into bit masks: with the PREFILTER the
+//     candidates (cheap low-word test, 7 instructions per window), otherwise
+//     the windows that are selected (full canonical test);
 //  2. the set bits of the whole tile are compacted into a shared-memory queue
 //     in position order (one block scan), so that
 //  3. the expensive part - full 64-bit evaluation of a candidate, extraction
-//     of the winning strand's k-mer, the store - is spread evenly over the 256
+//     of the winning strand's k-mer, the store - is spread evenly over the
 //     threads whatever the distribution of hits among the runs (a per-thread
 //     loop over its own hits costs max-over-lanes iterations per warp: measured
 //     2/3 of all issued instructions in the first version of this kernel).
+//     Tiles with more hits than the queue holds (d < 4, pathological
+//     sequence) take the per-thread loop instead.
+#define MG_SEL_THREADS 128
+#define MG_SEL_RPT (MG_TILE_THREADS / MG_SEL_THREADS)          // runs per thread = 2
+#define MG_QUEUE_CAP 4096
+#define MG_SEL_ROUNDS 4                                          // queue entries a thread keeps in registers
+
+template <bool PREFILTER>
+__device__ __forceinline__ uint32_t scan_run(const MgKHasher &H, const MgRun &R)
+{
+  uint32_t m = 0;
+  if (PREFILTER)
+    {
+#pragma unroll
+      for (int i = 0; i < MG_RUN; ++i)
+        { // candidate <=> min(low product word of fwd, of rc) < pfLim; one predicated OR per window
+          const uint32_t pf = mg_run_fwd_lo(R, i) * H.pfMul, pr = mg_run_rc_lo(R, i) * H.pfMul;
+          const uint32_t mn = min(pf, pr);
+          asm("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}"
+              : "+r"(m) : "r"(mn), "r"(H.pfLim), "r"(1u << i));
+        }
+    }
+  else
+    {
+#pragma unroll
+      for (int i = 0; i < MG_RUN; ++i)
+        { uint64_t km; bool isF;
+          if (mg_eval_window(H, R, i, &km, &isF)) m |= 1u << i;
+        }
+    }
+  return m;
+}
+
 template <bool PREFILTER, bool ORDERED, bool TMA, bool SCATTER>
-__global__ void __launch_bounds__(MG_TILE_THREADS) hash_select_kernel(const SelectParams P)
+__global__ void __launch_bounds__(MG_SEL_THREADS) hash_select_kernel(const SelectParams P)
 {
   constexpr int NBUF = TMA ? 2 : 1;
+  constexpr int NWARPS = MG_SEL_THREADS / 32;
   __shared__ __align__(128) uint64_t sPack[NBUF][MG_TILE_PACK_BYTES / 8];
   __shared__ __align__(128) uint32_t sEnds[TMA ? 2 : 1][TMA ? (MG_TILE_ENDS_BYTES / 4) : 4];
   __shared__ __align__(8) uint64_t sBar[2];
-  __shared__ uint16_t sQueue[MG_TILE_BASES];
+  __shared__ uint16_t sQueue[MG_QUEUE_CAP];
   __shared__ uint32_t sSel[ORDERED ? MG_TILE_THREADS : 1];     // ORDERED: selected windows per run
   __shared__ uint32_t sDst[ORDERED ? MG_TILE_THREADS : 1];     // ORDERED: output offset of each run
   __shared__ uint32_t sTile[2];
-  __shared__ uint32_t sWarp[MG_TILE_THREADS / 32];
+  __shared__ uint32_t sWarp[NWARPS];
   __shared__ uint64_t sBase;
 
   const MgKHasher &H = P.H;
   const uint32_t tid = threadIdx.x;
   const uint32_t lane = tid & 31;
+  uint32_t nSelectedLocal = 0;                             // SCATTER: this thread's share of the total
 
   if (tid == 0)
     { if (TMA)
@@ -124,78 +159,132 @@ __global__ void __launch_bounds__(MG_TILE_THREADS) hash_select_kernel(const Sele
             }
         }
 
-      // ---- this thread's run: 64 bases of sequence, 64 end flags
-      const uint64_t word = (uint64_t)tile * MG_TILE_THREADS + tid;
-      uint64_t w0, w1, eflags;
+      // ---- this thread's two runs: words 2t, 2t+1 (+ overlap word 2t+2), 96 end flags
+      const uint32_t run0 = tid * MG_SEL_RPT;
+      const uint64_t word = (uint64_t)tile * MG_TILE_THREADS + run0;
+      uint64_t w0, w1, w2;
+      uint32_t e0, e1, e2;
       if (TMA)
         { mg_mbar_wait(&sBar[stage], (it >> 1) & 1);
-          w0 = sPack[buf][tid];
-          w1 = sPack[buf][tid + 1];
-          eflags = (uint64_t)sEnds[buf][tid] | ((uint64_t)sEnds[buf][tid + 1] << 32);
+          w0 = sPack[buf][run0]; w1 = sPack[buf][run0 + 1]; w2 = sPack[buf][run0 + 2];
+          e0 = sEnds[buf][run0]; e1 = sEnds[buf][run0 + 1]; e2 = sEnds[buf][run0 + 2];
         }
       else
-        { w0 = __ldg(P.packed + word);
-          w1 = __ldg(P.packed + word + 1);
-          eflags = (uint64_t)__ldg(P.ends + word) | ((uint64_t)__ldg(P.ends + word + 1) << 32);
-          sPack[0][tid] = w0;                              // phase 3 reads the tile from shared memory
-          if (tid == MG_TILE_THREADS - 1) sPack[0][MG_TILE_THREADS] = w1;
+        { w0 = __ldg(P.packed + word); w1 = __ldg(P.packed + word + 1); w2 = __ldg(P.packed + word + 2);
+          e0 = __ldg(P.ends + word); e1 = __ldg(P.ends + word + 1); e2 = __ldg(P.ends + word + 2);
+          sPack[0][run0] = w0;                             // phase 3 reads the tile from shared memory
+          sPack[0][run0 + 1] = w1;
+          if (tid == MG_SEL_THREADS - 1) sPack[0][MG_TILE_THREADS] = w2;
         }
       const uint64_t tileBase = (uint64_t)tile * MG_TILE_BASES;
-      const uint32_t usable = mg_run_usable(eflags, H.k, tileBase + (uint64_t)tid * MG_RUN, P.nBases);
-      const MgRun R = mg_run_prepare(w0, w1, H.k);
-
-      // ---- phase 1: mask over the 32 window starts of the run
-      uint32_t m = 0;
-      if (PREFILTER)
-        {
-#pragma unroll
-          for (int i = 0; i < MG_RUN; ++i)
-            { // candidate <=> min(low product word of fwd, of rc) < pfLim; one predicated OR per window
-              const uint32_t pf = mg_run_fwd_lo(R, i) * H.pfMul, pr = mg_run_rc_lo(R, i) * H.pfMul;
-              const uint32_t mn = min(pf, pr);
-              asm("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}"
-                  : "+r"(m) : "r"(mn), "r"(H.pfLim), "r"(1u << i));
-            }
-        }
-      else
-        {
-#pragma unroll
-          for (int i = 0; i < MG_RUN; ++i)
-            { uint64_t km; bool isF;
-              if (mg_eval_window(H, R, i, &km, &isF)) m |= 1u << i;
-            }
-        }
-      m &= usable;
+      uint32_t m[MG_SEL_RPT];
+      { const uint64_t p0 = tileBase + (uint64_t)run0 * MG_RUN;
+        const MgRun RA = mg_run_prepare(w0, w1, H.k);
+        m[0] = scan_run<PREFILTER>(H, RA) & mg_run_usable((uint64_t)e0 | ((uint64_t)e1 << 32), H.k, p0, P.nBases);
+        const MgRun RB = mg_run_prepare(w1, w2, H.k);
+        m[1] = scan_run<PREFILTER>(H, RB) & mg_run_usable((uint64_t)e1 | ((uint64_t)e2 << 32), H.k, p0 + MG_RUN, P.nBases);
+      }
 
       // ---- phase 2: queue of (run, window) in position order
       uint32_t nQueue;
-      uint32_t qoff = mg_block_excl_scan256(__popc(m), sWarp, &nQueue);
-      if (ORDERED) sSel[tid] = 0;
-      while (m)
-        { uint32_t i = __ffs(m) - 1; m &= m - 1;
-          sQueue[qoff++] = (uint16_t)((tid << 5) | i);
+      uint32_t qoff = mg_block_excl_scan<NWARPS>(__popc(m[0]) + __popc(m[1]), sWarp, &nQueue);
+      const bool queued = nQueue <= MG_QUEUE_CAP;          // block-uniform
+      if (ORDERED) { sSel[run0] = 0; sSel[run0 + 1] = 0; }
+      if (queued)
+        {
+#pragma unroll
+          for (int r = 0; r < MG_SEL_RPT; ++r)
+            { uint32_t mm = m[r];
+              while (mm)
+                { uint32_t i = __ffs(mm) - 1; mm &= mm - 1;
+                  sQueue[qoff++] = (uint16_t)(((run0 + r) << 5) | i);
+                }
+            }
         }
       __syncthreads();
 
-      // ---- phase 3: balanced evaluation and output
+      // ---- phase 3: evaluation and output
       const uint64_t *sWords = sPack[buf];
-      if (!ORDERED)
-        { // count mode: order is irrelevant, reserve output space per warp
-          for (uint32_t base = 0; base < nQueue; base += MG_TILE_THREADS)
-            { const uint32_t q = base + tid;
-              uint64_t km = 0; bool isF = false, ok = false;
-              uint32_t e = 0;
+      // number of entries this thread handles: a slice of the queue, or (overfull tile) its own windows
+      if (!ORDERED && queued && nQueue <= MG_SEL_ROUNDS * MG_SEL_THREADS)
+        { // count mode, the usual tile: every thread evaluates its (<= MG_SEL_ROUNDS) queue entries into
+          // registers first, so that output space is reserved with ONE atomic per tile (per-warp
+          // reservations serialise on the single counter: measured 56 % of stall samples) and the
+          // scatter atomics of a thread are all in flight together
+          uint64_t km[MG_SEL_ROUNDS];
+          uint32_t ent[MG_SEL_ROUNDS];
+          uint32_t okMask = 0, fMask = 0;
+#pragma unroll
+          for (int r = 0; r < MG_SEL_ROUNDS; ++r)
+            { const uint32_t q = r * MG_SEL_THREADS + tid;
+              km[r] = 0; ent[r] = 0;
               if (q < nQueue)
-                { e = sQueue[q];
-                  ok = eval_entry(H, sWords, e, &km, &isF);
+                { bool isF;
+                  ent[r] = sQueue[q];
+                  if (eval_entry(H, sWords, ent[r], &km[r], &isF)) { okMask |= 1u << r; if (isF) fMask |= 1u << r; }
                 }
+            }
+          if (SCATTER)
+            { nSelectedLocal += __popc(okMask);
+              uint32_t pos[MG_SEL_ROUNDS], region[MG_SEL_ROUNDS];
+#pragma unroll
+              for (int r = 0; r < MG_SEL_ROUNDS; ++r)
+                if ((okMask >> r) & 1u)
+                  { region[r] = (uint32_t)(mg_slot_hash(km[r], P.slotBits) >> P.regionBits);
+                    pos[r] = atomicAdd(&P.cursors[region[r]], 1u);
+                  }
+#pragma unroll
+              for (int r = 0; r < MG_SEL_ROUNDS; ++r)
+                if ((okMask >> r) & 1u)
+                  { if (pos[r] < P.bucketCap) P.buckets[(uint64_t)region[r] * P.bucketCap + pos[r]] = km[r];
+                    else
+                      { const uint32_t o = atomicAdd(&P.cursors[P.nRegions], 1u);
+                        if (o < P.overflowCap) P.overflow[o] = km[r];
+                      }
+                  }
+            }
+          else
+            { uint32_t total;
+              const uint32_t off = mg_block_excl_scan<NWARPS>(__popc(okMask), sWarp, &total);
+              if (tid == 0) sBase = total ? atomicAdd(P.count, (unsigned long long)total) : 0ull;
+              __syncthreads();
+              uint64_t dst = sBase + off;
+#pragma unroll
+              for (int r = 0; r < MG_SEL_ROUNDS; ++r)
+                if ((okMask >> r) & 1u)
+                  { if (dst < P.cap)
+                      { P.outKmer[dst] = (P.strandBit && ((fMask >> r) & 1u)) ? (km[r] | (1ull << 63)) : km[r];
+                        if (P.outPos) P.outPos[dst] = (uint32_t)(tileBase + ent[r]);   // ent = run*32 + window
+                      }
+                    ++dst;
+                  }
+            }
+        }
+      else if (!ORDERED)
+        { // count mode, crowded tile: warp-aggregated reservations, per-thread loop when even the queue overflowed
+          uint32_t own0 = m[0], own1 = m[1];
+          for (uint32_t base = 0;; base += MG_SEL_THREADS)
+            { uint64_t km = 0; bool isF = false, ok = false;
+              uint32_t e = 0;
+              bool have;
+              if (queued)
+                { if (base >= nQueue) break;
+                  have = base + tid < nQueue;
+                  if (have) e = sQueue[base + tid];
+                }
+              else
+                { have = (own0 | own1) != 0;
+                  if (!__any_sync(0xffffffffu, have)) break;
+                  if (own0) { uint32_t i = __ffs(own0) - 1; own0 &= own0 - 1; e = (run0 << 5) | i; }
+                  else if (own1) { uint32_t i = __ffs(own1) - 1; own1 &= own1 - 1; e = ((run0 + 1) << 5) | i; }
+                }
+              if (have) ok = eval_entry(H, sWords, e, &km, &isF);
               const uint32_t ballot = __ballot_sync(0xffffffffu, ok);
               if (!ballot) continue;
               if (SCATTER)
-                { // fused K2 -> K3a: the atomic's round trip hides behind the other warps' hashing
-                  if (lane == 0) atomicAdd(P.count, (unsigned long long)__popc(ballot));
-                  if (ok)
-                    { const uint32_t region = (uint32_t)(mg_slot_hash(km, P.slotBits) >> P.regionBits);
+                { if (ok)
+                    { ++nSelectedLocal;
+                      const uint32_t region = (uint32_t)(mg_slot_hash(km, P.slotBits) >> P.regionBits);
                       const uint32_t pos = atomicAdd(&P.cursors[region], 1u);
                       if (pos < P.bucketCap) P.buckets[(uint64_t)region * P.bucketCap + pos] = km;
                       else
@@ -220,15 +309,28 @@ __global__ void __launch_bounds__(MG_TILE_THREADS) hash_select_kernel(const Sele
         }
       else
         { // input order: pass 1 marks the selected windows of every run ...
-          if (PREFILTER)
-            { for (uint32_t q = tid; q < nQueue; q += MG_TILE_THREADS)
+          if (!queued)
+            { // overfull tile: every thread resolves its own windows
+#pragma unroll
+              for (int r = 0; r < MG_SEL_RPT; ++r)
+                { uint32_t mm = m[r], sel = 0;
+                  while (mm)
+                    { uint32_t i = __ffs(mm) - 1; mm &= mm - 1;
+                      uint64_t km; bool isF;
+                      if (!PREFILTER || eval_entry(H, sWords, ((run0 + r) << 5) | i, &km, &isF)) sel |= 1u << i;
+                    }
+                  sSel[run0 + r] = sel;
+                }
+            }
+          else if (PREFILTER)
+            { for (uint32_t q = tid; q < nQueue; q += MG_SEL_THREADS)
                 { const uint32_t e = sQueue[q];
                   uint64_t km; bool isF;
                   if (eval_entry(H, sWords, e, &km, &isF)) atomicOr(&sSel[e >> 5], 1u << (e & 31u));
                 }
             }
           else
-            { for (uint32_t q = tid; q < nQueue; q += MG_TILE_THREADS)
+            { for (uint32_t q = tid; q < nQueue; q += MG_SEL_THREADS)
                 { const uint32_t e = sQueue[q];
                   atomicOr(&sSel[e >> 5], 1u << (e & 31u));          // the queue already holds the selected windows
                 }
@@ -236,9 +338,10 @@ __global__ void __launch_bounds__(MG_TILE_THREADS) hash_select_kernel(const Sele
           __syncthreads();
           // ... a scan over the runs + the look-back over the tiles place them ...
           uint32_t total;
-          const uint32_t mySel = sSel[tid];
-          const uint32_t off = mg_block_excl_scan256(__popc(mySel), sWarp, &total);
-          sDst[tid] = off;
+          const uint32_t selA = sSel[run0], selB = sSel[run0 + 1];
+          const uint32_t off = mg_block_excl_scan<NWARPS>(__popc(selA) + __popc(selB), sWarp, &total);
+          sDst[run0] = off;
+          sDst[run0 + 1] = off + __popc(selA);
           if (tid < 32)
             { uint32_t excl = mg_lookback(P.status, tile, total);
               if (tid == 0)
@@ -248,9 +351,19 @@ __global__ void __launch_bounds__(MG_TILE_THREADS) hash_select_kernel(const Sele
             }
           __syncthreads();
           const uint64_t outBase = sBase;
-          // ... pass 2 writes them, again spread over all threads
-          for (uint32_t q = tid; q < nQueue; q += MG_TILE_THREADS)
-            { const uint32_t e = sQueue[q];
+          // ... pass 2 writes them, again spread over all threads (or per owner when overfull)
+          uint32_t own0 = selA, own1 = selB;
+          for (uint32_t q = tid;; q += MG_SEL_THREADS)
+            { uint32_t e;
+              if (queued)
+                { if (q >= nQueue) break;
+                  e = sQueue[q];
+                }
+              else
+                { if (own0) { uint32_t i = __ffs(own0) - 1; own0 &= own0 - 1; e = (run0 << 5) | i; }
+                  else if (own1) { uint32_t i = __ffs(own1) - 1; own1 &= own1 - 1; e = ((run0 + 1) << 5) | i; }
+                  else break;
+                }
               const uint32_t src = e >> 5, bit = e & 31u;
               const uint32_t selBits = sSel[src];
               if (!((selBits >> bit) & 1u)) continue;
@@ -264,6 +377,10 @@ __global__ void __launch_bounds__(MG_TILE_THREADS) hash_select_kernel(const Sele
                 }
             }
         }
+    }
+  if (SCATTER)
+    { nSelectedLocal = mg_warp_sum(nSelectedLocal);
+      if (lane == 0 && nSelectedLocal) atomicAdd(P.count, (unsigned long long)nSelectedLocal);
     }
 }
 
@@ -282,12 +399,12 @@ static int launch_select(const SelectParams &P, cudaStream_t st)
 {
   static int blocksPerSm = 0;
   if (!blocksPerSm)
-    { MG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, hash_select_kernel<PF, ORD, TMA, SC>, MG_TILE_THREADS, 0));
+    { MG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, hash_select_kernel<PF, ORD, TMA, SC>, MG_SEL_THREADS, 0));
       if (blocksPerSm < 1) blocksPerSm = 1;
     }
   uint64_t grid = (uint64_t)mg_num_sms() * blocksPerSm;
   if (grid > P.nTiles) grid = P.nTiles;
-  hash_select_kernel<PF, ORD, TMA, SC><<<(unsigned)grid, MG_TILE_THREADS, 0, st>>>(P);
+  hash_select_kernel<PF, ORD, TMA, SC><<<(unsigned)grid, MG_SEL_THREADS, 0, st>>>(P);
   MG_LAUNCH_CHECK("hash_select");
   return MODGPU_OK;
 }

@@ -153,7 +153,7 @@ MGHD uint64_t mg_run_rc(const MgRun &R, uint32_t i, uint64_t mask)
 MGHD uint32_t mg_blocked_mask(uint64_t ends, uint32_t k)
 {
   uint32_t L = k - 1;                       // window of flags to OR, 0..30
-  if (L == 0) return 0u;
+  if (L == 0 || ends == 0) return 0u;       // no sequence ends in sight (the common case)
   uint64_t s = ends;                        // OR over 1 flag
   uint32_t have = 1;
   while (have * 2 <= L) { s |= s >> have; have *= 2; }   // OR over `have` flags, have = 2^m <= L
@@ -173,6 +173,27 @@ MGHD bool mg_eval_window(const MgKHasher &H, const MgRun &R, uint32_t i, uint64_
   *isF = fw;
   bool lowOk = (hv & ((1ull << H.tz) - 1)) == 0;
   bool oddOk = (hv >> H.tz) * H.oddInv <= H.oddLim;
+  return lowOk && oddOk;
+}
+
+// The same for ONE window given the run's two packed words (phase 3 of the
+// kernel, where only the few queued windows are evaluated): the forward k-mer
+// is a bit field of w0:w1 and the reverse complement is computed from the k-mer
+// itself (reverse the 2-bit groups, complement, realign) instead of preparing
+// the whole reverse-complement stream.
+MGHD bool mg_eval_single(const MgKHasher &H, uint64_t w0, uint64_t w1, uint32_t i, uint64_t *kmer, bool *isF)
+{
+  const uint32_t sh = 128 - 2 * (i + H.k);              // 4..126: bits of w0:w1 below the window
+  uint64_t f = (sh >= 64) ? (w0 >> (sh - 64)) : ((w0 << (64 - sh)) | (w1 >> sh));
+  f &= H.mask;
+  const uint64_t r = (~mg_pairrev64(f)) >> H.shift;
+  uint64_t hf = mg_hash(H, f), hr = mg_hash(H, r);
+  bool fw = hf < hr;
+  uint64_t hv = fw ? hf : hr;
+  *kmer = fw ? f : r;
+  *isF = fw;
+  bool lowOk = (hv & ((1ull << H.tz) - 1)) == 0;
+  bool oddOk = (H.oddInv == 1) || ((hv >> H.tz) * H.oddInv <= H.oddLim);    // odd part 1: d is a power of two
   return lowOk && oddOk;
 }
 

@@ -44,10 +44,11 @@ __device__ __forceinline__ uint32_t mg_warp_sum(uint32_t v)
   return v;
 }
 
-// exclusive scan of one value per thread over a 256-thread block.
-// sWarp: 8 words of shared memory.  Returns the thread's exclusive prefix and
-// the block total.  Contains one __syncthreads.
-__device__ __forceinline__ uint32_t mg_block_excl_scan256(uint32_t v, uint32_t *sWarp, uint32_t *total)
+// exclusive scan of one value per thread over a block of NWARPS warps.
+// sWarp: NWARPS words of shared memory.  Returns the thread's exclusive prefix
+// and the block total.  Contains one __syncthreads.
+template <int NWARPS>
+__device__ __forceinline__ uint32_t mg_block_excl_scan(uint32_t v, uint32_t *sWarp, uint32_t *total)
 {
   uint32_t incl = mg_warp_incl_scan(v);
   uint32_t w = threadIdx.x >> 5;
@@ -55,7 +56,7 @@ __device__ __forceinline__ uint32_t mg_block_excl_scan256(uint32_t v, uint32_t *
   __syncthreads();
   uint32_t pre = 0, tot = 0;
 #pragma unroll
-  for (int i = 0; i < MG_TILE_THREADS / 32; ++i)
+  for (int i = 0; i < NWARPS; ++i)
     { uint32_t t = sWarp[i];
       if ((uint32_t)i < w) pre += t;
       tot += t;
@@ -63,6 +64,9 @@ __device__ __forceinline__ uint32_t mg_block_excl_scan256(uint32_t v, uint32_t *
   *total = tot;
   return pre + incl - v;
 }
+
+__device__ __forceinline__ uint32_t mg_block_excl_scan256(uint32_t v, uint32_t *sWarp, uint32_t *total)
+{ return mg_block_excl_scan<MG_TILE_THREADS / 32>(v, sWarp, total); }
 
 // ------------------------------------------------ decoupled look-back scan --
 // status word: flag (high 32 bits: 0 none, 1 tile aggregate, 2 inclusive

@@ -64,7 +64,12 @@ int64_t hm_select(int k, int d, uint64_t factor1, const uint8_t *bytes, uint64_t
           for (uint32_t i = 0; i < 32; ++i) cand |= (mg_prefilter_candidate(H, R, i) ? 1u : 0u) << i;
           cand &= usable;
           for (uint32_t i = 0; i < 32; ++i)
-            if (cand >> i & 1) { uint64_t km; bool f; if (mg_eval_window(H, R, i, &km, &f)) sel |= 1u << i; }
+            if (cand >> i & 1)
+              { uint64_t km, km2; bool f, f2;
+                bool a = mg_eval_window(H, R, i, &km, &f), b = mg_eval_single(H, words[T], words[T + 1], i, &km2, &f2);
+                if (a != b || (a && (km != km2 || f != f2))) return -2000000 - (int64_t)(p0 + i);
+                if (a) sel |= 1u << i;
+              }
         }
       else
         { for (uint32_t i = 0; i < 32; ++i) { uint64_t km; bool f; if (mg_eval_window(H, R, i, &km, &f)) sel |= 1u << i; }
@@ -73,7 +78,10 @@ int64_t hm_select(int k, int d, uint64_t factor1, const uint8_t *bytes, uint64_t
       for (uint32_t i = 0; i < 32; ++i)
         if (sel >> i & 1)
           { uint64_t km; bool f;
-            mg_eval_window(H, R, i, &km, &f);
+            uint64_t km2; bool f2;
+            bool ok1 = mg_eval_window(H, R, i, &km2, &f2);
+            bool ok2 = mg_eval_single(H, words[T], words[T + 1], i, &km, &f);     // what the kernel's phase 3 uses
+            if (!ok1 || !ok2 || km != km2 || f != f2) return -1000000 - (int64_t)(p0 + i);
             if (n < cap) { kmer[n] = km; gpos[n] = (uint32_t)(p0 + i); isF[n] = f ? 1 : 0; }
             ++n;
           }
