@@ -205,6 +205,42 @@ int modgpuModsetSelectDevice(ModgpuModset *ms, const uint8_t *d_bases, const uin
 /* same with the batch in host memory (one chunk, < 2^32 bases) */
 int modgpuModsetSelectHost(ModgpuModset *ms, const char *bases, const uint64_t *offs,
                            uint64_t nSeq, int isAscii, const uint64_t **d_kmers, uint64_t *nSelected);
+/* Multi-GPU count mode without host round trips: K1 + K2 with the selected k-mers
+ * written into nOwners segments (segCap entries each) of the caller's send buffer,
+ * segment o holding the k-mers owned by rank o (modgpuOwnerOf); d_counts[o] (uint32)
+ * receives their number and exceeds segCap when the segment overflowed (the
+ * caller then repeats the batch through modgpuModsetSelectDevice). */
+int modgpuModsetSelectOwnersDevice(ModgpuModset *ms, const uint8_t *d_bases, const uint64_t *d_offs,
+                                   uint64_t nSeq, uint64_t nBases, int isAscii, uint32_t nOwners,
+                                   uint64_t *d_segments, uint64_t segCap, uint32_t *d_counts);
+int modgpuModsetSelectOwnersHost(ModgpuModset *ms, const char *bases, const uint64_t *offs, uint64_t nSeq,
+                                 int isAscii, uint32_t nOwners, uint64_t *d_segments, uint64_t segCap,
+                                 uint32_t *d_counts);
+/* Fully fused multi-GPU build: K2 scatters every selected k-mer into bucket
+ * (owner * R + region) of the caller's send buffer (R = modgpuModsetRegions(),
+ * bucketCap entries per bucket, fill counts in d_cursors[nOwners * R]); after an
+ * equal-split all-to-all of buckets and cursors the owner builds each of its
+ * table regions in shared memory straight from the nSrc received buckets.
+ * K-mers beyond a bucket's capacity travel in per-owner overflow segments
+ * (overflowCap entries, counts in d_ovfCounts[nOwners], which exceed overflowCap
+ * when even those overflowed).  *d_count (device) = number selected. */
+uint32_t modgpuModsetRegions(ModgpuModset *ms);
+int modgpuModsetSelectBucketsDevice(ModgpuModset *ms, const uint8_t *d_bases, const uint64_t *d_offs,
+                                    uint64_t nSeq, uint64_t nBases, int isAscii, uint32_t nOwners,
+                                    uint64_t *d_buckets, uint32_t bucketCap, uint32_t *d_cursors,
+                                    uint64_t *d_overflow, uint64_t overflowCap, uint32_t *d_ovfCounts,
+                                    uint64_t *d_count);
+int modgpuModsetSelectBucketsHost(ModgpuModset *ms, const char *bases, const uint64_t *offs, uint64_t nSeq,
+                                  int isAscii, uint32_t nOwners, uint64_t *d_buckets, uint32_t bucketCap,
+                                  uint32_t *d_cursors, uint64_t *d_overflow, uint64_t overflowCap,
+                                  uint32_t *d_ovfCounts, uint64_t *d_count);
+int modgpuModsetBuildFromBuckets(ModgpuModset *ms, const uint64_t *d_buckets, const uint32_t *d_cursors,
+                                 uint32_t bucketCap, uint32_t nSrc, const uint64_t *d_overflow,
+                                 uint64_t overflowCap, const uint32_t *d_ovfCounts);
+/* insert + count nSegs received segments whose fill counts are in device memory
+ * (expectedN sizes the table's region buckets) */
+int modgpuModsetInsertSegments(ModgpuModset *ms, const uint64_t *d_segments, uint32_t nSegs, uint64_t segCap,
+                               const uint32_t *d_counts, uint64_t expectedN);
 /* insert + count a device list of k-mers into the object's table */
 int modgpuModsetInsertDevice(ModgpuModset *ms, const uint64_t *d_kmers, uint64_t n);
 int modgpuModsetClear(ModgpuModset *ms);

@@ -78,6 +78,13 @@ _SIGS = {
     "modgpuModsetImport": (C.c_int, [vp, vp, vp, vp, u64]),
     "modgpuModsetSelectDevice": (C.c_int, [vp, vp, vp, u64, u64, C.c_int, C.POINTER(vp), C.POINTER(u64)]),
     "modgpuModsetSelectHost": (C.c_int, [vp, vp, vp, u64, C.c_int, C.POINTER(vp), C.POINTER(u64)]),
+    "modgpuModsetSelectOwnersDevice": (C.c_int, [vp, vp, vp, u64, u64, C.c_int, u32, vp, u64, vp]),
+    "modgpuModsetSelectOwnersHost": (C.c_int, [vp, vp, vp, u64, C.c_int, u32, vp, u64, vp]),
+    "modgpuModsetRegions": (u32, [vp]),
+    "modgpuModsetSelectBucketsDevice": (C.c_int, [vp, vp, vp, u64, u64, C.c_int, u32, vp, u32, vp, vp, u64, vp, vp]),
+    "modgpuModsetSelectBucketsHost": (C.c_int, [vp, vp, vp, u64, C.c_int, u32, vp, u32, vp, vp, u64, vp, vp]),
+    "modgpuModsetBuildFromBuckets": (C.c_int, [vp, vp, vp, u32, u32, vp, u64, vp]),
+    "modgpuModsetInsertSegments": (C.c_int, [vp, vp, u32, u64, vp, u64]),
     "modgpuModsetInsertDevice": (C.c_int, [vp, vp, u64]),
     "modgpuModsetClear": (C.c_int, [vp]),
     "modgpuOwnerOf": (u32, [u64, u32]),

@@ -27,6 +27,19 @@ struct MgBulk { uint32_t slotBits, regionBits, nRegions, cap; uint32_t *cursors;
 int mg_table_bulk_begin(ModgpuTable *t, uint64_t expectedN, uint64_t maxN, MgBulk *b, cudaStream_t st);
 const uint32_t *mg_table_bulk_overflow_count(const ModgpuTable *t);
 int mg_table_bulk_finish(ModgpuTable *t, const MgBulk *b, cudaStream_t st);
+int mg_hash_select_peer(const ModgpuHasher *h, const uint64_t *d_packed, const uint32_t *d_ends, uint64_t nBases,
+                        uint64_t *d_count, void *d_workspace, int flags, uint32_t slotBits, uint32_t regionBits,
+                        uint32_t nOwners, uint32_t bucketCap, uint32_t *d_cursors, uint64_t *d_buckets,
+                        uint64_t *d_overflow, uint64_t overflowCap, uint32_t *d_ovfCounts, cudaStream_t st);
+int mg_table_build_from_buckets(ModgpuTable *t, const uint64_t *d_buckets, const uint32_t *d_cursors, uint32_t cap, uint32_t nSrc,
+                                const uint64_t *d_overflow, uint64_t overflowCap, const uint32_t *d_ovfCounts, cudaStream_t st);
+uint32_t mg_table_regions(const ModgpuTable *t);
+uint32_t mg_table_slot_bits(const ModgpuTable *t);
+int mg_hash_select_owners(const ModgpuHasher *h, const uint64_t *d_packed, const uint32_t *d_ends, uint64_t nBases,
+                          void *d_workspace, int flags, uint32_t nOwners, uint32_t *d_cursors, uint64_t *d_buf,
+                          uint64_t ownerCap, cudaStream_t st);
+int mg_table_insert_segments(ModgpuTable *t, const uint64_t *d_segs, uint32_t nSegs, uint64_t segCap,
+                             const uint32_t *d_counts, uint64_t expectedN, cudaStream_t st);
 int mg_hash_select_scatter(const ModgpuHasher *h, const uint64_t *d_packed, const uint32_t *d_ends, uint64_t nBases,
                            uint64_t *d_count, void *d_workspace, int flags, uint32_t slotBits, uint32_t regionBits,
                            uint32_t bucketCap, uint32_t *d_cursors, uint64_t *d_buckets, uint64_t *d_overflow,
@@ -499,6 +512,110 @@ extern "C" int modgpuModsetSelectHost(ModgpuModset *ms, const char *bases, const
   if (nb) MG_CUDA(cudaMemcpyAsync(ms->bases[0].p, bases, nb, cudaMemcpyHostToDevice, ms->stream));
   MG_CUDA(cudaMemcpyAsync(ms->offs[0].p, offs, (nSeq + 1) * 8, cudaMemcpyHostToDevice, ms->stream));
   return modgpuModsetSelectDevice(ms, (const uint8_t *)ms->bases[0].p, (const uint64_t *)ms->offs[0].p, nSeq, nb, isAscii, d_kmers, nSelected);
+}
+
+// multi-GPU, sync-free: K1 + K2 with the selected k-mers written into nOwners segments of the caller's
+// send buffer (segment o = k-mers owned by rank o), counts in d_counts (uint32 per owner)
+extern "C" int modgpuModsetSelectOwnersDevice(ModgpuModset *ms, const uint8_t *d_bases, const uint64_t *d_offs,
+                                              uint64_t nSeq, uint64_t nBases, int isAscii, uint32_t nOwners,
+                                              uint64_t *d_segments, uint64_t segCap, uint32_t *d_counts)
+{
+  cudaStream_t st = ms->stream;
+  if (nBases >= (1ull << 32)) { mg_set_error("modgpuModsetSelectOwnersDevice: batch exceeds 2^32-1 bases"); return MODGPU_EINVAL; }
+  const uint64_t words = modgpuPackedWords(nBases);
+  int rc;
+  if ((rc = ms->packed.ensure(words * 8)) || (rc = ms->ends.ensure(words * 4)) ||
+      (rc = ms->work.ensure(modgpuHashSelectWorkspace(nBases))))
+    return rc;
+  { ProfScope p(ms, MODGPU_T_PACK, 2);
+    if ((rc = modgpuPack2bit(d_bases, nBases, isAscii, (uint64_t *)ms->packed.p, st))) return rc;
+    if ((rc = modgpuMarkEnds(d_offs, nSeq, nBases, (uint32_t *)ms->ends.p, st))) return rc;
+  }
+  ProfScope p(ms, MODGPU_T_SELECT, 1);
+  return mg_hash_select_owners(&ms->hasher, (const uint64_t *)ms->packed.p, (const uint32_t *)ms->ends.p, nBases, ms->work.p,
+                               ms->selFlags, nOwners, d_counts, d_segments, segCap, st);
+}
+
+extern "C" int modgpuModsetSelectOwnersHost(ModgpuModset *ms, const char *bases, const uint64_t *offs, uint64_t nSeq,
+                                            int isAscii, uint32_t nOwners, uint64_t *d_segments, uint64_t segCap,
+                                            uint32_t *d_counts)
+{
+  if (!nSeq) return MODGPU_OK;
+  int rc = check_offsets(offs, nSeq);
+  if (rc) return rc;
+  const uint64_t nb = offs[nSeq];
+  if (nb >= (1ull << 32)) { mg_set_error("modgpuModsetSelectOwnersHost: batch exceeds 2^32-1 bases"); return MODGPU_EINVAL; }
+  if ((rc = ms->bases[0].ensure(nb + 64)) || (rc = ms->offs[0].ensure((nSeq + 1) * 8))) return rc;
+  if (nb) MG_CUDA(cudaMemcpyAsync(ms->bases[0].p, bases, nb, cudaMemcpyHostToDevice, ms->stream));
+  MG_CUDA(cudaMemcpyAsync(ms->offs[0].p, offs, (nSeq + 1) * 8, cudaMemcpyHostToDevice, ms->stream));
+  return modgpuModsetSelectOwnersDevice(ms, (const uint8_t *)ms->bases[0].p, (const uint64_t *)ms->offs[0].p, nSeq, nb, isAscii,
+                                        nOwners, d_segments, segCap, d_counts);
+}
+
+extern "C" uint32_t modgpuModsetRegions(ModgpuModset *ms) { return mg_table_regions(ms->table); }
+
+// multi-GPU, fully fused: K1 + K2 scattering into per-(owner, region) buckets of the caller's send buffer
+extern "C" int modgpuModsetSelectBucketsDevice(ModgpuModset *ms, const uint8_t *d_bases, const uint64_t *d_offs,
+                                               uint64_t nSeq, uint64_t nBases, int isAscii, uint32_t nOwners,
+                                               uint64_t *d_buckets, uint32_t bucketCap, uint32_t *d_cursors,
+                                               uint64_t *d_overflow, uint64_t overflowCap, uint32_t *d_ovfCounts,
+                                               uint64_t *d_count)
+{
+  cudaStream_t st = ms->stream;
+  if (nBases >= (1ull << 32)) { mg_set_error("modgpuModsetSelectBucketsDevice: batch exceeds 2^32-1 bases"); return MODGPU_EINVAL; }
+  const uint64_t words = modgpuPackedWords(nBases);
+  int rc;
+  if ((rc = ms->packed.ensure(words * 8)) || (rc = ms->ends.ensure(words * 4)) ||
+      (rc = ms->work.ensure(modgpuHashSelectWorkspace(nBases))))
+    return rc;
+  { ProfScope p(ms, MODGPU_T_PACK, 2);
+    if ((rc = modgpuPack2bit(d_bases, nBases, isAscii, (uint64_t *)ms->packed.p, st))) return rc;
+    if ((rc = modgpuMarkEnds(d_offs, nSeq, nBases, (uint32_t *)ms->ends.p, st))) return rc;
+  }
+  ProfScope p(ms, MODGPU_T_SELECT, 1);
+  return mg_hash_select_peer(&ms->hasher, (const uint64_t *)ms->packed.p, (const uint32_t *)ms->ends.p, nBases, d_count, ms->work.p,
+                             ms->selFlags, mg_table_slot_bits(ms->table), 11, nOwners, bucketCap, d_cursors, d_buckets,
+                             d_overflow, overflowCap, d_ovfCounts, st);
+}
+
+extern "C" int modgpuModsetSelectBucketsHost(ModgpuModset *ms, const char *bases, const uint64_t *offs, uint64_t nSeq,
+                                             int isAscii, uint32_t nOwners, uint64_t *d_buckets, uint32_t bucketCap,
+                                             uint32_t *d_cursors, uint64_t *d_overflow, uint64_t overflowCap,
+                                             uint32_t *d_ovfCounts, uint64_t *d_count)
+{
+  if (!nSeq) return MODGPU_OK;
+  int rc = check_offsets(offs, nSeq);
+  if (rc) return rc;
+  const uint64_t nb = offs[nSeq];
+  if (nb >= (1ull << 32)) { mg_set_error("modgpuModsetSelectBucketsHost: batch exceeds 2^32-1 bases"); return MODGPU_EINVAL; }
+  if ((rc = ms->bases[0].ensure(nb + 64)) || (rc = ms->offs[0].ensure((nSeq + 1) * 8))) return rc;
+  if (nb) MG_CUDA(cudaMemcpyAsync(ms->bases[0].p, bases, nb, cudaMemcpyHostToDevice, ms->stream));
+  MG_CUDA(cudaMemcpyAsync(ms->offs[0].p, offs, (nSeq + 1) * 8, cudaMemcpyHostToDevice, ms->stream));
+  return modgpuModsetSelectBucketsDevice(ms, (const uint8_t *)ms->bases[0].p, (const uint64_t *)ms->offs[0].p, nSeq, nb, isAscii,
+                                         nOwners, d_buckets, bucketCap, d_cursors, d_overflow, overflowCap, d_ovfCounts, d_count);
+}
+
+// build the object's table regions from nSrc received bucket arrays (+ overflow segments)
+extern "C" int modgpuModsetBuildFromBuckets(ModgpuModset *ms, const uint64_t *d_buckets, const uint32_t *d_cursors,
+                                            uint32_t bucketCap, uint32_t nSrc, const uint64_t *d_overflow,
+                                            uint64_t overflowCap, const uint32_t *d_ovfCounts)
+{
+  ProfScope p(ms, MODGPU_T_INSERT, 2);
+  int rc = mg_table_build_from_buckets(ms->table, d_buckets, d_cursors, bucketCap, nSrc, d_overflow, overflowCap, d_ovfCounts, ms->stream);
+  if (rc) return rc;
+  ms->dirty = true;
+  return MODGPU_OK;
+}
+
+// insert + count nSegs received segments (device counts, uint32 each) into the object's table
+extern "C" int modgpuModsetInsertSegments(ModgpuModset *ms, const uint64_t *d_segments, uint32_t nSegs, uint64_t segCap,
+                                          const uint32_t *d_counts, uint64_t expectedN)
+{
+  ProfScope p(ms, MODGPU_T_INSERT, 3);
+  int rc = mg_table_insert_segments(ms->table, d_segments, nSegs, segCap, d_counts, expectedN, ms->stream);
+  if (rc) return rc;
+  ms->dirty = true;
+  return MODGPU_OK;
 }
 
 extern "C" int modgpuModsetInsertDevice(ModgpuModset *ms, const uint64_t *d_kmers, uint64_t n)

@@ -50,6 +50,12 @@ struct SelectParams {
   uint64_t *buckets;
   uint64_t *overflow;
   uint64_t overflowCap;
+  // OUT == 2: selected k-mers go into nOwners contiguous segments of a send
+  // buffer (multi-GPU: one segment per owner GPU), ownerCursor[o] counts them
+  uint32_t nOwners;
+  uint32_t *ownerCursor;
+  uint64_t *ownerBuf;
+  uint64_t ownerCap;
 };
 
 // Phase 2 helper: evaluate queue entry e = (source thread << 5 | window) of the
@@ -106,9 +112,16 @@ __device__ __forceinline__ uint32_t scan_run(const MgKHasher &H, const MgRun &R)
   return m;
 }
 
-template <bool PREFILTER, bool ORDERED, bool TMA, bool SCATTER>
+// OUT: 0 = list, 1 = scatter into the table's region buckets, 2 = per-owner segments,
+//      3 = per-(owner, region) buckets: what the owner's region build consumes directly
+template <bool PREFILTER, bool ORDERED, bool TMA, int OUT>
 __global__ void __launch_bounds__(MG_SEL_THREADS) hash_select_kernel(const SelectParams P)
 {
+  constexpr bool SCATTER = (OUT == 1 || OUT == 3);
+  constexpr bool OWNERS = (OUT == 2);
+  constexpr bool PEER = (OUT == 3);
+  __shared__ uint32_t sOwn[OWNERS ? 64 : 1];
+  __shared__ uint32_t sOwnBase[OWNERS ? 64 : 1];
   constexpr int NBUF = TMA ? 2 : 1;
   constexpr int NWARPS = MG_SEL_THREADS / 32;
   __shared__ __align__(128) uint64_t sPack[NBUF][MG_TILE_PACK_BYTES / 8];
@@ -190,6 +203,7 @@ __global__ void __launch_bounds__(MG_SEL_THREADS) hash_select_kernel(const Selec
       uint32_t qoff = mg_block_excl_scan<NWARPS>(__popc(m[0]) + __popc(m[1]), sWarp, &nQueue);
       const bool queued = nQueue <= MG_QUEUE_CAP;          // block-uniform
       if (ORDERED) { sSel[run0] = 0; sSel[run0 + 1] = 0; }
+      if (OWNERS && tid < 64) sOwn[tid] = 0;
       if (queued)
         {
 #pragma unroll
@@ -224,19 +238,44 @@ __global__ void __launch_bounds__(MG_SEL_THREADS) hash_select_kernel(const Selec
                   if (eval_entry(H, sWords, ent[r], &km[r], &isF)) { okMask |= 1u << r; if (isF) fMask |= 1u << r; }
                 }
             }
-          if (SCATTER)
+          if (OWNERS)
+            { // per-owner segments: rank inside the tile through shared memory, one reservation per owner and tile
+              uint32_t own[MG_SEL_ROUNDS], rk[MG_SEL_ROUNDS];
+#pragma unroll
+              for (int r = 0; r < MG_SEL_ROUNDS; ++r)
+                if ((okMask >> r) & 1u)
+                  { own[r] = mg_owner(km[r], P.nOwners);
+                    rk[r] = atomicAdd(&sOwn[own[r]], 1u);
+                  }
+              __syncthreads();
+              if (tid < P.nOwners) sOwnBase[tid] = sOwn[tid] ? atomicAdd(&P.ownerCursor[tid], sOwn[tid]) : 0u;
+              __syncthreads();
+#pragma unroll
+              for (int r = 0; r < MG_SEL_ROUNDS; ++r)
+                if ((okMask >> r) & 1u)
+                  { const uint64_t dst = (uint64_t)sOwnBase[own[r]] + rk[r];
+                    if (dst < P.ownerCap) P.ownerBuf[(uint64_t)own[r] * P.ownerCap + dst] = km[r];
+                  }
+            }
+          else if (SCATTER)
             { nSelectedLocal += __popc(okMask);
               uint32_t pos[MG_SEL_ROUNDS], region[MG_SEL_ROUNDS];
 #pragma unroll
               for (int r = 0; r < MG_SEL_ROUNDS; ++r)
                 if ((okMask >> r) & 1u)
                   { region[r] = (uint32_t)(mg_slot_hash(km[r], P.slotBits) >> P.regionBits);
+                    if (PEER) region[r] += mg_owner(km[r], P.nOwners) * P.nRegions;      // bucket index = owner * R + region
                     pos[r] = atomicAdd(&P.cursors[region[r]], 1u);
                   }
 #pragma unroll
               for (int r = 0; r < MG_SEL_ROUNDS; ++r)
                 if ((okMask >> r) & 1u)
                   { if (pos[r] < P.bucketCap) P.buckets[(uint64_t)region[r] * P.bucketCap + pos[r]] = km[r];
+                    else if (PEER)
+                      { const uint32_t ow = region[r] / P.nRegions;
+                        const uint32_t o = atomicAdd(&P.ownerCursor[ow], 1u);
+                        if (o < P.overflowCap) P.overflow[(uint64_t)ow * P.overflowCap + o] = km[r];
+                      }
                     else
                       { const uint32_t o = atomicAdd(&P.cursors[P.nRegions], 1u);
                         if (o < P.overflowCap) P.overflow[o] = km[r];
@@ -281,12 +320,26 @@ __global__ void __launch_bounds__(MG_SEL_THREADS) hash_select_kernel(const Selec
               if (have) ok = eval_entry(H, sWords, e, &km, &isF);
               const uint32_t ballot = __ballot_sync(0xffffffffu, ok);
               if (!ballot) continue;
+              if (OWNERS)
+                { if (ok)
+                    { const uint32_t o = mg_owner(km, P.nOwners);
+                      const uint64_t dst = atomicAdd(&P.ownerCursor[o], 1u);
+                      if (dst < P.ownerCap) P.ownerBuf[(uint64_t)o * P.ownerCap + dst] = km;
+                    }
+                  continue;
+                }
               if (SCATTER)
                 { if (ok)
                     { ++nSelectedLocal;
-                      const uint32_t region = (uint32_t)(mg_slot_hash(km, P.slotBits) >> P.regionBits);
+                      uint32_t region = (uint32_t)(mg_slot_hash(km, P.slotBits) >> P.regionBits);
+                      const uint32_t ow = PEER ? mg_owner(km, P.nOwners) : 0u;
+                      if (PEER) region += ow * P.nRegions;
                       const uint32_t pos = atomicAdd(&P.cursors[region], 1u);
                       if (pos < P.bucketCap) P.buckets[(uint64_t)region * P.bucketCap + pos] = km;
+                      else if (PEER)
+                        { const uint32_t o = atomicAdd(&P.ownerCursor[ow], 1u);
+                          if (o < P.overflowCap) P.overflow[(uint64_t)ow * P.overflowCap + o] = km;
+                        }
                       else
                         { const uint32_t o = atomicAdd(&P.cursors[P.nRegions], 1u);
                           if (o < P.overflowCap) P.overflow[o] = km;
@@ -394,7 +447,7 @@ extern "C" uint64_t modgpuHashSelectWorkspace(uint64_t nBases)
 
 MgKHasher mg_khasher_from(const ModgpuHasher *h) { return mg_make_khasher(h->k, h->w, h->factor1); }
 
-template <bool PF, bool ORD, bool TMA, bool SC = false>
+template <bool PF, bool ORD, bool TMA, int SC = 0>
 static int launch_select(const SelectParams &P, cudaStream_t st)
 {
   static int blocksPerSm = 0;
@@ -466,10 +519,77 @@ int mg_hash_select_scatter(const ModgpuHasher *h, const uint64_t *d_packed, cons
   MG_CUDA(cudaMemsetAsync(d_workspace, 0, 64, st));
   const bool pf = P.H.prefilter && !(flags & MODGPU_SEL_NOPREFILTER);
   const bool tma = !(flags & MODGPU_SEL_NOTMA);
-  if (pf && tma) return launch_select<true, false, true, true>(P, st);
-  if (pf) return launch_select<true, false, false, true>(P, st);
-  if (tma) return launch_select<false, false, true, true>(P, st);
-  return launch_select<false, false, false, true>(P, st);
+  if (pf && tma) return launch_select<true, false, true, 1>(P, st);
+  if (pf) return launch_select<true, false, false, 1>(P, st);
+  if (tma) return launch_select<false, false, true, 1>(P, st);
+  return launch_select<false, false, false, 1>(P, st);
+}
+
+// K2 with the selected k-mers bucketed by owner GPU (multi-GPU count mode): segment o of d_buf
+// (ownerCap entries each) receives the k-mers owned by rank o, d_cursors[o] (zeroed here) their number
+// (which exceeds ownerCap when the segment overflowed: the caller must then fall back to the list path).
+int mg_hash_select_owners(const ModgpuHasher *h, const uint64_t *d_packed, const uint32_t *d_ends, uint64_t nBases,
+                          void *d_workspace, int flags, uint32_t nOwners, uint32_t *d_cursors, uint64_t *d_buf,
+                          uint64_t ownerCap, cudaStream_t st)
+{
+  if (nBases >= (1ull << 32)) { mg_set_error("hash_select: batch of %llu bases exceeds 2^32-1", (unsigned long long)nBases); return MODGPU_EINVAL; }
+  if (nOwners < 1 || nOwners > 64) { mg_set_error("hash_select: nOwners %u out of range 1..64", nOwners); return MODGPU_EINVAL; }
+  MG_CUDA(cudaMemsetAsync(d_cursors, 0, nOwners * sizeof(uint32_t), st));
+  if (!nBases) return MODGPU_OK;
+  SelectParams P;
+  memset(&P, 0, sizeof(P));
+  P.H = mg_khasher_from(h);
+  P.packed = d_packed; P.ends = d_ends; P.nBases = nBases;
+  uint64_t words = (nBases + 31) / 32;
+  P.nTiles = (uint32_t)((words + MG_TILE_THREADS - 1) / MG_TILE_THREADS);
+  P.ticket = (uint32_t *)d_workspace;
+  P.status = (uint64_t *)((char *)d_workspace + 64);
+  P.count = (unsigned long long *)((char *)d_workspace + 8);       // unused total
+  P.nOwners = nOwners; P.ownerCursor = d_cursors; P.ownerBuf = d_buf; P.ownerCap = ownerCap;
+  MG_CUDA(cudaMemsetAsync(d_workspace, 0, 64, st));
+  const bool pf = P.H.prefilter && !(flags & MODGPU_SEL_NOPREFILTER);
+  const bool tma = !(flags & MODGPU_SEL_NOTMA);
+  if (pf && tma) return launch_select<true, false, true, 2>(P, st);
+  if (pf) return launch_select<true, false, false, 2>(P, st);
+  if (tma) return launch_select<false, false, true, 2>(P, st);
+  return launch_select<false, false, false, 2>(P, st);
+}
+
+// K2 with the selected k-mers written into per-(owner, region) buckets (multi-GPU, fully fused):
+// bucket (o * nRegions + r) of d_buckets (bucketCap entries) holds the k-mers owned by rank o that fall
+// into region r of its table; d_cursors[o * nRegions + r] (zeroed here) counts them; k-mers beyond a
+// bucket's capacity go to the owner's overflow segment d_overflow[o * overflowCap ..] / d_ovfCounts[o].
+int mg_hash_select_peer(const ModgpuHasher *h, const uint64_t *d_packed, const uint32_t *d_ends, uint64_t nBases,
+                        uint64_t *d_count, void *d_workspace, int flags, uint32_t slotBits, uint32_t regionBits,
+                        uint32_t nOwners, uint32_t bucketCap, uint32_t *d_cursors, uint64_t *d_buckets,
+                        uint64_t *d_overflow, uint64_t overflowCap, uint32_t *d_ovfCounts, cudaStream_t st)
+{
+  if (nBases >= (1ull << 32)) { mg_set_error("hash_select: batch of %llu bases exceeds 2^32-1", (unsigned long long)nBases); return MODGPU_EINVAL; }
+  if (nOwners < 1 || nOwners > 64) { mg_set_error("hash_select: nOwners %u out of range 1..64", nOwners); return MODGPU_EINVAL; }
+  const uint32_t nRegions = 1u << (slotBits - regionBits);
+  MG_CUDA(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
+  MG_CUDA(cudaMemsetAsync(d_cursors, 0, (size_t)nOwners * nRegions * sizeof(uint32_t), st));
+  MG_CUDA(cudaMemsetAsync(d_ovfCounts, 0, nOwners * sizeof(uint32_t), st));
+  if (!nBases) return MODGPU_OK;
+  SelectParams P;
+  memset(&P, 0, sizeof(P));
+  P.H = mg_khasher_from(h);
+  P.packed = d_packed; P.ends = d_ends; P.nBases = nBases;
+  uint64_t words = (nBases + 31) / 32;
+  P.nTiles = (uint32_t)((words + MG_TILE_THREADS - 1) / MG_TILE_THREADS);
+  P.count = (unsigned long long *)d_count;
+  P.ticket = (uint32_t *)d_workspace;
+  P.status = (uint64_t *)((char *)d_workspace + 64);
+  P.slotBits = slotBits; P.regionBits = regionBits; P.nRegions = nRegions; P.bucketCap = bucketCap;
+  P.cursors = d_cursors; P.buckets = d_buckets; P.overflow = d_overflow; P.overflowCap = overflowCap;
+  P.nOwners = nOwners; P.ownerCursor = d_ovfCounts;
+  MG_CUDA(cudaMemsetAsync(d_workspace, 0, 64, st));
+  const bool pf = P.H.prefilter && !(flags & MODGPU_SEL_NOPREFILTER);
+  const bool tma = !(flags & MODGPU_SEL_NOTMA);
+  if (pf && tma) return launch_select<true, false, true, 3>(P, st);
+  if (pf) return launch_select<true, false, false, 3>(P, st);
+  if (tma) return launch_select<false, false, true, 3>(P, st);
+  return launch_select<false, false, false, 3>(P, st);
 }
 
 // ---------------------------------------------------------------- locate --

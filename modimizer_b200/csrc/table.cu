@@ -149,20 +149,46 @@ __global__ void __launch_bounds__(256) bucket_scatter_kernel(const uint64_t *__r
     }
 }
 
+// the same scatter reading nSegs segments of segCap k-mers whose fill counts sit in device memory
+// (what the multi-GPU exchange delivers: one segment per source rank)
+__global__ void __launch_bounds__(256) bucket_scatter_seg_kernel(const uint64_t *__restrict__ segs, uint32_t nSegs, uint64_t segCap,
+                                                                 const uint32_t *__restrict__ segCounts, uint32_t slotBits,
+                                                                 uint32_t nRegions, uint32_t cap, uint32_t *cursors,
+                                                                 uint64_t *__restrict__ buckets, uint64_t *__restrict__ overflow,
+                                                                 uint64_t overflowCap, uint32_t *error)
+{
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint32_t sg = 0; sg < nSegs; ++sg)
+    { uint64_t n = segCounts[sg];
+      if (n > segCap) { n = segCap; atomicExch(error, 3u); }          // the sender overflowed its segment
+      const uint64_t *kmers = segs + (uint64_t)sg * segCap;
+      for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        { const uint64_t key = kmers[i] & 0x3FFFFFFFFFFFFFFFull;
+          const uint32_t region = (uint32_t)(mg_slot_hash(key, slotBits) >> MG_REGION_BITS);
+          const uint32_t pos = atomicAdd(&cursors[region], 1u);
+          if (pos < cap) buckets[(uint64_t)region * cap + pos] = key;
+          else
+            { const uint32_t o = atomicAdd(&cursors[nRegions], 1u);
+              if (o < overflowCap) overflow[o] = key; else atomicExch(error, 1u);
+            }
+        }
+    }
+}
+
 // one block builds one region: load (or, for a logically empty table, create)
 // its 2048 slots in shared memory, insert + count the bucket with shared-memory
 // atomics, store the region back.  Streaming, coalesced, 16 bytes per thread.
+#define MG_BUILD_PRELOAD 4
+// One block builds one region from nSrc buckets (one per source rank in the multi-GPU exchange):
+// source s has its buckets at buckets + s * srcStride * cap and its cursors at cursors + s * srcStride.
 template <bool FRESH>
-__global__ void __launch_bounds__(256) region_build_kernel(MgSlot *slots, uint32_t slotBits, const uint64_t *__restrict__ buckets,
-                                                           const uint32_t *__restrict__ cursors, uint32_t cap,
-                                                           unsigned long long *entries, uint32_t *error)
+__global__ void __launch_bounds__(256) region_build_multi_kernel(MgSlot *slots, uint32_t slotBits, const uint64_t *__restrict__ buckets,
+                                                                 const uint32_t *__restrict__ cursors, uint32_t cap, uint32_t nSrc,
+                                                                 uint64_t srcStride, unsigned long long *entries, uint32_t *error)
 {
   __shared__ uint4 sR[MG_REGION_SLOTS];
   const uint32_t region = blockIdx.x;
   uint4 *g = reinterpret_cast<uint4 *>(slots) + (uint64_t)region * MG_REGION_SLOTS;
-  uint32_t cnt = cursors[region];
-  if (cnt > cap) cnt = cap;
-  if (!FRESH && cnt == 0) return;                              // nothing to add: leave the region alone
   uint4 e;
   e.x = 0xFFFFFFFFu; e.y = 0xFFFFFFFFu; e.z = 0u; e.w = MG_AUX_FRESH;
 #pragma unroll
@@ -170,10 +196,72 @@ __global__ void __launch_bounds__(256) region_build_kernel(MgSlot *slots, uint32
     sR[i * 256 + threadIdx.x] = FRESH ? e : __ldcs(g + i * 256 + threadIdx.x);
   __syncthreads();
   MgSlot *sS = reinterpret_cast<MgSlot *>(sR);
-  const uint64_t *b = buckets + (uint64_t)region * cap;
   uint32_t fresh = 0;
-  for (uint32_t j = threadIdx.x; j < cnt; j += 256)
-    { const unsigned long long key = b[j];
+  for (uint32_t src = 0; src < nSrc; ++src)
+    { uint32_t cnt = cursors[src * srcStride + region];
+      if (cnt > cap) cnt = cap;
+      const uint64_t *b = buckets + ((uint64_t)src * srcStride + region) * cap;
+      for (uint32_t j = threadIdx.x; j < cnt; j += 256)
+        { const unsigned long long key = b[j] & 0x3FFFFFFFFFFFFFFFull;
+          uint32_t s = (uint32_t)mg_slot_hash(key, slotBits) & (MG_REGION_SLOTS - 1);
+          uint32_t probes = 0;
+          for (; probes < MG_REGION_SLOTS; ++probes, s = (s + 1) & (MG_REGION_SLOTS - 1))
+            { unsigned long long *kp = reinterpret_cast<unsigned long long *>(&sS[s].key);
+              unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(kp);
+              if (cur == key) break;
+              if (cur == MG_EMPTY)
+                { unsigned long long old = atomicCAS(kp, MG_EMPTY, key);
+                  if (old == MG_EMPTY) { ++fresh; break; }
+                  if (old == key) break;
+                }
+            }
+          if (probes == MG_REGION_SLOTS) { atomicExch(error, 1u); continue; }
+          atomicAdd(&sS[s].count, 1u);
+        }
+    }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < MG_REGION_SLOTS / 256; ++i) __stcs(g + i * 256 + threadIdx.x, sR[i * 256 + threadIdx.x]);
+  fresh = mg_warp_sum(fresh);
+  if (mg_lane() == 0 && fresh) atomicAdd(entries, (unsigned long long)fresh);
+}
+
+template <bool FRESH, int PRELOAD>
+__global__ void __launch_bounds__(256) region_build_kernel(MgSlot *slots, uint32_t slotBits, const uint64_t *__restrict__ buckets,
+                                                              const uint32_t *__restrict__ cursors, uint32_t cap,
+                                                              unsigned long long *entries, uint32_t *error)
+{
+  __shared__ uint4 sR[MG_REGION_SLOTS];
+  const uint32_t region = blockIdx.x;
+  uint4 *g = reinterpret_cast<uint4 *>(slots) + (uint64_t)region * MG_REGION_SLOTS;
+  uint32_t cnt = cursors[region];
+  if (cnt > cap) cnt = cap;
+  if (!FRESH && cnt == 0) return;                              // nothing to add: leave the region alone
+  // the bucket's k-mers first: their DRAM latency overlaps the creation / load of the region
+  const uint64_t *b = buckets + (uint64_t)region * cap;
+  unsigned long long pre[PRELOAD > 0 ? PRELOAD : 1];
+#pragma unroll
+  for (int u = 0; u < PRELOAD; ++u)
+    { const uint32_t j = u * 256 + threadIdx.x;
+      pre[u] = (j < cnt) ? __ldcs(reinterpret_cast<const unsigned long long *>(b) + j) : MG_EMPTY;
+    }
+  uint4 e;
+  e.x = 0xFFFFFFFFu; e.y = 0xFFFFFFFFu; e.z = 0u; e.w = MG_AUX_FRESH;
+#pragma unroll
+  for (int i = 0; i < MG_REGION_SLOTS / 256; ++i)
+    sR[i * 256 + threadIdx.x] = FRESH ? e : __ldcs(g + i * 256 + threadIdx.x);
+  __syncthreads();
+  MgSlot *sS = reinterpret_cast<MgSlot *>(sR);
+  uint32_t fresh = 0;
+  for (uint32_t j = threadIdx.x, u = 0; j < cnt; j += 256, ++u)
+    { unsigned long long key;
+      if (u < (uint32_t)PRELOAD)
+        { // select from the preloaded registers without dynamic indexing
+          key = pre[0];
+#pragma unroll
+          for (int v = 1; v < PRELOAD; ++v) if (u == (uint32_t)v) key = pre[v];
+        }
+      else key = b[j];
       uint32_t s = (uint32_t)mg_slot_hash(key, slotBits) & (MG_REGION_SLOTS - 1);
       uint32_t probes = 0;
       for (; probes < MG_REGION_SLOTS; ++probes, s = (s + 1) & (MG_REGION_SLOTS - 1))
@@ -423,12 +511,16 @@ const uint32_t *mg_table_bulk_overflow_count(const ModgpuTable *t) { return t->d
 
 int mg_table_bulk_finish(ModgpuTable *t, const MgBulk *b, cudaStream_t st)
 {
+  static int variant = -1;
+  if (variant < 0) { const char *v = getenv("MODGPU_BUILD_VARIANT"); variant = v ? atoi(v) : 0; }
+#define MG_BUILD_LAUNCH(FR, PL) region_build_kernel<FR, PL><<<b->nRegions, 256, 0, st>>>(t->slots, t->slotBits, b->buckets, b->cursors, b->cap, t->dEntries, t->dError)
   if (t->clearPending)
-    { region_build_kernel<true><<<b->nRegions, 256, 0, st>>>(t->slots, t->slotBits, b->buckets, b->cursors, b->cap, t->dEntries, t->dError);
+    { if (variant == 1) MG_BUILD_LAUNCH(true, 4); else if (variant == 2) MG_BUILD_LAUNCH(true, 2); else MG_BUILD_LAUNCH(true, 0);
       t->clearPending = false;
     }
   else
-    region_build_kernel<false><<<b->nRegions, 256, 0, st>>>(t->slots, t->slotBits, b->buckets, b->cursors, b->cap, t->dEntries, t->dError);
+    { if (variant == 1) MG_BUILD_LAUNCH(false, 4); else if (variant == 2) MG_BUILD_LAUNCH(false, 2); else MG_BUILD_LAUNCH(false, 0); }
+#undef MG_BUILD_LAUNCH
   MG_LAUNCH_CHECK("region_build");
   // stragglers of over-full buckets go straight into HBM; their number is only known on the device:
   // the insert kernel reads it as the 64-bit word {cursors[nRegions], cursors[nRegions+1] == 0}
@@ -452,6 +544,49 @@ int mg_table_insert_bulk(ModgpuTable *t, const uint64_t *d_kmers, uint64_t n, cu
   MG_LAUNCH_CHECK("bucket_scatter");
   return mg_table_bulk_finish(t, &b, st);
 }
+
+// bulk insert of nSegs device segments with device-side counts (no host round trip)
+int mg_table_insert_segments(ModgpuTable *t, const uint64_t *d_segs, uint32_t nSegs, uint64_t segCap,
+                             const uint32_t *d_counts, uint64_t expectedN, cudaStream_t st)
+{
+  if (!nSegs || !segCap) return MODGPU_OK;
+  MgBulk b;
+  int rc = mg_table_bulk_begin(t, expectedN, (uint64_t)nSegs * segCap, &b, st);
+  if (rc) return rc;
+  bucket_scatter_seg_kernel<<<grid_for(segCap, 16), 256, 0, st>>>(d_segs, nSegs, segCap, d_counts, t->slotBits, b.nRegions, b.cap,
+                                                                  b.cursors, b.buckets, b.overflow, b.overflowCap, t->dError);
+  MG_LAUNCH_CHECK("bucket_scatter_seg");
+  return mg_table_bulk_finish(t, &b, st);
+}
+
+// build every region from nSrc received bucket arrays (each nRegions x cap) + per-source overflow segments
+int mg_table_build_from_buckets(ModgpuTable *t, const uint64_t *d_buckets, const uint32_t *d_cursors, uint32_t cap, uint32_t nSrc,
+                                const uint64_t *d_overflow, uint64_t overflowCap, const uint32_t *d_ovfCounts, cudaStream_t st)
+{
+  const uint32_t nRegions = (uint32_t)(t->nSlots >> MG_REGION_BITS);
+  if (t->clearPending)
+    { region_build_multi_kernel<true><<<nRegions, 256, 0, st>>>(t->slots, t->slotBits, d_buckets, d_cursors, cap, nSrc, nRegions, t->dEntries, t->dError);
+      t->clearPending = false;
+    }
+  else
+    region_build_multi_kernel<false><<<nRegions, 256, 0, st>>>(t->slots, t->slotBits, d_buckets, d_cursors, cap, nSrc, nRegions, t->dEntries, t->dError);
+  MG_LAUNCH_CHECK("region_build_multi");
+  // the (rare) k-mers that did not fit their bucket at the sender: direct inserts, counts on the device.
+  // d_ovfCounts are uint32; widen into the table's scratch so that the insert kernel can read 64-bit counts.
+  if (!t->dCursors) MG_CUDA(cudaMalloc(&t->dCursors, ((size_t)nRegions + 16) * sizeof(uint32_t)));
+  for (uint32_t s = 0; d_overflow && s < nSrc; ++s)
+    { unsigned long long *wide = t->dEntries + 4 + (s & 3);
+      MG_CUDA(cudaMemsetAsync(wide, 0, 8, st));
+      MG_CUDA(cudaMemcpyAsync(wide, d_ovfCounts + s, 4, cudaMemcpyDeviceToDevice, st));
+      table_insert_kernel<false><<<grid_for(65536, 4), 256, 0, st>>>(t->slots, t->slotBits, d_overflow + (uint64_t)s * overflowCap, wide,
+                                                                     overflowCap, nullptr, t->dEntries, t->dError);
+      MG_LAUNCH_CHECK("overflow_insert");
+    }
+  return MODGPU_OK;
+}
+
+uint32_t mg_table_regions(const ModgpuTable *t) { return (uint32_t)(t->nSlots >> MG_REGION_BITS); }
+uint32_t mg_table_slot_bits(const ModgpuTable *t) { return t->slotBits; }
 
 uint64_t mg_table_bulk_threshold(const ModgpuTable *t) { return t->nSlots / 8; }
 

@@ -56,6 +56,18 @@ class ShardedModset:
         # all kernels and NCCL calls are ordered on torch's current stream
         self.local.set_stream(torch.cuda.current_stream().cuda_stream)
         self.total_selected = 0
+        self.w = w
+        # fused, sync-free exchange (default for world > 1): per-owner segments straight out of hash_select,
+        # equal-split all-to-all, bulk insert of the received segments with device-side counts
+        self.fused = True
+        # fused flavour: "peer" = per-(owner, region) buckets consumed directly by the owner's region build
+        #                "segments" = per-owner segments + a scatter pass at the receiver
+        self.fused_mode = "peer"
+        self._peer_cap = 0
+        self._seg_cap = 0
+        self._sel_pending = 0
+        self._sel_acc = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self._ovf_acc = torch.zeros(1, dtype=torch.int32, device=self.dev)
 
     def close(self):
         self.local.close()
@@ -66,6 +78,8 @@ class ShardedModset:
     def _route_and_insert(self, kptr, n):
         st = torch.cuda.current_stream().cuda_stream
         self.total_selected += n
+        if self.world > 1:
+            self._sel_pending += n
         if self.world == 1:
             check(self._lib.modgpuModsetInsertDevice(self.local._p, C.c_void_p(kptr), n), "insert")
             return n
@@ -80,12 +94,113 @@ class ShardedModset:
         self._keep = (send, recv)            # keep alive until the stream has consumed them
         return n
 
+    # ---- fused exchange ---------------------------------------------------
+    def _ensure_segments(self, nbases):
+        expected = nbases // max(self.w, 1) + 1
+        cap = int(expected / self.world * 1.15) + 8192
+        if cap > self._seg_cap:
+            self._seg_cap = cap
+            self._send = torch.empty(self.world * cap, dtype=torch.int64, device=self.dev)
+            self._recv = torch.empty(self.world * cap, dtype=torch.int64, device=self.dev)
+            self._scount = torch.zeros(self.world, dtype=torch.int32, device=self.dev)
+            self._rcount = torch.zeros(self.world, dtype=torch.int32, device=self.dev)
+        return expected
+
+    def _exchange_and_insert(self, expected):
+        cap = self._seg_cap
+        dist.all_to_all_single(self._rcount, self._scount, group=self.group)
+        dist.all_to_all_single(self._recv, self._send, group=self.group)          # equal splits of cap k-mers
+        check(self._lib.modgpuModsetInsertSegments(self.local._p, C.c_void_p(self._recv.data_ptr()), self.world, cap,
+                                                   C.c_void_p(self._rcount.data_ptr()), expected), "insertSegments")
+        self._sel_acc += self._scount.sum()
+        self._ovf_acc = torch.maximum(self._ovf_acc, (self._scount.max() > cap).to(torch.int32).reshape(1))
+
+    def _ensure_peer(self, nbases):
+        import math
+        R = int(self._lib.modgpuModsetRegions(self.local._p))
+        expected = nbases // max(self.w, 1) + 1
+        mean = expected / float(self.world * R)
+        # bucket capacity: Poisson mean + 10 % + 4 sigma; what does not fit (repeated k-mers pile up in
+        # their bucket) travels in the per-owner overflow segments, exchanged with their true sizes
+        cap = (int(1.1 * mean + 4.0 * math.sqrt(mean) + 8) + 1) & ~1
+        if cap > self._peer_cap:
+            self._peer_cap, self._R = cap, R
+            self._ovf_cap = max(65536, expected // 4)
+            n = self.world * R
+            self._sb = torch.empty(n * cap, dtype=torch.int64, device=self.dev)
+            self._rb = torch.empty(n * cap, dtype=torch.int64, device=self.dev)
+            self._sc = torch.zeros(n, dtype=torch.int32, device=self.dev)
+            self._rc = torch.zeros(n, dtype=torch.int32, device=self.dev)
+            self._so = torch.empty(self.world * self._ovf_cap, dtype=torch.int64, device=self.dev)
+            self._soc = torch.zeros(self.world, dtype=torch.int32, device=self.dev)
+            self._roc = torch.zeros(self.world, dtype=torch.int32, device=self.dev)
+            self._cnt = torch.zeros(1, dtype=torch.int64, device=self.dev)
+
+    def _peer_exchange_and_build(self):
+        """returns False when some rank's overflow segment overflowed: nothing was exchanged or inserted, every
+        rank takes the list path for this batch (the decision is collective)"""
+        g, G, oc = self.group, self.world, self._ovf_cap
+        dist.all_to_all_single(self._roc, self._soc, group=g)                        # overflow counts
+        flag = (self._soc.max() > oc).to(torch.int64).reshape(1)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=g)
+        host = torch.cat([flag, self._soc.to(torch.int64), self._roc.to(torch.int64), self._cnt]).cpu().tolist()   # the one sync
+        if host[0]:
+            return False
+        ssz, rsz = [int(x) for x in host[1:1 + G]], [int(x) for x in host[1 + G:1 + 2 * G]]
+        dist.all_to_all_single(self._rc, self._sc, group=g)                          # bucket fill counts
+        dist.all_to_all_single(self._rb, self._sb, group=g)                          # the buckets, equal splits
+        check(self._lib.modgpuModsetBuildFromBuckets(self.local._p, C.c_void_p(self._rb.data_ptr()), C.c_void_p(self._rc.data_ptr()),
+                                                     self._peer_cap, G, None, 0, None), "buildFromBuckets")
+        if sum(ssz) or sum(rsz) or True:                                             # collective: every rank calls it
+            so = torch.cat([self._so[o * oc:o * oc + ssz[o]] for o in range(G)]) if sum(ssz) else self._so[:0]
+            ro = torch.empty(sum(rsz), dtype=torch.int64, device=self.dev)
+            dist.all_to_all_single(ro, so, output_split_sizes=rsz, input_split_sizes=ssz, group=g)
+            if ro.numel():
+                check(self._lib.modgpuModsetInsertDevice(self.local._p, C.c_void_p(ro.data_ptr()), ro.numel()), "insertOverflow")
+            self._keep = (so, ro)
+        self._sel_pending += int(host[-1])
+        return True
+
+    def synchronize(self):
+        """finish the outstanding fused batches; returns the number of k-mers this rank selected since the
+        last call.  Raises when a segment overflowed (heavily skewed batch): repeat it with fused = False."""
+        if self.world == 1:
+            n, self.total_selected = self.total_selected, 0
+            return n
+        vals = torch.cat([self._sel_acc, self._ovf_acc.to(torch.int64)]).cpu().tolist()
+        self._sel_acc.zero_(); self._ovf_acc.zero_()
+        if vals[1]:
+            raise ModgpuError("owner segment overflow (skewed batch): repeat with ShardedModset.fused = False")
+        n, self._sel_pending = int(vals[0]) + self._sel_pending, 0
+        return n
+
     def add_device(self, d_bases, d_offsets, nseq, nbases, is_ascii=0):
         """this rank's chunk, resident in device memory (< 2^32 bases per call)"""
         if self.world == 1:                      # nothing to route: the single-GPU pipeline (fused select -> table)
             n = self.local.add_device(d_bases, d_offsets, nseq, nbases, is_ascii)
             self.total_selected += n
             return n
+        if self.fused and self.fused_mode == "peer":
+            self._ensure_peer(nbases)
+            check(self._lib.modgpuModsetSelectBucketsDevice(self.local._p, C.c_void_p(d_bases), C.c_void_p(d_offsets), nseq, nbases,
+                                                            is_ascii, self.world, C.c_void_p(self._sb.data_ptr()), self._peer_cap,
+                                                            C.c_void_p(self._sc.data_ptr()), C.c_void_p(self._so.data_ptr()),
+                                                            self._ovf_cap, C.c_void_p(self._soc.data_ptr()),
+                                                            C.c_void_p(self._cnt.data_ptr())), "selectBuckets")
+            if self._peer_exchange_and_build():
+                return 0                         # the count comes from synchronize()
+            return self._add_device_list(d_bases, d_offsets, nseq, nbases, is_ascii)
+        if self.fused:
+            expected = self._ensure_segments(nbases)
+            check(self._lib.modgpuModsetSelectOwnersDevice(self.local._p, C.c_void_p(d_bases), C.c_void_p(d_offsets), nseq, nbases,
+                                                           is_ascii, self.world, C.c_void_p(self._send.data_ptr()), self._seg_cap,
+                                                           C.c_void_p(self._scount.data_ptr())), "selectOwners")
+            self._exchange_and_insert(expected)
+            return 0                             # asynchronous: the count comes from synchronize()
+        return self._add_device_list(d_bases, d_offsets, nseq, nbases, is_ascii)
+
+    def _add_device_list(self, d_bases, d_offsets, nseq, nbases, is_ascii=0):
+        """list-based exchange: robust for any skew (variable all-to-all of the selected list)"""
         kptr = C.c_void_p()
         n = C.c_uint64()
         check(self._lib.modgpuModsetSelectDevice(self.local._p, C.c_void_p(d_bases), C.c_void_p(d_offsets), nseq, nbases,
@@ -98,11 +213,33 @@ class ShardedModset:
         offsets = np.ascontiguousarray(offsets, np.uint64)
         return self.add_pointers(data.ctypes.data, offsets.ctypes.data, len(offsets) - 1, is_ascii)
 
-    def add_pointers(self, host_ptr, offsets_ptr, nseq, is_ascii=0):
+    def add_pointers(self, host_ptr, offsets_ptr, nseq, is_ascii=0, nbases=None):
         if self.world == 1:
             n = self.local.add_pointers(host_ptr, offsets_ptr, nseq, is_ascii)
             self.total_selected += n
             return n
+        if self.fused and nbases is None:
+            nbases = int((C.c_uint64 * (nseq + 1)).from_address(offsets_ptr)[nseq])
+        if self.fused and self.fused_mode == "peer":
+            self._ensure_peer(nbases)
+            check(self._lib.modgpuModsetSelectBucketsHost(self.local._p, C.c_void_p(host_ptr), C.c_void_p(offsets_ptr), nseq,
+                                                          is_ascii, self.world, C.c_void_p(self._sb.data_ptr()), self._peer_cap,
+                                                          C.c_void_p(self._sc.data_ptr()), C.c_void_p(self._so.data_ptr()),
+                                                          self._ovf_cap, C.c_void_p(self._soc.data_ptr()),
+                                                          C.c_void_p(self._cnt.data_ptr())), "selectBuckets")
+            if self._peer_exchange_and_build():
+                return 0
+            return self._add_pointers_list(host_ptr, offsets_ptr, nseq, is_ascii)
+        if self.fused:
+            expected = self._ensure_segments(nbases)
+            check(self._lib.modgpuModsetSelectOwnersHost(self.local._p, C.c_void_p(host_ptr), C.c_void_p(offsets_ptr), nseq,
+                                                         is_ascii, self.world, C.c_void_p(self._send.data_ptr()), self._seg_cap,
+                                                         C.c_void_p(self._scount.data_ptr())), "selectOwners")
+            self._exchange_and_insert(expected)
+            return 0
+        return self._add_pointers_list(host_ptr, offsets_ptr, nseq, is_ascii)
+
+    def _add_pointers_list(self, host_ptr, offsets_ptr, nseq, is_ascii=0):
         kptr = C.c_void_p()
         n = C.c_uint64()
         check(self._lib.modgpuModsetSelectHost(self.local._p, C.c_void_p(host_ptr), C.c_void_p(offsets_ptr), nseq,

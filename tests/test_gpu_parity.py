@@ -449,6 +449,87 @@ def test_gpu_matches_golden(mg, name):
 
 
 # --------------------------------------------------------------- multi-GPU --
+def test_peer_buckets_single_gpu(mg, torch_cuda, orc):
+    """fully fused multi-GPU building blocks on one GPU: hash_select into per-(owner, region) buckets with tiny
+    bucket capacity (forces the overflow segments), then every owner's share is built into its own table:
+    the union of the G tables == the plain modset"""
+    import ctypes as C
+    from modimizer_b200 import _lib
+    lib = _lib.load()
+    sp = he.read_spec(12345, 300000, 42, 3000, 2000)
+    nreads = 2000
+    data = he.reads(sp, 0, nreads)
+    offs = np.arange(nreads + 1, dtype=np.uint64) * np.uint64(3000)
+    dev = torch_cuda.device("cuda:0")
+    d_b = torch_cuda.from_numpy(data).to(dev); d_o = torch_cuda.from_numpy(offs.view(np.int64)).to(dev)
+    for (k, d, G, cap) in ((31, 64, 2, 64), (19, 31, 3, 4), (19, 31, 1, 200)):
+        src = mg.Modset(22, k, d, 17)
+        src.set_stream(torch_cuda.cuda.current_stream().cuda_stream)
+        R = lib.modgpuModsetRegions(src._p)
+        oms = orc.modset_new(22, k, d, 17)
+        tot = orc.modset_add(oms, data, offs)
+        ovf_cap = tot + 16
+        sb = torch_cuda.zeros(G * R * cap, dtype=torch_cuda.int64, device=dev)
+        sc = torch_cuda.zeros(G * R, dtype=torch_cuda.int32, device=dev)
+        so = torch_cuda.zeros(G * ovf_cap, dtype=torch_cuda.int64, device=dev)
+        soc = torch_cuda.zeros(G, dtype=torch_cuda.int32, device=dev)
+        cnt = torch_cuda.zeros(1, dtype=torch_cuda.int64, device=dev)
+        _lib.check(lib.modgpuModsetSelectBucketsDevice(src._p, d_b.data_ptr(), d_o.data_ptr(), nreads, len(data), 0, G, sb.data_ptr(), cap,
+                                                       sc.data_ptr(), so.data_ptr(), ovf_cap, soc.data_ptr(), cnt.data_ptr()), "selectBuckets")
+        torch_cuda.cuda.synchronize()
+        assert int(cnt.item()) == tot
+        allv, alld = [], []
+        for g in range(G):                                   # owner g builds from "its" slice of the send buffer
+            t = mg.Modset(22, k, d, 17)
+            t.set_stream(torch_cuda.cuda.current_stream().cuda_stream)
+            _lib.check(lib.modgpuModsetBuildFromBuckets(t._p, sb.data_ptr() + g * R * cap * 8, sc.data_ptr() + g * R * 4, cap, 1,
+                                                        so.data_ptr() + g * ovf_cap * 8, ovf_cap, soc.data_ptr() + g * 4), "build")
+            v, dd, _ = t.sorted_dump()
+            assert all(lib.modgpuOwnerOf(int(x), G) == g for x in v[:200])
+            allv.append(v); alld.append(dd)
+            t.close()
+        v = np.concatenate(allv); dd = np.concatenate(alld)
+        o = np.argsort(v)
+        ov, od, _ = orc.modset_sorted(oms)
+        assert np.array_equal(v[o], ov) and np.array_equal(dd[o], od), (k, d, G)
+        src.close(); orc._modset_free(oms)
+
+
+def test_owner_segments_single_gpu(mg, torch_cuda, orc):
+    """the fused multi-GPU building blocks on one GPU: hash_select into per-owner segments, then a bulk
+    insert of those segments (as if received from peers) == the plain modset"""
+    import ctypes as C
+    from modimizer_b200 import _lib
+    lib = _lib.load()
+    sp = he.read_spec(12345, 300000, 42, 3000, 2000)
+    nreads = 2000
+    data = he.reads(sp, 0, nreads)
+    offs = np.arange(nreads + 1, dtype=np.uint64) * np.uint64(3000)
+    dev = torch_cuda.device("cuda:0")
+    d_b = torch_cuda.from_numpy(data).to(dev); d_o = torch_cuda.from_numpy(offs.view(np.int64)).to(dev)
+    for (k, d, G) in ((31, 64, 3), (19, 31, 8), (19, 4, 2)):
+        ms = mg.Modset(22, k, d, 17)
+        ms.set_stream(torch_cuda.cuda.current_stream().cuda_stream)
+        oms = orc.modset_new(22, k, d, 17)
+        tot = orc.modset_add(oms, data, offs)
+        cap = int(tot / G * 1.3) + 1000
+        seg = torch_cuda.zeros(G * cap, dtype=torch_cuda.int64, device=dev)
+        cnt = torch_cuda.zeros(G, dtype=torch_cuda.int32, device=dev)
+        _lib.check(lib.modgpuModsetSelectOwnersDevice(ms._p, d_b.data_ptr(), d_o.data_ptr(), nreads, len(data), 0, G,
+                                                      seg.data_ptr(), cap, cnt.data_ptr()), "selectOwners")
+        torch_cuda.cuda.synchronize()
+        c = cnt.cpu().numpy()
+        assert int(c.sum()) == tot and (c <= cap).all()
+        segs = seg.cpu().numpy().view(np.uint64).reshape(G, cap)
+        for g in range(G):
+            assert all(lib.modgpuOwnerOf(int(x), G) == g for x in segs[g, :min(int(c[g]), 300)])
+        _lib.check(lib.modgpuModsetInsertSegments(ms._p, seg.data_ptr(), G, cap, cnt.data_ptr(), tot), "insertSegments")
+        gv, gd, _ = ms.sorted_dump(); ov, od, _ = orc.modset_sorted(oms)
+        assert np.array_equal(gv, ov) and np.array_equal(gd, od), (k, d, G)
+        ms.close(); orc._modset_free(oms)
+
+
+
 def _sharded_worker(rank, world, port, tmpdir):
     import os, sys
     here = os.path.dirname(os.path.abspath(__file__))
@@ -466,10 +547,18 @@ def _sharded_worker(rank, world, port, tmpdir):
     data = he.reads(sp, rank * per, per)
     offs = np.arange(per + 1, dtype=np.uint64) * np.uint64(5000)
     sm = ShardedModset(22, 19, 31, 17)
-    n1 = sm.add(data, offs)                                   # host path
+    sm.add(data, offs)                                        # host path (fused exchange)
+    n1 = sm.synchronize()
     d_b = torch.from_numpy(data).cuda(); d_o = torch.from_numpy(offs.view(np.int64)).cuda()
-    n2 = sm.add_device(d_b.data_ptr(), d_o.data_ptr(), per, len(data))   # device path, same data again
-    assert n1 == n2
+    sm.add_device(d_b.data_ptr(), d_o.data_ptr(), per, len(data))        # device path, same data again
+    n2 = sm.synchronize()
+    assert n1 == n2 and n1 > 0
+    sm.fused_mode = "segments"                                # per-owner segments + scatter at the receiver
+    sm.add_device(d_b.data_ptr(), d_o.data_ptr(), per, len(data))
+    assert sm.synchronize() == n1
+    sm.fused = False                                          # the list-based exchange, once more
+    n3 = sm.add_device(d_b.data_ptr(), d_o.data_ptr(), per, len(data))
+    assert n3 == n1
     v, d, i = sm.gather_sorted_dump()
     h = sm.histogram()
     gmax = sm.global_max()
@@ -492,7 +581,8 @@ def test_sharded_modset_two_gpus(mg, torch_cuda, orc, tmp_path):
     data = he.reads(sp, 0, 600)
     offs = np.arange(601, dtype=np.uint64) * np.uint64(5000)
     oms = orc.modset_new(22, 19, 31, 17)
-    orc.modset_add(oms, data, offs); orc.modset_add(oms, data, offs)        # every rank added its chunk twice
+    for _ in range(4):                                        # every rank added its chunk four times
+        orc.modset_add(oms, data, offs)
     ov, od, _ = orc.modset_sorted(oms)
     assert np.array_equal(r["v"], ov) and np.array_equal(r["d"], od)
     assert np.array_equal(r["h"], orc.modset_hist(oms)) and int(r["gmax"]) == len(ov)
