@@ -245,6 +245,27 @@ int modgpuModsetInsertSegments(ModgpuModset *ms, const uint64_t *d_segments, uin
 int modgpuModsetInsertDevice(ModgpuModset *ms, const uint64_t *d_kmers, uint64_t n);
 int modgpuModsetClear(ModgpuModset *ms);
 
+/* ------------------------------------------------ whole-set operations --
+ * modsetDepthPrune (modset.c:64-77): keep entries with min <= depth < max
+ * (max == 0: no upper bound), renumbered in their old index order. */
+int modgpuModsetPrune(ModgpuModset *ms, int min, int max);
+/* modsetMerge (modset.c:106-128): union of b into a; depths add (clamp 65535), copy
+ * numbers add (clamp 3), new entries numbered in b's index order.  Returns 1 when
+ * merged, 0 when the hashers differ (reference returns false), < 0 on error. */
+int modgpuModsetMerge(ModgpuModset *a, ModgpuModset *b);
+/* modsetCreate for an existing hasher (e.g. read from a file) */
+ModgpuModset *modgpuModsetCreateWithHasher(int bits, const ModgpuHasher *h);
+/* modsetWrite / modsetRead (modset.c:79-104): the reference's "MSHSTv2" file, readable by an
+ * unmodified `modutils -r`; gzip != 0 compresses like fzopen(path,"w") (utils.c:108-127) */
+int modgpuModsetWriteMod(ModgpuModset *ms, const char *path, int gzip);
+ModgpuModset *modgpuModsetReadMod(const char *path);
+/* hot loop of modasm's readsetFileRead (modasm.c:151-191): per read the hits
+ * (index | 0x80000000 when forward) and dx (U16 distance to the previous hit) of
+ * the modimizers found in the set, the misses per read, and depth re-counted from
+ * these reads (resetDepth != 0 zeroes it first).  Returns the hit total. */
+uint64_t modgpuModsetReadset(ModgpuModset *ms, const char *bases, const uint64_t *offs, uint64_t nSeq, int isAscii,
+                             int resetDepth, uint64_t *hitOff, uint32_t *hit, uint16_t *dx, int32_t *nMiss, uint64_t cap);
+
 /* per-kernel accumulated device time (ms) since the last reset, measured with
  * CUDA events on the object's stream when profiling is enabled */
 #define MODGPU_T_PACK 0

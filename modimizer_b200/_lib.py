@@ -90,6 +90,12 @@ _SIGS = {
     "modgpuOwnerOf": (u32, [u64, u32]),
     "modgpuOwnerCount": (C.c_int, [vp, u64, u32, vp, vp]),
     "modgpuOwnerScatter": (C.c_int, [vp, u64, u32, vp, vp, vp]),
+    "modgpuModsetPrune": (C.c_int, [vp, C.c_int, C.c_int]),
+    "modgpuModsetMerge": (C.c_int, [vp, vp]),
+    "modgpuModsetCreateWithHasher": (vp, [C.c_int, C.POINTER(Hasher)]),
+    "modgpuModsetWriteMod": (C.c_int, [vp, C.c_char_p, C.c_int]),
+    "modgpuModsetReadMod": (vp, [C.c_char_p]),
+    "modgpuModsetReadset": (u64, [vp, vp, vp, u64, C.c_int, C.c_int, vp, vp, vp, vp, u64]),
     "modgpuModsetProfile": (C.c_int, [vp, C.c_int]),
     "modgpuModsetTimes": (C.c_int, [vp, vp, vp]),
     "modgpuReferenceBuild": (vp, [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, u64, C.c_int, vp]),

@@ -21,6 +21,7 @@
 #include <stdlib.h>
 #include "mg_device.cuh"
 #include "mg_scan.cuh"
+#include "mg_table.cuh"
 
 struct ModgpuTable {
   MgSlot *slots;
@@ -42,11 +43,6 @@ struct ModgpuTable {
   uint64_t overflowCap;
 };
 
-#define MG_REGION_BITS 11
-#define MG_REGION_SLOTS (1u << MG_REGION_BITS)
-__device__ __forceinline__ uint64_t next_slot(uint64_t s)
-{ return (s & ~(uint64_t)(MG_REGION_SLOTS - 1)) | ((s + 1) & (MG_REGION_SLOTS - 1)); }
-
 // ------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(256) table_clear_kernel(MgSlot *slots, uint64_t nSlots)
 {
@@ -55,35 +51,6 @@ __global__ void __launch_bounds__(256) table_clear_kernel(MgSlot *slots, uint64_
   e.x = 0xFFFFFFFFu; e.y = 0xFFFFFFFFu; e.z = 0u; e.w = MG_AUX_FRESH;
   uint4 *p = reinterpret_cast<uint4 *>(slots);
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nSlots; i += stride) p[i] = e;
-}
-
-// find-or-insert; returns the slot or UINT64_MAX when the table is full
-__device__ __forceinline__ uint64_t probe_insert(MgSlot *slots, uint32_t slotBits, uint64_t key, bool *isNew)
-{
-  uint64_t s = mg_slot_hash(key, slotBits);
-  *isNew = false;
-  for (uint32_t probes = 0; probes < MG_REGION_SLOTS; ++probes, s = next_slot(s))
-    { unsigned long long *kp = reinterpret_cast<unsigned long long *>(&slots[s].key);
-      unsigned long long cur = __ldcg(kp);
-      if (cur == key) return s;
-      if (cur == MG_EMPTY)
-        { unsigned long long old = atomicCAS(kp, MG_EMPTY, (unsigned long long)key);
-          if (old == MG_EMPTY) { *isNew = true; return s; }
-          if (old == key) return s;
-        }
-    }
-  return 0xFFFFFFFFFFFFFFFFull;
-}
-
-__device__ __forceinline__ uint64_t probe_find(const MgSlot *slots, uint32_t slotBits, uint64_t key)
-{
-  uint64_t s = mg_slot_hash(key, slotBits);
-  for (uint32_t probes = 0; probes < MG_REGION_SLOTS; ++probes, s = next_slot(s))
-    { unsigned long long cur = __ldcg(reinterpret_cast<const unsigned long long *>(&slots[s].key));
-      if (cur == key) return s;
-      if (cur == MG_EMPTY) break;
-    }
-  return 0xFFFFFFFFFFFFFFFFull;
 }
 
 // n is read from device memory (the count hash_select just produced) so that no
@@ -585,6 +552,7 @@ int mg_table_build_from_buckets(ModgpuTable *t, const uint64_t *d_buckets, const
   return MODGPU_OK;
 }
 
+void mg_table_counters(ModgpuTable *t, unsigned long long **entries, uint32_t **error) { *entries = t->dEntries; *error = t->dError; }
 uint32_t mg_table_regions(const ModgpuTable *t) { return (uint32_t)(t->nSlots >> MG_REGION_BITS); }
 uint32_t mg_table_slot_bits(const ModgpuTable *t) { return t->slotBits; }
 

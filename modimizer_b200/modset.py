@@ -224,6 +224,57 @@ class Modset:
                                            depth.ctypes.data if depth is not None else None,
                                            info.ctypes.data if info is not None else None, len(value)), "modsetImport")
 
+    def prune(self, min_depth, max_depth=0):
+        """modsetDepthPrune (reference modset.c:64-77): keep min <= depth < max (0 = no upper bound)"""
+        check(self._lib.modgpuModsetPrune(self._p, int(min_depth), int(max_depth)), "modsetDepthPrune")
+
+    def merge(self, other):
+        """modsetMerge (reference modset.c:106-128); False when the hashers are incompatible"""
+        rc = self._lib.modgpuModsetMerge(self._p, other._p)
+        if rc < 0:
+            raise ModgpuError("modsetMerge: " + _lib.last_error())
+        return bool(rc)
+
+    def write_mod(self, path, gzip=False):
+        """modsetWrite (reference modset.c:79-88): "MSHSTv2" file an unmodified modutils -r can load"""
+        check(self._lib.modgpuModsetWriteMod(self._p, str(path).encode(), 1 if gzip else 0), "modsetWrite")
+
+    @classmethod
+    def read_mod(cls, path):
+        """modsetRead (reference modset.c:90-104), plain or gzip'd"""
+        lib = _lib.require_device()
+        p = lib.modgpuModsetReadMod(str(path).encode())
+        if not p:
+            raise ModgpuError("modsetRead: " + _lib.last_error())
+        bits = 0
+        ms = cls(bits, _handle=p)
+        return ms
+
+    def readset(self, data, offsets=None, is_ascii=None, reset_depth=True, cap=None):
+        """hot loop of modasm's readsetFileRead (reference modasm.c:151-191)"""
+        if offsets is None:
+            data, offsets, auto = concat(data)
+        else:
+            data = np.ascontiguousarray(data, np.uint8)
+            auto = 1 if (data.size and data.max() > 3) else 0
+        if is_ascii is None:
+            is_ascii = auto
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        nseq = len(offsets) - 1
+        if cap is None:
+            cap = max(1, len(data))
+        ho = np.zeros(nseq + 1, np.uint64)
+        hit = np.zeros(cap, np.uint32)
+        dx = np.zeros(cap, np.uint16)
+        miss = np.zeros(max(nseq, 1), np.int32)
+        n = self._lib.modgpuModsetReadset(self._p, data.ctypes.data if data.size else None, offsets.ctypes.data, nseq,
+                                          int(is_ascii), 1 if reset_depth else 0, ho.ctypes.data, hit.ctypes.data,
+                                          dx.ctypes.data, miss.ctypes.data, cap)
+        if n == U64MAX:
+            raise ModgpuError("readset: " + _lib.last_error())
+        n = int(min(n, cap))
+        return dict(hitOff=ho, hit=hit[:n], dx=dx[:n], nMiss=miss[:nseq])
+
     def write_text(self, path):
         """-wt dump (reference modutils.c:191-200)"""
         v, d, i = self.export()

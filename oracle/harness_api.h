@@ -56,6 +56,13 @@ int HX(modset_summary)(HxModset *ms, char *buf, int n);             /* modset.c:
 void HX(modset_prune)(HxModset *ms, int min, int max);              /* modset.c:64-77 */
 int HX(modset_merge)(HxModset *a, HxModset *b);                     /* modset.c:106-128 */
 
+/* hot loop of modasm's readsetFileRead (modasm.c:151-191): depth is zeroed and
+   re-counted from these reads; per read the hits (index | 0x80000000 when the
+   k-mer was seen forward) with dx = pos - previous hit's pos (U16), and the
+   number of modimizers that miss the set.  Returns the hit total. */
+int64_t HX(readset)(HxModset *ms, const char *codes, const uint64_t *offs, int64_t nseq,
+                    uint64_t *hitOff, uint32_t *hit, uint16_t *dx, int32_t *nMiss, int64_t cap);
+
 /* modmap reference index (modmap.c:93-134 + referencePack :74-91).
    counts = { nHashes, nCopy1, nCopy2, nMulti } */
 HxRef *HX(ref_build)(int bits, int k, int w, int seed, const char *codes,

@@ -315,6 +315,37 @@ int orc_modset_merge(HxModset *a, HxModset *b)
   return 1;
 }
 
+/* ----------------------------------------------------------------- readset */
+typedef struct { HxModset *ms; uint32_t *hit; uint16_t *dx; int64_t cap, n; int32_t *miss; int lastPos; } ReadsetCtx;
+
+static void emit_readset(void *ctx, uint64_t kmer, int pos, int isF)   /* modasm.c:168-178 */
+{
+  ReadsetCtx *c = (ReadsetCtx *)ctx;
+  uint32_t ix = modset_find(c->ms, kmer, 0);
+  if (!ix) { ++*c->miss; return; }
+  if (c->n < c->cap)
+    { c->hit[c->n] = isF ? (ix | 0x80000000u) : ix;
+      c->dx[c->n] = (uint16_t)(pos - c->lastPos);
+    }
+  c->lastPos = pos;
+  ++c->n;
+  if (c->ms->depth[ix] != 0xFFFF) ++c->ms->depth[ix];
+}
+
+int64_t orc_readset(HxModset *ms, const char *codes, const uint64_t *offs, int64_t nseq,
+                    uint64_t *hitOff, uint32_t *hit, uint16_t *dx, int32_t *nMiss, int64_t cap)
+{
+  memset(ms->depth, 0, ((size_t)ms->max + 1) * sizeof(uint16_t));    /* modasm.c:158 */
+  ReadsetCtx c = { ms, hit, dx, cap, 0, 0, 0 };
+  for (int64_t r = 0; r < nseq; ++r)
+    { hitOff[r] = (uint64_t)c.n;
+      nMiss[r] = 0; c.miss = &nMiss[r]; c.lastPos = 0;
+      scan_sequence(&ms->hasher, codes + offs[r], (int)(offs[r + 1] - offs[r]), emit_readset, &c);
+    }
+  hitOff[nseq] = (uint64_t)c.n;
+  return c.n;
+}
+
 /* -------------------------------------------------------- modmap reference */
 
 struct HxRef {

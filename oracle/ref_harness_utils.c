@@ -122,3 +122,30 @@ int ref_modset_summary(HxModset *h, char *buf, int n)
 void ref_modset_prune(HxModset *h, int min, int max) { modsetDepthPrune((Modset *)h, min, max); }
 
 int ref_modset_merge(HxModset *a, HxModset *b) { return modsetMerge((Modset *)a, (Modset *)b) ? 1 : 0; }
+
+/* the per-read statements of readsetFileRead (modasm.c:151-191) over the reference's own primitives;
+   modasm.c itself cannot be pulled in next to modutils.c (both define the same file-scope names) */
+int64_t ref_readset(HxModset *h, const char *codes, const uint64_t *offs, int64_t nseq,
+                    uint64_t *hitOff, uint32_t *hit, uint16_t *dx, int32_t *nMiss, int64_t cap)
+{
+  Modset *ms = (Modset *)h;
+  int64_t n = 0;
+  memset (ms->depth, 0, (ms->max+1)*sizeof(U16)) ;
+  for (int64_t r = 0; r < nseq; ++r)
+    { hitOff[r] = (uint64_t)n; nMiss[r] = 0;
+      SeqhashRCiterator *mi = modRCiterator(ms->hasher, (char *)codes + offs[r], (int)(offs[r + 1] - offs[r]));
+      U64 kmer; int lastPos = 0, pos; bool isForward;
+      while (modRCnext(mi, &kmer, &pos, &isForward))
+        { U32 index = modsetIndexFind(ms, kmer, false);
+          if (index)
+            { if (n < cap) { hit[n] = isForward ? (index | 0x80000000u) : index; dx[n] = pos - lastPos; }
+              lastPos = pos; ++n;
+              U16 *di = &ms->depth[index]; ++*di; if (!*di) *di = U16MAX;
+            }
+          else ++nMiss[r];
+        }
+      seqhashRCiteratorDestroy(mi);
+    }
+  hitOff[nseq] = (uint64_t)n;
+  return n;
+}

@@ -46,6 +46,7 @@ class Checker:
         f("modset_summary", C.c_int, [C.c_void_p, C.c_char_p, C.c_int])
         f("modset_prune", None, [C.c_void_p, C.c_int, C.c_int])
         f("modset_merge", C.c_int, [C.c_void_p, C.c_void_p])
+        f("readset", C.c_int64, [C.c_void_p, u8p, u64p, C.c_int64, u64p, u32p, u16p, i32p, C.c_int64])
         f("ref_build", C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_int, u8p, u64p, C.c_int64, u32p])
         f("ref_free", None, [C.c_void_p])
         f("ref_modset", C.c_void_p, [C.c_void_p])
@@ -109,6 +110,18 @@ class Checker:
         buf = C.create_string_buffer(4096)
         n = self._modset_summary(ms, buf, 4096)
         return buf.raw[:n].decode()
+
+    def readset(self, ms, codes, offs):
+        codes = np.ascontiguousarray(codes, np.uint8)
+        offs = np.ascontiguousarray(offs, np.uint64)
+        nseq = len(offs) - 1
+        cap = max(1, len(codes))
+        ho = np.zeros(nseq + 1, np.uint64)
+        hit = np.zeros(cap, np.uint32)
+        dx = np.zeros(cap, np.uint16)
+        miss = np.zeros(max(nseq, 1), np.int32)
+        n = self._readset(ms, codes, offs, nseq, ho, hit, dx, miss, cap)
+        return dict(hitOff=ho, hit=hit[:n], dx=dx[:n], nMiss=miss[:nseq])
 
     def ref_build(self, bits, k, w, seed, codes, offs):
         codes = np.ascontiguousarray(codes, np.uint8)

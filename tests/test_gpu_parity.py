@@ -427,6 +427,108 @@ def test_large_batch_properties(mg, torch_cuda):
     ms.close()
 
 
+# ------------------------------------------------------------- set operations --
+def _build_pair(mg, orc, bits, k, d, data, offs, exact=True):
+    ms = mg.Modset(bits, k, d, 17, exact_order=exact)
+    oms = orc.modset_new(bits, k, d, 17)
+    assert ms.add(data, offs, is_ascii=0) == orc.modset_add(oms, data, offs)
+    return ms, oms
+
+
+def test_prune_and_merge(mg, orc):
+    """modsetDepthPrune and modsetMerge (modset.c:64-77, 106-128): identical arrays, index order included"""
+    sp = he.read_spec(12345, 150000, 11, 2500, 3000)
+    d1 = he.reads(sp, 0, 1500); o1 = np.arange(1501, dtype=np.uint64) * np.uint64(2500)
+    d2 = he.reads(sp, 1000, 1200); o2 = np.arange(1201, dtype=np.uint64) * np.uint64(2500)
+    for (k, d) in ((19, 31), (31, 64)):
+        a, oa = _build_pair(mg, orc, 22, k, d, d1, o1)
+        b, ob = _build_pair(mg, orc, 22, k, d, d2, o2)
+        a.set_copy(3, 20, 40); orc._modset_setcopy(oa, 3, 20, 40)
+        b.set_copy(2, 15, 30); orc._modset_setcopy(ob, 2, 15, 30)
+        # prune b, then merge it into a
+        b.prune(3, 25); orc._modset_prune(ob, 3, 25)
+        for x, y in zip(b.export(), orc.modset_export(ob)):
+            assert np.array_equal(x, y), (k, d, "prune")
+        assert b.summary() == orc.modset_summary(ob)
+        b.prune(5, 0); orc._modset_prune(ob, 5, 0)                    # max = 0: no upper bound
+        for x, y in zip(b.export(), orc.modset_export(ob)):
+            assert np.array_equal(x, y), (k, d, "prune0")
+        assert a.merge(b) and orc._modset_merge(oa, ob) == 1
+        for x, y in zip(a.export(), orc.modset_export(oa)):
+            assert np.array_equal(x, y), (k, d, "merge")
+        assert a.summary() == orc.modset_summary(oa)
+        assert np.array_equal(a.histogram(), orc.modset_hist(oa))
+        # incompatible hashers are refused (modset.c:111)
+        c = mg.Modset(22, k, d + 1, 17)
+        assert not a.merge(c)
+        for m in (a, b, c):
+            m.close()
+        orc._modset_free(oa); orc._modset_free(ob)
+
+
+def test_mod_file_roundtrip_with_stock_modutils(mg, orc, tmp_path):
+    """modsetWrite / modsetRead (modset.c:79-104): a GPU-built .mod is loaded by the UNMODIFIED reference tool
+    (oracle/_ref/modutils -r), and a .mod written by the reference tool is loaded by us"""
+    import subprocess
+    sp = he.read_spec(4242, 100000, 3, 2000, 1000)
+    data = he.reads(sp, 0, 900); offs = np.arange(901, dtype=np.uint64) * np.uint64(2000)
+    ms, oms = _build_pair(mg, orc, 20, 19, 31, data, offs)
+    ms.set_copy(3, 20, 40); orc._modset_setcopy(oms, 3, 20, 40)
+    ov, od, oi = orc.modset_export(oms)
+    for gz in (False, True):
+        path = str(tmp_path / ("g%d.mod" % gz))
+        ms.write_mod(path, gzip=gz)
+        back = mg.Modset.read_mod(path)                                # our own reader
+        for x, y in zip(back.export(), (ov, od, oi)):
+            assert np.array_equal(x, y)
+        assert back.summary() == orc.modset_summary(oms)
+        assert (back.k, back.w, back.seed, back.factor1) == (19, 31, 17, ms.factor1)
+        back.close()
+    modutils = H.ref_cli("modutils")
+    if modutils:
+        wt, his = str(tmp_path / "dump.txt"), str(tmp_path / "dump.his")
+        r = subprocess.run([modutils, "-r", str(tmp_path / "g1.mod"), "-wt", wt, "-H", his], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        exp = ["modset bits 20 size %d k 19 w 31 seed 17" % (len(ov) + 1)]
+        exp += ["%d\t%s\t%d\t%d" % (j + 1, H.kmer_string(ov[j], 19), od[j], oi[j]) for j in range(len(ov))]
+        assert open(wt).read().splitlines() == exp
+        assert orc.modset_summary(oms) in r.stdout
+        # the other direction: the reference tool writes (gzip'd through fzopen), we read; and it can
+        # keep working on a set we wrote: lookups through ITS index[] (-P refpaint uses modsetIndexFind)
+        fa = str(tmp_path / "r.fa")
+        H.write_fasta(fa, [data[int(offs[j]):int(offs[j + 1])] for j in range(200)])
+        ref_mod = str(tmp_path / "ref.mod")
+        subprocess.run([modutils, "-c", "20", "19", "31", "17", "-a", fa, "-w", ref_mod], check=True, capture_output=True)
+        theirs = mg.Modset.read_mod(ref_mod)
+        o2 = orc.modset_new(20, 19, 31, 17)
+        orc.modset_add(o2, data[:int(offs[200])], offs[:201])
+        for x, y in zip(theirs.export(), orc.modset_export(o2)):
+            assert np.array_equal(x, y)
+        theirs.close(); orc._modset_free(o2)
+        paint = subprocess.run([modutils, "-r", str(tmp_path / "g0.mod"), "-P", fa], capture_output=True, text=True)
+        assert paint.returncode == 0 and paint.stdout.count("\n  ") > 1000          # hits found through the rebuilt index[]
+    ms.close(); orc._modset_free(oms)
+
+
+def test_readset_loop(mg, orc):
+    """modasm readsetFileRead hot loop (modasm.c:151-191) against the oracle"""
+    g = he.genome(777, 0, 200000, 0)
+    offs = np.array([0, 120000, 120000, 200000], np.uint64)
+    sp = he.read_spec(777, 200000, 9, 3000, 20000)
+    rd = he.reads(sp, 0, 300); roffs = np.arange(301, dtype=np.uint64) * np.uint64(3000)
+    for (k, d) in ((19, 31), (31, 64), (15, 4)):
+        ms, oms = _build_pair(mg, orc, 22, k, d, g, offs)
+        for rep in range(2):                                            # twice: depth is reset and re-counted each time
+            gr = ms.readset(rd, roffs, is_ascii=0)
+            orr = orc.readset(oms, rd, roffs)
+            for key in orr:
+                assert np.array_equal(gr[key], orr[key]), (k, d, key)
+            assert len(orr["hit"]) > 100
+            for x, y in zip(ms.export(), orc.modset_export(oms)):
+                assert np.array_equal(x, y), (k, d, "depth recount")
+        ms.close(); orc._modset_free(oms)
+
+
 # ------------------------------------------------------------------ golden --
 def _golden_cases():
     import os, sys

@@ -144,6 +144,32 @@ def test_reference_and_query(orc, ref):
         orc._ref_free(ra); ref._ref_free(rb)
 
 
+def test_readset_loop(orc, ref):
+    """modasm readsetFileRead's per-read loop (modasm.c:151-191): hits with orientation bit, U16 dx, misses, recount"""
+    rng = np.random.default_rng(31)
+    g = rng.integers(0, 4, 60000).astype(np.uint8)
+    offs = np.array([0, 25000, 25000, 60000], np.uint64)
+    reads, roffs = [], [0]
+    for j in range(60):
+        s = int(rng.integers(0, 50000)); L = int(rng.integers(0, 4000))
+        r = g[s:s + L].copy()
+        if j % 3 == 0:
+            r = (3 - r)[::-1]
+        if j % 7 == 0:
+            r = rng.integers(0, 4, L).astype(np.uint8)
+        reads.append(r); roffs.append(roffs[-1] + L)
+    rd = np.concatenate(reads); roffs = np.array(roffs, np.uint64)
+    for (k, d) in ((19, 7), (31, 64), (12, 3)):
+        a, b = orc.modset_new(20, k, d, 17), ref.modset_new(20, k, d, 17)
+        orc.modset_add(a, g, offs); ref.modset_add(b, g, offs)
+        ra, rb = orc.readset(a, rd, roffs), ref.readset(b, rd, roffs)
+        for key in ra:
+            assert np.array_equal(ra[key], rb[key]), (k, d, key)
+        assert len(ra["hit"]) > 0 and (ra["hit"] >> 31).any() and not (ra["hit"] >> 31).all()
+        assert np.array_equal(orc.modset_hist(a), ref.modset_hist(b))
+        orc._modset_free(a); ref._modset_free(b)
+
+
 def test_stock_cli_byte_level(orc, ref, tmp_path):
     """the stock reference tools on FASTA files vs the oracle + our host formatters:
     -wt dump, -H histogram, summary lines, modmap build lines, Q and -v seed lines"""
