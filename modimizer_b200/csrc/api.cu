@@ -196,11 +196,13 @@ static int add_chunk_fused(ModgpuModset *ms, const uint8_t *d_bases, const uint6
   cudaStream_t st = ms->stream;
   const uint64_t words = modgpuPackedWords(nBases);
   int rc;
-  if ((rc = ms->packed.ensure(words * 8)) || (rc = ms->ends.ensure(words * 4)) ||
+  // K1 fused into K2's tile loader when the batch is 16-byte aligned: no packed stream is written at all
+  const bool fusePack = ((((uintptr_t)d_bases) & 15) == 0) && !(ms->selFlags & MODGPU_SEL_NOFUSEPACK);
+  if ((rc = (fusePack ? MODGPU_OK : ms->packed.ensure(words * 8))) || (rc = ms->ends.ensure(words * 4)) ||
       (rc = ms->work.ensure(modgpuHashSelectWorkspace(nBases))))
     return rc;
-  { ProfScope p(ms, MODGPU_T_PACK, 2);
-    if ((rc = modgpuPack2bit(d_bases, nBases, isAscii, (uint64_t *)ms->packed.p, st))) return rc;
+  { ProfScope p(ms, MODGPU_T_PACK, fusePack ? 1 : 2);
+    if (!fusePack && (rc = modgpuPack2bit(d_bases, nBases, isAscii, (uint64_t *)ms->packed.p, st))) return rc;
     if ((rc = modgpuMarkEnds(d_offs, nSeq, nBases, (uint32_t *)ms->ends.p, st))) return rc;
   }
   MgBulk b;
@@ -210,7 +212,7 @@ static int add_chunk_fused(ModgpuModset *ms, const uint8_t *d_bases, const uint6
   { ProfScope p(ms, MODGPU_T_SELECT, 1);
     if ((rc = mg_hash_select_scatter(&ms->hasher, (const uint64_t *)ms->packed.p, (const uint32_t *)ms->ends.p, nBases, dCount,
                                      ms->work.p, ms->selFlags, b.slotBits, b.regionBits, b.cap, b.cursors, b.buckets,
-                                     b.overflow, b.overflowCap, st)))
+                                     b.overflow, b.overflowCap, fusePack ? d_bases : nullptr, isAscii, st)))
       return rc;
   }
   MG_CUDA(cudaMemcpyAsync((void *)hCount, dCount, 8, cudaMemcpyDeviceToHost, st));
@@ -448,17 +450,18 @@ extern "C" int modgpuModsetSelectBucketsDevice(ModgpuModset *ms, const uint8_t *
   if (nBases >= (1ull << 32)) { mg_set_error("modgpuModsetSelectBucketsDevice: batch exceeds 2^32-1 bases"); return MODGPU_EINVAL; }
   const uint64_t words = modgpuPackedWords(nBases);
   int rc;
-  if ((rc = ms->packed.ensure(words * 8)) || (rc = ms->ends.ensure(words * 4)) ||
+  const bool fusePack = ((((uintptr_t)d_bases) & 15) == 0) && !(ms->selFlags & MODGPU_SEL_NOFUSEPACK);
+  if ((rc = (fusePack ? MODGPU_OK : ms->packed.ensure(words * 8))) || (rc = ms->ends.ensure(words * 4)) ||
       (rc = ms->work.ensure(modgpuHashSelectWorkspace(nBases))))
     return rc;
-  { ProfScope p(ms, MODGPU_T_PACK, 2);
-    if ((rc = modgpuPack2bit(d_bases, nBases, isAscii, (uint64_t *)ms->packed.p, st))) return rc;
+  { ProfScope p(ms, MODGPU_T_PACK, fusePack ? 1 : 2);
+    if (!fusePack && (rc = modgpuPack2bit(d_bases, nBases, isAscii, (uint64_t *)ms->packed.p, st))) return rc;
     if ((rc = modgpuMarkEnds(d_offs, nSeq, nBases, (uint32_t *)ms->ends.p, st))) return rc;
   }
   ProfScope p(ms, MODGPU_T_SELECT, 1);
   return mg_hash_select_peer(&ms->hasher, (const uint64_t *)ms->packed.p, (const uint32_t *)ms->ends.p, nBases, d_count, ms->work.p,
                              ms->selFlags, mg_table_slot_bits(ms->table), 11, nOwners, bucketCap, d_cursors, d_buckets,
-                             d_overflow, overflowCap, d_ovfCounts, st);
+                             d_overflow, overflowCap, d_ovfCounts, fusePack ? d_bases : nullptr, isAscii, st);
 }
 
 extern "C" int modgpuModsetSelectBucketsHost(ModgpuModset *ms, const char *bases, const uint64_t *offs, uint64_t nSeq,

@@ -56,6 +56,9 @@ struct SelectParams {
   uint32_t *ownerCursor;
   uint64_t *ownerBuf;
   uint64_t ownerCap;
+  // LOAD == 2: the batch as bytes (16-byte aligned), K1 fused into the tile loader
+  const uint8_t *raw;
+  uint32_t rawAscii;
 };
 
 // Phase 2 helper: evaluate queue entry e = (source thread << 5 | window) of the
@@ -114,9 +117,13 @@ __device__ __forceinline__ uint32_t scan_run(const MgKHasher &H, const MgRun &R)
 
 // OUT: 0 = list, 1 = scatter into the table's region buckets, 2 = per-owner segments,
 //      3 = per-(owner, region) buckets: what the owner's region build consumes directly
-template <bool PREFILTER, bool ORDERED, bool TMA, int OUT>
+// LOAD: 0 = plain loads of the packed stream, 1 = TMA bulk staging of the packed stream,
+//       2 = raw bytes (codes or ASCII): K1 fused into the tile loader, no packed stream in HBM at all
+template <bool PREFILTER, bool ORDERED, int LOAD, int OUT>
 __global__ void __launch_bounds__(MG_SEL_THREADS) hash_select_kernel(const SelectParams P)
 {
+  constexpr bool TMA = (LOAD == 1);
+  constexpr bool RAW = (LOAD == 2);
   constexpr bool SCATTER = (OUT == 1 || OUT == 3);
   constexpr bool OWNERS = (OUT == 2);
   constexpr bool PEER = (OUT == 3);
@@ -181,6 +188,45 @@ __global__ void __launch_bounds__(MG_SEL_THREADS) hash_select_kernel(const Selec
         { mg_mbar_wait(&sBar[stage], (it >> 1) & 1);
           w0 = sPack[buf][run0]; w1 = sPack[buf][run0 + 1]; w2 = sPack[buf][run0 + 2];
           e0 = sEnds[buf][run0]; e1 = sEnds[buf][run0 + 1]; e2 = sEnds[buf][run0 + 2];
+        }
+      else if (RAW)
+        { // K1 fused: this thread's 64 bytes -> two packed words (same SWAR as pack2bit_kernel)
+          const uint64_t b0 = word * MG_RUN;
+          e0 = __ldg(P.ends + word); e1 = __ldg(P.ends + word + 1); e2 = __ldg(P.ends + word + 2);
+          const bool ascii = P.rawAscii != 0;
+          if (b0 + 64 <= P.nBases)
+            { const uint4 *src = reinterpret_cast<const uint4 *>(P.raw + b0);
+              const uint4 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2), q3 = __ldg(src + 3);
+              const uint32_t va[8] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w };
+              const uint32_t vb[8] = { q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w };
+              w0 = mg_pack32(va, ascii); w1 = mg_pack32(vb, ascii);
+            }
+          else
+            { w0 = 0; w1 = 0;                              // the ragged end of the batch, byte by byte
+              for (uint32_t j = 0; j < 64 && b0 + j < P.nBases; ++j)
+                { const uint64_t c = (uint64_t)mg_code_of(P.raw[b0 + j], ascii) << (62 - 2 * (j & 31));
+                  if (j < 32) w0 |= c; else w1 |= c;
+                }
+            }
+          sPack[0][run0] = w0;
+          sPack[0][run0 + 1] = w1;
+          if (tid == 0)
+            { // the overlap word: the first 32 bases of the next tile
+              const uint64_t n0 = ((uint64_t)tile + 1) * MG_TILE_BASES;
+              uint64_t wn = 0;
+              if (n0 + 32 <= P.nBases)
+                { const uint4 *src = reinterpret_cast<const uint4 *>(P.raw + n0);
+                  const uint4 q0 = __ldg(src), q1 = __ldg(src + 1);
+                  const uint32_t va[8] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w };
+                  wn = mg_pack32(va, ascii);
+                }
+              else
+                for (uint32_t j = 0; j < 32 && n0 + j < P.nBases; ++j)
+                  wn |= (uint64_t)mg_code_of(P.raw[n0 + j], ascii) << (62 - 2 * j);
+              sPack[0][MG_TILE_THREADS] = wn;
+            }
+          __syncthreads();
+          w2 = sPack[0][run0 + 2];
         }
       else
         { w0 = __ldg(P.packed + word); w1 = __ldg(P.packed + word + 1); w2 = __ldg(P.packed + word + 2);
@@ -447,7 +493,7 @@ extern "C" uint64_t modgpuHashSelectWorkspace(uint64_t nBases)
 
 MgKHasher mg_khasher_from(const ModgpuHasher *h) { return mg_make_khasher(h->k, h->w, h->factor1); }
 
-template <bool PF, bool ORD, bool TMA, int SC = 0>
+template <bool PF, bool ORD, int TMA, int SC = 0>
 static int launch_select(const SelectParams &P, cudaStream_t st)
 {
   static int blocksPerSm = 0;
@@ -500,7 +546,7 @@ extern "C" int modgpuHashSelect(const ModgpuHasher *h, const uint64_t *d_packed,
 int mg_hash_select_scatter(const ModgpuHasher *h, const uint64_t *d_packed, const uint32_t *d_ends, uint64_t nBases,
                            uint64_t *d_count, void *d_workspace, int flags, uint32_t slotBits, uint32_t regionBits,
                            uint32_t bucketCap, uint32_t *d_cursors, uint64_t *d_buckets, uint64_t *d_overflow,
-                           uint64_t overflowCap, cudaStream_t st)
+                           uint64_t overflowCap, const uint8_t *d_raw, int rawAscii, cudaStream_t st)
 {
   if (nBases >= (1ull << 32)) { mg_set_error("hash_select: batch of %llu bases exceeds 2^32-1", (unsigned long long)nBases); return MODGPU_EINVAL; }
   MG_CUDA(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
@@ -519,6 +565,11 @@ int mg_hash_select_scatter(const ModgpuHasher *h, const uint64_t *d_packed, cons
   MG_CUDA(cudaMemsetAsync(d_workspace, 0, 64, st));
   const bool pf = P.H.prefilter && !(flags & MODGPU_SEL_NOPREFILTER);
   const bool tma = !(flags & MODGPU_SEL_NOTMA);
+  if (d_raw)
+    { P.raw = d_raw; P.rawAscii = rawAscii ? 1u : 0u;
+      if (pf) return launch_select<true, false, 2, 1>(P, st);
+      return launch_select<false, false, 2, 1>(P, st);
+    }
   if (pf && tma) return launch_select<true, false, true, 1>(P, st);
   if (pf) return launch_select<true, false, false, 1>(P, st);
   if (tma) return launch_select<false, false, true, 1>(P, st);
@@ -562,7 +613,8 @@ int mg_hash_select_owners(const ModgpuHasher *h, const uint64_t *d_packed, const
 int mg_hash_select_peer(const ModgpuHasher *h, const uint64_t *d_packed, const uint32_t *d_ends, uint64_t nBases,
                         uint64_t *d_count, void *d_workspace, int flags, uint32_t slotBits, uint32_t regionBits,
                         uint32_t nOwners, uint32_t bucketCap, uint32_t *d_cursors, uint64_t *d_buckets,
-                        uint64_t *d_overflow, uint64_t overflowCap, uint32_t *d_ovfCounts, cudaStream_t st)
+                        uint64_t *d_overflow, uint64_t overflowCap, uint32_t *d_ovfCounts,
+                        const uint8_t *d_raw, int rawAscii, cudaStream_t st)
 {
   if (nBases >= (1ull << 32)) { mg_set_error("hash_select: batch of %llu bases exceeds 2^32-1", (unsigned long long)nBases); return MODGPU_EINVAL; }
   if (nOwners < 1 || nOwners > 64) { mg_set_error("hash_select: nOwners %u out of range 1..64", nOwners); return MODGPU_EINVAL; }
@@ -586,6 +638,11 @@ int mg_hash_select_peer(const ModgpuHasher *h, const uint64_t *d_packed, const u
   MG_CUDA(cudaMemsetAsync(d_workspace, 0, 64, st));
   const bool pf = P.H.prefilter && !(flags & MODGPU_SEL_NOPREFILTER);
   const bool tma = !(flags & MODGPU_SEL_NOTMA);
+  if (d_raw)
+    { P.raw = d_raw; P.rawAscii = rawAscii ? 1u : 0u;
+      if (pf) return launch_select<true, false, 2, 3>(P, st);
+      return launch_select<false, false, 2, 3>(P, st);
+    }
   if (pf && tma) return launch_select<true, false, true, 3>(P, st);
   if (pf) return launch_select<true, false, false, 3>(P, st);
   if (tma) return launch_select<false, false, true, 3>(P, st);

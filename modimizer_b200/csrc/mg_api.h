@@ -20,7 +20,8 @@ int mg_table_bulk_finish(ModgpuTable *t, const MgBulk *b, cudaStream_t st);
 int mg_hash_select_peer(const ModgpuHasher *h, const uint64_t *d_packed, const uint32_t *d_ends, uint64_t nBases,
                         uint64_t *d_count, void *d_workspace, int flags, uint32_t slotBits, uint32_t regionBits,
                         uint32_t nOwners, uint32_t bucketCap, uint32_t *d_cursors, uint64_t *d_buckets,
-                        uint64_t *d_overflow, uint64_t overflowCap, uint32_t *d_ovfCounts, cudaStream_t st);
+                        uint64_t *d_overflow, uint64_t overflowCap, uint32_t *d_ovfCounts,
+                        const uint8_t *d_raw, int rawAscii, cudaStream_t st);
 int mg_table_build_from_buckets(ModgpuTable *t, const uint64_t *d_buckets, const uint32_t *d_cursors, uint32_t cap, uint32_t nSrc,
                                 const uint64_t *d_overflow, uint64_t overflowCap, const uint32_t *d_ovfCounts, cudaStream_t st);
 uint32_t mg_table_regions(const ModgpuTable *t);
@@ -33,7 +34,7 @@ int mg_table_insert_segments(ModgpuTable *t, const uint64_t *d_segs, uint32_t nS
 int mg_hash_select_scatter(const ModgpuHasher *h, const uint64_t *d_packed, const uint32_t *d_ends, uint64_t nBases,
                            uint64_t *d_count, void *d_workspace, int flags, uint32_t slotBits, uint32_t regionBits,
                            uint32_t bucketCap, uint32_t *d_cursors, uint64_t *d_buckets, uint64_t *d_overflow,
-                           uint64_t overflowCap, cudaStream_t st);
+                           uint64_t overflowCap, const uint8_t *d_raw, int rawAscii, cudaStream_t st);
 uint64_t mg_table_bulk_threshold(const ModgpuTable *t);
 int mg_slot_partition(const uint64_t *d_kmers, uint64_t n, uint32_t slotBits, uint32_t bucketBits,
                       uint64_t *d_out, uint64_t *d_scratch, cudaStream_t st);

@@ -255,12 +255,13 @@ def test_modset_build_count(mg, orc, exact):
         ms.close(); orc._modset_free(oms)
 
 
-@pytest.mark.parametrize("mode", ["bulk", "bulk_nofuse", "direct", "partitioned"])
+@pytest.mark.parametrize("mode", ["bulk", "bulk_nofusepack", "bulk_nofuse", "direct", "partitioned"])
 def test_insert_paths_agree(mg, orc, mode):
     """the three insert strategies (shared-memory region build, direct HBM probes,
     region-partitioned direct) give the oracle's modset: fresh table, repeated
     adds into a populated table, heavy skew (bucket overflow), histogram"""
-    flags = {"bulk": 255 << 8, "bulk_nofuse": (255 << 8) | 16, "direct": 1 << 8, "partitioned": 7 << 8}[mode]
+    flags = {"bulk": 255 << 8, "bulk_nofusepack": (255 << 8) | 32, "bulk_nofuse": (255 << 8) | 16, "direct": 1 << 8,
+             "partitioned": 7 << 8}[mode]
     sp = he.read_spec(12345, 300000, 42, 3000, 2000)
     nreads = 2500
     data = he.reads(sp, 0, nreads)
@@ -274,6 +275,13 @@ def test_insert_paths_agree(mg, orc, mode):
         for (d_, o_) in ((data, offs), (data[:3000 * 900], offs[:901]), (skew, np.array([0, 200000], np.uint64)), (data, offs)):
             assert ms.add(d_, o_, is_ascii=0) == orc.modset_add(oms, d_, o_)
             assert ms.max == orc._modset_max(oms)
+        # raw ASCII text (mixed case, N) with a ragged end, through the same path
+        part = data[:3000 * 77 + 13].copy()
+        asc = np.frombuffer(b"ACGT", np.uint8)[part]
+        asc[::7] |= 0x20                                      # lower case
+        asc[5000:5100] = ord("N"); part[5000:5100] = 0
+        po = np.array([0, 3000 * 40 + 1, 3000 * 40 + 1, len(part)], np.uint64)
+        assert ms.add(asc, po, is_ascii=1) == orc.modset_add(oms, part, po)
         gv, gd, gi = ms.sorted_dump(); ov, od, oi = orc.modset_sorted(oms)
         assert np.array_equal(gv, ov) and np.array_equal(gd, od)
         assert np.array_equal(ms.histogram(), orc.modset_hist(oms))
