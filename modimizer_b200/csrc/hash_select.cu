@@ -59,7 +59,20 @@ struct SelectParams {
   // LOAD == 2: the batch as bytes (16-byte aligned), K1 fused into the tile loader
   const uint8_t *raw;
   uint32_t rawAscii;
+  // LUTK != 0: the 16 KiB candidate table of mg_lut_entry (built per launch into the workspace)
+  const uint8_t *lut;
 };
+
+// workspace layout: [0, 64) ticket and scratch counters, [64, 64 + MG_LUT_SIZE) candidate table, then the
+// look-back descriptors of the ordered kernel
+#define MG_WS_LUT 64
+#define MG_WS_STATUS (64 + MG_LUT_SIZE)
+
+__global__ void __launch_bounds__(256) lut_build_kernel(const MgKHasher H, uint8_t *lut)
+{
+  const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x < MG_LUT_SIZE) lut[x] = (uint8_t)mg_lut_entry(H, x);
+}
 
 // Phase 2 helper: evaluate queue entry e = (source thread << 5 | window) of the
 // current tile from the shared-memory copy of the packed words.
@@ -115,36 +128,27 @@ __device__ __forceinline__ uint32_t scan_run(const MgKHasher &H, const MgRun &R)
   return m;
 }
 
-// OUT: 0 = list, 1 = scatter into the table's region buckets, 2 = per-owner segments,
-//      3 = per-(owner, region) buckets: what the owner's region build consumes directly
-// LOAD: 0 = plain loads of the packed stream, 1 = TMA bulk staging of the packed stream,
-//       2 = raw bytes (codes or ASCII): K1 fused into the tile loader, no packed stream in HBM at all
-template <bool PREFILTER, bool ORDERED, int LOAD, int OUT>
-__global__ void __launch_bounds__(MG_SEL_THREADS) hash_select_kernel(const SelectParams P)
+// ---------------------------------------------------------------- ordered --
+// Input-order output (modmap hit lists, exact index numbering): block-level queue,
+// a scan over the runs and a decoupled look-back over the tiles place the k-mers.
+// TMA: the packed stream and the end flags are staged by bulk copies (double buffered).
+template <bool PREFILTER, bool TMA>
+__global__ void __launch_bounds__(MG_SEL_THREADS) hash_select_ordered_kernel(const SelectParams P)
 {
-  constexpr bool TMA = (LOAD == 1);
-  constexpr bool RAW = (LOAD == 2);
-  constexpr bool SCATTER = (OUT == 1 || OUT == 3);
-  constexpr bool OWNERS = (OUT == 2);
-  constexpr bool PEER = (OUT == 3);
-  __shared__ uint32_t sOwn[OWNERS ? 64 : 1];
-  __shared__ uint32_t sOwnBase[OWNERS ? 64 : 1];
   constexpr int NBUF = TMA ? 2 : 1;
   constexpr int NWARPS = MG_SEL_THREADS / 32;
   __shared__ __align__(128) uint64_t sPack[NBUF][MG_TILE_PACK_BYTES / 8];
   __shared__ __align__(128) uint32_t sEnds[TMA ? 2 : 1][TMA ? (MG_TILE_ENDS_BYTES / 4) : 4];
   __shared__ __align__(8) uint64_t sBar[2];
   __shared__ uint16_t sQueue[MG_QUEUE_CAP];
-  __shared__ uint32_t sSel[ORDERED ? MG_TILE_THREADS : 1];     // ORDERED: selected windows per run
-  __shared__ uint32_t sDst[ORDERED ? MG_TILE_THREADS : 1];     // ORDERED: output offset of each run
+  __shared__ uint32_t sSel[MG_TILE_THREADS];      // selected windows per run
+  __shared__ uint32_t sDst[MG_TILE_THREADS];      // output offset of each run
   __shared__ uint32_t sTile[2];
   __shared__ uint32_t sWarp[NWARPS];
   __shared__ uint64_t sBase;
 
   const MgKHasher &H = P.H;
   const uint32_t tid = threadIdx.x;
-  const uint32_t lane = tid & 31;
-  uint32_t nSelectedLocal = 0;                             // SCATTER: this thread's share of the total
 
   if (tid == 0)
     { if (TMA)
@@ -189,45 +193,6 @@ __global__ void __launch_bounds__(MG_SEL_THREADS) hash_select_kernel(const Selec
           w0 = sPack[buf][run0]; w1 = sPack[buf][run0 + 1]; w2 = sPack[buf][run0 + 2];
           e0 = sEnds[buf][run0]; e1 = sEnds[buf][run0 + 1]; e2 = sEnds[buf][run0 + 2];
         }
-      else if (RAW)
-        { // K1 fused: this thread's 64 bytes -> two packed words (same SWAR as pack2bit_kernel)
-          const uint64_t b0 = word * MG_RUN;
-          e0 = __ldg(P.ends + word); e1 = __ldg(P.ends + word + 1); e2 = __ldg(P.ends + word + 2);
-          const bool ascii = P.rawAscii != 0;
-          if (b0 + 64 <= P.nBases)
-            { const uint4 *src = reinterpret_cast<const uint4 *>(P.raw + b0);
-              const uint4 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2), q3 = __ldg(src + 3);
-              const uint32_t va[8] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w };
-              const uint32_t vb[8] = { q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w };
-              w0 = mg_pack32(va, ascii); w1 = mg_pack32(vb, ascii);
-            }
-          else
-            { w0 = 0; w1 = 0;                              // the ragged end of the batch, byte by byte
-              for (uint32_t j = 0; j < 64 && b0 + j < P.nBases; ++j)
-                { const uint64_t c = (uint64_t)mg_code_of(P.raw[b0 + j], ascii) << (62 - 2 * (j & 31));
-                  if (j < 32) w0 |= c; else w1 |= c;
-                }
-            }
-          sPack[0][run0] = w0;
-          sPack[0][run0 + 1] = w1;
-          if (tid == 0)
-            { // the overlap word: the first 32 bases of the next tile
-              const uint64_t n0 = ((uint64_t)tile + 1) * MG_TILE_BASES;
-              uint64_t wn = 0;
-              if (n0 + 32 <= P.nBases)
-                { const uint4 *src = reinterpret_cast<const uint4 *>(P.raw + n0);
-                  const uint4 q0 = __ldg(src), q1 = __ldg(src + 1);
-                  const uint32_t va[8] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w };
-                  wn = mg_pack32(va, ascii);
-                }
-              else
-                for (uint32_t j = 0; j < 32 && n0 + j < P.nBases; ++j)
-                  wn |= (uint64_t)mg_code_of(P.raw[n0 + j], ascii) << (62 - 2 * j);
-              sPack[0][MG_TILE_THREADS] = wn;
-            }
-          __syncthreads();
-          w2 = sPack[0][run0 + 2];
-        }
       else
         { w0 = __ldg(P.packed + word); w1 = __ldg(P.packed + word + 1); w2 = __ldg(P.packed + word + 2);
           e0 = __ldg(P.ends + word); e1 = __ldg(P.ends + word + 1); e2 = __ldg(P.ends + word + 2);
@@ -248,8 +213,7 @@ __global__ void __launch_bounds__(MG_SEL_THREADS) hash_select_kernel(const Selec
       uint32_t nQueue;
       uint32_t qoff = mg_block_excl_scan<NWARPS>(__popc(m[0]) + __popc(m[1]), sWarp, &nQueue);
       const bool queued = nQueue <= MG_QUEUE_CAP;          // block-uniform
-      if (ORDERED) { sSel[run0] = 0; sSel[run0 + 1] = 0; }
-      if (OWNERS && tid < 64) sOwn[tid] = 0;
+      sSel[run0] = 0; sSel[run0 + 1] = 0;
       if (queued)
         {
 #pragma unroll
@@ -263,45 +227,287 @@ __global__ void __launch_bounds__(MG_SEL_THREADS) hash_select_kernel(const Selec
         }
       __syncthreads();
 
-      // ---- phase 3: evaluation and output
+      // ---- phase 3: pass 1 marks the selected windows of every run ...
       const uint64_t *sWords = sPack[buf];
-      // number of entries this thread handles: a slice of the queue, or (overfull tile) its own windows
-      if (!ORDERED && queued && nQueue <= MG_SEL_ROUNDS * MG_SEL_THREADS)
-        { // count mode, the usual tile: every thread evaluates its (<= MG_SEL_ROUNDS) queue entries into
-          // registers first, so that output space is reserved with ONE atomic per tile (per-warp
-          // reservations serialise on the single counter: measured 56 % of stall samples) and the
-          // scatter atomics of a thread are all in flight together
+      if (!queued)
+        { // overfull tile: every thread resolves its own windows
+#pragma unroll
+          for (int r = 0; r < MG_SEL_RPT; ++r)
+            { uint32_t mm = m[r], sel = 0;
+              while (mm)
+                { uint32_t i = __ffs(mm) - 1; mm &= mm - 1;
+                  uint64_t km; bool isF;
+                  if (!PREFILTER || eval_entry(H, sWords, ((run0 + r) << 5) | i, &km, &isF)) sel |= 1u << i;
+                }
+              sSel[run0 + r] = sel;
+            }
+        }
+      else if (PREFILTER)
+        { for (uint32_t q = tid; q < nQueue; q += MG_SEL_THREADS)
+            { const uint32_t e = sQueue[q];
+              uint64_t km; bool isF;
+              if (eval_entry(H, sWords, e, &km, &isF)) atomicOr(&sSel[e >> 5], 1u << (e & 31u));
+            }
+        }
+      else
+        { for (uint32_t q = tid; q < nQueue; q += MG_SEL_THREADS)
+            { const uint32_t e = sQueue[q];
+              atomicOr(&sSel[e >> 5], 1u << (e & 31u));          // the queue already holds the selected windows
+            }
+        }
+      __syncthreads();
+      // ... a scan over the runs + the look-back over the tiles place them ...
+      uint32_t total;
+      const uint32_t selA = sSel[run0], selB = sSel[run0 + 1];
+      const uint32_t off = mg_block_excl_scan<NWARPS>(__popc(selA) + __popc(selB), sWarp, &total);
+      sDst[run0] = off;
+      sDst[run0 + 1] = off + __popc(selA);
+      if (tid < 32)
+        { uint32_t excl = mg_lookback(P.status, tile, total);
+          if (tid == 0)
+            { sBase = excl;
+              if (tile == P.nTiles - 1) *P.count = (unsigned long long)excl + total;
+            }
+        }
+      __syncthreads();
+      const uint64_t outBase = sBase;
+      // ... pass 2 writes them, again spread over all threads (or per owner when overfull)
+      uint32_t own0 = selA, own1 = selB;
+      for (uint32_t q = tid;; q += MG_SEL_THREADS)
+        { uint32_t e;
+          if (queued)
+            { if (q >= nQueue) break;
+              e = sQueue[q];
+            }
+          else
+            { if (own0) { uint32_t i = __ffs(own0) - 1; own0 &= own0 - 1; e = (run0 << 5) | i; }
+              else if (own1) { uint32_t i = __ffs(own1) - 1; own1 &= own1 - 1; e = ((run0 + 1) << 5) | i; }
+              else break;
+            }
+          const uint32_t src = e >> 5, bit = e & 31u;
+          const uint32_t selBits = sSel[src];
+          if (!((selBits >> bit) & 1u)) continue;
+          uint64_t km; bool isF;
+          eval_entry(H, sWords, e, &km, &isF);
+          const uint64_t dst = outBase + sDst[src] + __popc(selBits & ((1u << bit) - 1u));
+          if (dst < P.cap)
+            { if (P.strandBit && isF) km |= 1ull << 63;
+              P.outKmer[dst] = km;
+              if (P.outPos) P.outPos[dst] = (uint32_t)(tileBase + e);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ count --
+// Count mode (order irrelevant).  One block barrier per tile; everything after the
+// tile is in shared memory is WARP-local: a warp compacts the candidates of its own
+// 2048 windows into its own queue (warp scan), spreads their full evaluation evenly
+// over its lanes, keeps up to MG_SEL_ROUNDS results per lane in registers so that
+// the atomics of a lane are all in flight together, and writes them out.
+// OUT: 0 = list, 1 = scatter into the table's region buckets, 2 = per-owner segments,
+//      3 = per-(owner, region) buckets: what the owner's region build consumes directly
+// LOAD: 0 = plain loads of the packed stream, 1 = TMA bulk staging of the packed stream,
+//       2 = raw bytes (codes or ASCII): K1 fused into the tile loader, no packed stream in HBM at all
+#define MG_WQ_CAP 512                                         // queue entries per warp (of its 2048 windows)
+
+// 16 bytes -> 16 two-bit codes, first base in the top bits (K1 arithmetic, mg_pack4;
+// the four gathered bytes are merged with three byte permutes instead of shifts and masks)
+template <bool ASCII>
+__device__ __forceinline__ uint32_t pack16_dev(const uint4 q)
+{
+  uint32_t c0, c1, c2, c3;
+  if (ASCII)
+    { c0 = ((q.x >> 1) ^ (q.x >> 2)) & 0x03030303u; c1 = ((q.y >> 1) ^ (q.y >> 2)) & 0x03030303u;
+      c2 = ((q.z >> 1) ^ (q.z >> 2)) & 0x03030303u; c3 = ((q.w >> 1) ^ (q.w >> 2)) & 0x03030303u;
+    }
+  else
+    { c0 = q.x & 0x03030303u; c1 = q.y & 0x03030303u; c2 = q.z & 0x03030303u; c3 = q.w & 0x03030303u; }
+  const uint32_t p0 = c0 * 0x40100401u, p1 = c1 * 0x40100401u, p2 = c2 * 0x40100401u, p3 = c3 * 0x40100401u;
+  const uint32_t t = __byte_perm(p0, p1, 0x3700), u = __byte_perm(p2, p3, 0x0037);
+  return __byte_perm(t, u, 0x3254);
+}
+
+template <bool ASCII>
+__device__ __forceinline__ uint64_t pack32_raw(const uint8_t *raw, uint64_t b0, uint64_t nBases)
+{
+  if (b0 + 32 <= nBases)
+    { const uint4 *src = reinterpret_cast<const uint4 *>(raw + b0);
+      return ((uint64_t)pack16_dev<ASCII>(__ldg(src)) << 32) | pack16_dev<ASCII>(__ldg(src + 1));
+    }
+  uint64_t w = 0;                                             // the ragged end of the batch, byte by byte
+  for (uint32_t j = 0; j < 32 && b0 + j < nBases; ++j)
+    w |= (uint64_t)mg_code_of(raw[b0 + j], ASCII) << (62 - 2 * j);
+  return w;
+}
+
+template <bool PREFILTER, int LOAD, int OUT, bool ASCII, int LUTK>
+__global__ void __launch_bounds__(MG_SEL_THREADS) hash_count_kernel(const SelectParams P)
+{
+  static_assert(LUTK == 0 || PREFILTER, "the table-driven scan is a prefilter");
+  __shared__ __align__(16) uint8_t sLut[LUTK ? MG_LUT_SIZE : 16];
+  constexpr bool TMA = (LOAD == 1);
+  constexpr bool RAW = (LOAD == 2);
+  constexpr bool SCATTER = (OUT == 1 || OUT == 3);
+  constexpr bool OWNERS = (OUT == 2);
+  constexpr bool PEER = (OUT == 3);
+  constexpr int NWARPS = MG_SEL_THREADS / 32;
+  __shared__ __align__(128) uint64_t sPack[2][MG_TILE_PACK_BYTES / 8];
+  __shared__ __align__(128) uint32_t sEnds[TMA ? 2 : 1][TMA ? (MG_TILE_ENDS_BYTES / 4) : 4];
+  __shared__ __align__(8) uint64_t sBar[2];
+  __shared__ uint16_t sQueue[NWARPS][MG_WQ_CAP];
+  __shared__ uint32_t sOwn[OWNERS ? NWARPS : 1][OWNERS ? 64 : 1];
+  __shared__ uint32_t sOwnBase[OWNERS ? NWARPS : 1][OWNERS ? 64 : 1];
+  __shared__ uint32_t sTile[2];
+
+  const MgKHasher &H = P.H;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t lane = tid & 31, warp = tid >> 5;
+  uint16_t *wq = sQueue[warp];
+  uint32_t nSelectedLocal = 0;                             // SCATTER: this thread's share of the total
+
+  if (tid == 0)
+    { if (TMA)
+        { mg_mbar_init(&sBar[0], 1);
+          mg_mbar_init(&sBar[1], 1);
+          mg_fence_barrier_init();
+          mg_fence_proxy_async();
+        }
+      uint32_t t0 = atomicAdd(P.ticket, 1u);
+      sTile[0] = t0;
+      if (TMA && t0 < P.nTiles)
+        { mg_mbar_expect_tx(&sBar[0], MG_TILE_PACK_BYTES + MG_TILE_ENDS_BYTES);
+          mg_tma_load_1d(sPack[0], P.packed + (uint64_t)t0 * MG_TILE_THREADS, MG_TILE_PACK_BYTES, &sBar[0]);
+          mg_tma_load_1d(sEnds[0], P.ends + (uint64_t)t0 * MG_TILE_THREADS, MG_TILE_ENDS_BYTES, &sBar[0]);
+        }
+    }
+  if (LUTK)
+    { const uint4 *src = reinterpret_cast<const uint4 *>(P.lut);
+      uint4 *dst = reinterpret_cast<uint4 *>(sLut);
+      for (uint32_t i = tid; i < MG_LUT_SIZE / 16; i += MG_SEL_THREADS) dst[i] = __ldg(src + i);
+    }
+  if (!TMA || LUTK) __syncthreads();
+
+  for (uint32_t it = 0;; ++it)
+    { const uint32_t stage = it & 1;
+      // the ONE block barrier of a tile.  TMA: at the top (everyone is done reading the buffer the next
+      // bulk copy lands in, sTile[stage] is visible); otherwise after the tile has been written to
+      // sPack[stage] (which nobody reads any more: its last readers passed the previous barrier).
+      if (TMA) __syncthreads();
+      const uint32_t tile = sTile[stage];
+      if (tile >= P.nTiles) break;
+
+      if (tid == 0)
+        { uint32_t tn = atomicAdd(P.ticket, 1u);
+          sTile[stage ^ 1] = tn;
+          if (TMA && tn < P.nTiles)
+            { mg_mbar_expect_tx(&sBar[stage ^ 1], MG_TILE_PACK_BYTES + MG_TILE_ENDS_BYTES);
+              mg_tma_load_1d(sPack[stage ^ 1], P.packed + (uint64_t)tn * MG_TILE_THREADS, MG_TILE_PACK_BYTES, &sBar[stage ^ 1]);
+              mg_tma_load_1d(sEnds[stage ^ 1], P.ends + (uint64_t)tn * MG_TILE_THREADS, MG_TILE_ENDS_BYTES, &sBar[stage ^ 1]);
+            }
+        }
+
+      // ---- this thread's two runs: words 2t, 2t+1 (+ overlap word 2t+2), 96 end flags
+      const uint32_t run0 = tid * MG_SEL_RPT;
+      const uint64_t word = (uint64_t)tile * MG_TILE_THREADS + run0;
+      uint64_t w0, w1, w2;
+      uint32_t e0, e1, e2;
+      if (TMA)
+        { mg_mbar_wait(&sBar[stage], (it >> 1) & 1);
+          w0 = sPack[stage][run0]; w1 = sPack[stage][run0 + 1]; w2 = sPack[stage][run0 + 2];
+          e0 = sEnds[stage][run0]; e1 = sEnds[stage][run0 + 1]; e2 = sEnds[stage][run0 + 2];
+        }
+      else
+        { e0 = __ldg(P.ends + word); e1 = __ldg(P.ends + word + 1); e2 = __ldg(P.ends + word + 2);
+          if (RAW)
+            { // K1 fused: this thread's 64 bytes -> two packed words
+              const uint64_t b0 = word * MG_RUN;
+              w0 = pack32_raw<ASCII>(P.raw, b0, P.nBases);
+              w1 = pack32_raw<ASCII>(P.raw, b0 + 32, P.nBases);
+              // the overlap word of the tile: the first 32 bases of the next one
+              if (tid == MG_SEL_THREADS - 1) sPack[stage][MG_TILE_THREADS] = pack32_raw<ASCII>(P.raw, b0 + 64, P.nBases);
+            }
+          else
+            { w0 = __ldg(P.packed + word); w1 = __ldg(P.packed + word + 1);
+              if (tid == MG_SEL_THREADS - 1) sPack[stage][MG_TILE_THREADS] = __ldg(P.packed + word + 2);
+            }
+          sPack[stage][run0] = w0;                         // phase 3 reads the tile from shared memory
+          sPack[stage][run0 + 1] = w1;
+          __syncthreads();
+          w2 = sPack[stage][run0 + 2];
+        }
+      const uint64_t tileBase = (uint64_t)tile * MG_TILE_BASES;
+      uint32_t m0, m1;
+      { const uint64_t p0 = tileBase + (uint64_t)run0 * MG_RUN;
+        if (LUTK)
+          mg_lut_scan<LUTK ? LUTK : 31>(sLut, w0, w1, w2, &m0, &m1);
+        else
+          { const MgRun RA = mg_run_prepare(w0, w1, H.k);
+            m0 = scan_run<PREFILTER>(H, RA);
+            const MgRun RB = mg_run_prepare(w1, w2, H.k);
+            m1 = scan_run<PREFILTER>(H, RB);
+          }
+        m0 &= mg_run_usable((uint64_t)e0 | ((uint64_t)e1 << 32), H.k, p0, P.nBases);
+        m1 &= mg_run_usable((uint64_t)e1 | ((uint64_t)e2 << 32), H.k, p0 + MG_RUN, P.nBases);
+      }
+
+      // ---- phase 2 (warp): queue of (run, window) of this warp's 64 runs
+      const uint32_t cnt = __popc(m0) + __popc(m1);
+      const uint32_t incl = mg_warp_incl_scan(cnt);
+      const uint32_t nW = __shfl_sync(0xffffffffu, incl, 31);
+      if (nW == 0) continue;
+      const bool queued = nW <= MG_WQ_CAP;                 // warp-uniform
+      if (queued)
+        { uint32_t qoff = incl - cnt;
+          uint32_t mm = m0;
+          while (mm) { const uint32_t i = __ffs(mm) - 1; mm &= mm - 1; wq[qoff++] = (uint16_t)((run0 << 5) | i); }
+          mm = m1;
+          while (mm) { const uint32_t i = __ffs(mm) - 1; mm &= mm - 1; wq[qoff++] = (uint16_t)(((run0 + 1) << 5) | i); }
+        }
+      __syncwarp();
+
+      // ---- phase 3 (warp): evaluation and output
+      const uint64_t *sWords = sPack[stage];
+      if (queued && nW <= MG_SEL_ROUNDS * 32)
+        { // the usual case: every lane evaluates its (<= MG_SEL_ROUNDS) queue entries into registers first
           uint64_t km[MG_SEL_ROUNDS];
           uint32_t ent[MG_SEL_ROUNDS];
           uint32_t okMask = 0, fMask = 0;
 #pragma unroll
           for (int r = 0; r < MG_SEL_ROUNDS; ++r)
-            { const uint32_t q = r * MG_SEL_THREADS + tid;
+            { const uint32_t q = r * 32 + lane;
               km[r] = 0; ent[r] = 0;
-              if (q < nQueue)
+              if (q < nW)
                 { bool isF;
-                  ent[r] = sQueue[q];
+                  ent[r] = wq[q];
                   if (eval_entry(H, sWords, ent[r], &km[r], &isF)) { okMask |= 1u << r; if (isF) fMask |= 1u << r; }
                 }
             }
           if (OWNERS)
-            { // per-owner segments: rank inside the tile through shared memory, one reservation per owner and tile
+            { // per-owner segments: rank inside the warp's tile through shared memory, one reservation per owner
               uint32_t own[MG_SEL_ROUNDS], rk[MG_SEL_ROUNDS];
+              sOwn[warp][lane] = 0; sOwn[warp][lane + 32] = 0;
+              __syncwarp();
 #pragma unroll
               for (int r = 0; r < MG_SEL_ROUNDS; ++r)
                 if ((okMask >> r) & 1u)
                   { own[r] = mg_owner(km[r], P.nOwners);
-                    rk[r] = atomicAdd(&sOwn[own[r]], 1u);
+                    rk[r] = atomicAdd(&sOwn[warp][own[r]], 1u);
                   }
-              __syncthreads();
-              if (tid < P.nOwners) sOwnBase[tid] = sOwn[tid] ? atomicAdd(&P.ownerCursor[tid], sOwn[tid]) : 0u;
-              __syncthreads();
+              __syncwarp();
+#pragma unroll
+              for (uint32_t o = lane; o < 64; o += 32)
+                { const uint32_t c = (o < P.nOwners) ? sOwn[warp][o] : 0u;
+                  sOwnBase[warp][o] = c ? atomicAdd(&P.ownerCursor[o], c) : 0u;
+                }
+              __syncwarp();
 #pragma unroll
               for (int r = 0; r < MG_SEL_ROUNDS; ++r)
                 if ((okMask >> r) & 1u)
-                  { const uint64_t dst = (uint64_t)sOwnBase[own[r]] + rk[r];
+                  { const uint64_t dst = (uint64_t)sOwnBase[warp][own[r]] + rk[r];
                     if (dst < P.ownerCap) P.ownerBuf[(uint64_t)own[r] * P.ownerCap + dst] = km[r];
                   }
+              __syncwarp();
             }
           else if (SCATTER)
             { nSelectedLocal += __popc(okMask);
@@ -329,11 +535,14 @@ __global__ void __launch_bounds__(MG_SEL_THREADS) hash_select_kernel(const Selec
                   }
             }
           else
-            { uint32_t total;
-              const uint32_t off = mg_block_excl_scan<NWARPS>(__popc(okMask), sWarp, &total);
-              if (tid == 0) sBase = total ? atomicAdd(P.count, (unsigned long long)total) : 0ull;
-              __syncthreads();
-              uint64_t dst = sBase + off;
+            { // list: one reservation per warp and tile
+              const uint32_t c = __popc(okMask);
+              const uint32_t inc2 = mg_warp_incl_scan(c);
+              const uint32_t total = __shfl_sync(0xffffffffu, inc2, 31);
+              unsigned long long wbase = 0;
+              if (lane == 0 && total) wbase = atomicAdd(P.count, (unsigned long long)total);
+              wbase = __shfl_sync(0xffffffffu, wbase, 0);
+              uint64_t dst = wbase + inc2 - c;
 #pragma unroll
               for (int r = 0; r < MG_SEL_ROUNDS; ++r)
                 if ((okMask >> r) & 1u)
@@ -345,17 +554,17 @@ __global__ void __launch_bounds__(MG_SEL_THREADS) hash_select_kernel(const Selec
                   }
             }
         }
-      else if (!ORDERED)
-        { // count mode, crowded tile: warp-aggregated reservations, per-thread loop when even the queue overflowed
-          uint32_t own0 = m[0], own1 = m[1];
-          for (uint32_t base = 0;; base += MG_SEL_THREADS)
+      else
+        { // crowded warp: warp-aggregated reservations per round; per-lane loop when even the queue overflowed
+          uint32_t own0 = m0, own1 = m1;
+          for (uint32_t base = 0;; base += 32)
             { uint64_t km = 0; bool isF = false, ok = false;
               uint32_t e = 0;
               bool have;
               if (queued)
-                { if (base >= nQueue) break;
-                  have = base + tid < nQueue;
-                  if (have) e = sQueue[base + tid];
+                { if (base >= nW) break;
+                  have = base + lane < nW;
+                  if (have) e = wq[base + lane];
                 }
               else
                 { have = (own0 | own1) != 0;
@@ -406,76 +615,6 @@ __global__ void __launch_bounds__(MG_SEL_THREADS) hash_select_kernel(const Selec
                 }
             }
         }
-      else
-        { // input order: pass 1 marks the selected windows of every run ...
-          if (!queued)
-            { // overfull tile: every thread resolves its own windows
-#pragma unroll
-              for (int r = 0; r < MG_SEL_RPT; ++r)
-                { uint32_t mm = m[r], sel = 0;
-                  while (mm)
-                    { uint32_t i = __ffs(mm) - 1; mm &= mm - 1;
-                      uint64_t km; bool isF;
-                      if (!PREFILTER || eval_entry(H, sWords, ((run0 + r) << 5) | i, &km, &isF)) sel |= 1u << i;
-                    }
-                  sSel[run0 + r] = sel;
-                }
-            }
-          else if (PREFILTER)
-            { for (uint32_t q = tid; q < nQueue; q += MG_SEL_THREADS)
-                { const uint32_t e = sQueue[q];
-                  uint64_t km; bool isF;
-                  if (eval_entry(H, sWords, e, &km, &isF)) atomicOr(&sSel[e >> 5], 1u << (e & 31u));
-                }
-            }
-          else
-            { for (uint32_t q = tid; q < nQueue; q += MG_SEL_THREADS)
-                { const uint32_t e = sQueue[q];
-                  atomicOr(&sSel[e >> 5], 1u << (e & 31u));          // the queue already holds the selected windows
-                }
-            }
-          __syncthreads();
-          // ... a scan over the runs + the look-back over the tiles place them ...
-          uint32_t total;
-          const uint32_t selA = sSel[run0], selB = sSel[run0 + 1];
-          const uint32_t off = mg_block_excl_scan<NWARPS>(__popc(selA) + __popc(selB), sWarp, &total);
-          sDst[run0] = off;
-          sDst[run0 + 1] = off + __popc(selA);
-          if (tid < 32)
-            { uint32_t excl = mg_lookback(P.status, tile, total);
-              if (tid == 0)
-                { sBase = excl;
-                  if (tile == P.nTiles - 1) *P.count = (unsigned long long)excl + total;
-                }
-            }
-          __syncthreads();
-          const uint64_t outBase = sBase;
-          // ... pass 2 writes them, again spread over all threads (or per owner when overfull)
-          uint32_t own0 = selA, own1 = selB;
-          for (uint32_t q = tid;; q += MG_SEL_THREADS)
-            { uint32_t e;
-              if (queued)
-                { if (q >= nQueue) break;
-                  e = sQueue[q];
-                }
-              else
-                { if (own0) { uint32_t i = __ffs(own0) - 1; own0 &= own0 - 1; e = (run0 << 5) | i; }
-                  else if (own1) { uint32_t i = __ffs(own1) - 1; own1 &= own1 - 1; e = ((run0 + 1) << 5) | i; }
-                  else break;
-                }
-              const uint32_t src = e >> 5, bit = e & 31u;
-              const uint32_t selBits = sSel[src];
-              if (!((selBits >> bit) & 1u)) continue;
-              uint64_t km; bool isF;
-              eval_entry(H, sWords, e, &km, &isF);
-              const uint64_t dst = outBase + sDst[src] + __popc(selBits & ((1u << bit) - 1u));
-              if (dst < P.cap)
-                { if (P.strandBit && isF) km |= 1ull << 63;
-                  P.outKmer[dst] = km;
-                  if (P.outPos) P.outPos[dst] = (uint32_t)(tileBase + e);
-                }
-            }
-        }
     }
   if (SCATTER)
     { nSelectedLocal = mg_warp_sum(nSelectedLocal);
@@ -488,24 +627,61 @@ extern "C" uint64_t modgpuHashSelectWorkspace(uint64_t nBases)
 {
   uint64_t words = (nBases + 31) / 32;
   uint64_t tiles = (words + MG_TILE_THREADS - 1) / MG_TILE_THREADS;
-  return 64 + tiles * sizeof(uint64_t);          // ticket (+pad) then descriptors
+  return MG_WS_STATUS + tiles * sizeof(uint64_t);  // ticket (+pad), candidate table, then descriptors
 }
 
 MgKHasher mg_khasher_from(const ModgpuHasher *h) { return mg_make_khasher(h->k, h->w, h->factor1); }
 
-template <bool PF, bool ORD, int TMA, int SC = 0>
-static int launch_select(const SelectParams &P, cudaStream_t st)
+template <bool PF, bool TMA>
+static int launch_ordered(const SelectParams &P, cudaStream_t st)
 {
   static int blocksPerSm = 0;
   if (!blocksPerSm)
-    { MG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, hash_select_kernel<PF, ORD, TMA, SC>, MG_SEL_THREADS, 0));
+    { MG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, hash_select_ordered_kernel<PF, TMA>, MG_SEL_THREADS, 0));
       if (blocksPerSm < 1) blocksPerSm = 1;
     }
   uint64_t grid = (uint64_t)mg_num_sms() * blocksPerSm;
   if (grid > P.nTiles) grid = P.nTiles;
-  hash_select_kernel<PF, ORD, TMA, SC><<<(unsigned)grid, MG_SEL_THREADS, 0, st>>>(P);
-  MG_LAUNCH_CHECK("hash_select");
+  hash_select_ordered_kernel<PF, TMA><<<(unsigned)grid, MG_SEL_THREADS, 0, st>>>(P);
+  MG_LAUNCH_CHECK("hash_select_ordered");
   return MODGPU_OK;
+}
+
+template <bool PF, int LOAD, int OUT, bool ASCII, int LUTK>
+static int launch_count(const SelectParams &P, cudaStream_t st)
+{
+  static int blocksPerSm = 0;
+  if (!blocksPerSm)
+    { MG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, hash_count_kernel<PF, LOAD, OUT, ASCII, LUTK>, MG_SEL_THREADS, 0));
+      if (blocksPerSm < 1) blocksPerSm = 1;
+    }
+  uint64_t grid = (uint64_t)mg_num_sms() * blocksPerSm;
+  if (grid > P.nTiles) grid = P.nTiles;
+  if (LUTK)
+    { lut_build_kernel<<<MG_LUT_SIZE / 256, 256, 0, st>>>(P.H, const_cast<uint8_t *>(P.lut));
+      MG_LAUNCH_CHECK("lut_build");
+    }
+  hash_count_kernel<PF, LOAD, OUT, ASCII, LUTK><<<(unsigned)grid, MG_SEL_THREADS, 0, st>>>(P);
+  MG_LAUNCH_CHECK("hash_count");
+  return MODGPU_OK;
+}
+
+// count mode dispatch over (scan, loader) for one output mode.  scan: 0 full evaluation of every window,
+// 1 multiplicative low-word prefilter, 30/31 table-driven prefilter for that k
+template <int OUT, bool PF, int LUTK>
+static int dispatch_count_load(const SelectParams &P, bool tma, cudaStream_t st)
+{
+  if (P.raw) return P.rawAscii ? launch_count<PF, 2, OUT, true, LUTK>(P, st) : launch_count<PF, 2, OUT, false, LUTK>(P, st);
+  return tma ? launch_count<PF, 1, OUT, false, LUTK>(P, st) : launch_count<PF, 0, OUT, false, LUTK>(P, st);
+}
+
+template <int OUT>
+static int dispatch_count(const SelectParams &P, bool pf, bool tma, int flags, cudaStream_t st)
+{
+  if (!pf) return dispatch_count_load<OUT, false, 0>(P, tma, st);
+  if (P.H.lut && !(flags & MODGPU_SEL_NOLUT))
+    return P.H.k == 31 ? dispatch_count_load<OUT, true, 31>(P, tma, st) : dispatch_count_load<OUT, true, 30>(P, tma, st);
+  return dispatch_count_load<OUT, true, 0>(P, tma, st);
 }
 
 extern "C" int modgpuHashSelect(const ModgpuHasher *h, const uint64_t *d_packed, const uint32_t *d_ends,
@@ -527,18 +703,15 @@ extern "C" int modgpuHashSelect(const ModgpuHasher *h, const uint64_t *d_packed,
   P.outKmer = d_kmers; P.outPos = d_gpos; P.cap = cap;
   P.count = (unsigned long long *)d_count;
   P.ticket = (uint32_t *)d_workspace;
-  P.status = (uint64_t *)((char *)d_workspace + 64);
+  P.status = (uint64_t *)((char *)d_workspace + MG_WS_STATUS);
+  P.lut = (const uint8_t *)d_workspace + MG_WS_LUT;
   MG_CUDA(cudaMemsetAsync(d_workspace, 0, modgpuHashSelectWorkspace(nBases), st));
   const bool pf = P.H.prefilter && !(flags & MODGPU_SEL_NOPREFILTER);
   const bool ord = (flags & MODGPU_SEL_ORDERED) != 0;
   const bool tma = !(flags & MODGPU_SEL_NOTMA);
-#define MG_SEL_CASE(a, b, c) if (pf == a && ord == b && tma == c) return launch_select<a, b, c>(P, st);
-  MG_SEL_CASE(true, true, true) MG_SEL_CASE(true, true, false)
-  MG_SEL_CASE(true, false, true) MG_SEL_CASE(true, false, false)
-  MG_SEL_CASE(false, true, true) MG_SEL_CASE(false, true, false)
-  MG_SEL_CASE(false, false, true) MG_SEL_CASE(false, false, false)
-#undef MG_SEL_CASE
-  return MODGPU_EINVAL;
+  if (!ord) return dispatch_count<0>(P, pf, tma, flags, st);
+  if (pf) return tma ? launch_ordered<true, true>(P, st) : launch_ordered<true, false>(P, st);
+  return tma ? launch_ordered<false, true>(P, st) : launch_ordered<false, false>(P, st);
 }
 
 // K2 fused with the bucket scatter of the bulk insert (count mode): no list.
@@ -559,21 +732,15 @@ int mg_hash_select_scatter(const ModgpuHasher *h, const uint64_t *d_packed, cons
   P.nTiles = (uint32_t)((words + MG_TILE_THREADS - 1) / MG_TILE_THREADS);
   P.count = (unsigned long long *)d_count;
   P.ticket = (uint32_t *)d_workspace;
-  P.status = (uint64_t *)((char *)d_workspace + 64);
+  P.status = (uint64_t *)((char *)d_workspace + MG_WS_STATUS);
+  P.lut = (const uint8_t *)d_workspace + MG_WS_LUT;
   P.slotBits = slotBits; P.regionBits = regionBits; P.nRegions = 1u << (slotBits - regionBits); P.bucketCap = bucketCap;
   P.cursors = d_cursors; P.buckets = d_buckets; P.overflow = d_overflow; P.overflowCap = overflowCap;
   MG_CUDA(cudaMemsetAsync(d_workspace, 0, 64, st));
   const bool pf = P.H.prefilter && !(flags & MODGPU_SEL_NOPREFILTER);
   const bool tma = !(flags & MODGPU_SEL_NOTMA);
-  if (d_raw)
-    { P.raw = d_raw; P.rawAscii = rawAscii ? 1u : 0u;
-      if (pf) return launch_select<true, false, 2, 1>(P, st);
-      return launch_select<false, false, 2, 1>(P, st);
-    }
-  if (pf && tma) return launch_select<true, false, true, 1>(P, st);
-  if (pf) return launch_select<true, false, false, 1>(P, st);
-  if (tma) return launch_select<false, false, true, 1>(P, st);
-  return launch_select<false, false, false, 1>(P, st);
+  if (d_raw) { P.raw = d_raw; P.rawAscii = rawAscii ? 1u : 0u; }
+  return dispatch_count<1>(P, pf, tma, flags, st);
 }
 
 // K2 with the selected k-mers bucketed by owner GPU (multi-GPU count mode): segment o of d_buf
@@ -594,16 +761,14 @@ int mg_hash_select_owners(const ModgpuHasher *h, const uint64_t *d_packed, const
   uint64_t words = (nBases + 31) / 32;
   P.nTiles = (uint32_t)((words + MG_TILE_THREADS - 1) / MG_TILE_THREADS);
   P.ticket = (uint32_t *)d_workspace;
-  P.status = (uint64_t *)((char *)d_workspace + 64);
+  P.status = (uint64_t *)((char *)d_workspace + MG_WS_STATUS);
+  P.lut = (const uint8_t *)d_workspace + MG_WS_LUT;
   P.count = (unsigned long long *)((char *)d_workspace + 8);       // unused total
   P.nOwners = nOwners; P.ownerCursor = d_cursors; P.ownerBuf = d_buf; P.ownerCap = ownerCap;
   MG_CUDA(cudaMemsetAsync(d_workspace, 0, 64, st));
   const bool pf = P.H.prefilter && !(flags & MODGPU_SEL_NOPREFILTER);
   const bool tma = !(flags & MODGPU_SEL_NOTMA);
-  if (pf && tma) return launch_select<true, false, true, 2>(P, st);
-  if (pf) return launch_select<true, false, false, 2>(P, st);
-  if (tma) return launch_select<false, false, true, 2>(P, st);
-  return launch_select<false, false, false, 2>(P, st);
+  return dispatch_count<2>(P, pf, tma, flags, st);
 }
 
 // K2 with the selected k-mers written into per-(owner, region) buckets (multi-GPU, fully fused):
@@ -631,22 +796,16 @@ int mg_hash_select_peer(const ModgpuHasher *h, const uint64_t *d_packed, const u
   P.nTiles = (uint32_t)((words + MG_TILE_THREADS - 1) / MG_TILE_THREADS);
   P.count = (unsigned long long *)d_count;
   P.ticket = (uint32_t *)d_workspace;
-  P.status = (uint64_t *)((char *)d_workspace + 64);
+  P.status = (uint64_t *)((char *)d_workspace + MG_WS_STATUS);
+  P.lut = (const uint8_t *)d_workspace + MG_WS_LUT;
   P.slotBits = slotBits; P.regionBits = regionBits; P.nRegions = nRegions; P.bucketCap = bucketCap;
   P.cursors = d_cursors; P.buckets = d_buckets; P.overflow = d_overflow; P.overflowCap = overflowCap;
   P.nOwners = nOwners; P.ownerCursor = d_ovfCounts;
   MG_CUDA(cudaMemsetAsync(d_workspace, 0, 64, st));
   const bool pf = P.H.prefilter && !(flags & MODGPU_SEL_NOPREFILTER);
   const bool tma = !(flags & MODGPU_SEL_NOTMA);
-  if (d_raw)
-    { P.raw = d_raw; P.rawAscii = rawAscii ? 1u : 0u;
-      if (pf) return launch_select<true, false, 2, 3>(P, st);
-      return launch_select<false, false, 2, 3>(P, st);
-    }
-  if (pf && tma) return launch_select<true, false, true, 3>(P, st);
-  if (pf) return launch_select<true, false, false, 3>(P, st);
-  if (tma) return launch_select<false, false, true, 3>(P, st);
-  return launch_select<false, false, false, 3>(P, st);
+  if (d_raw) { P.raw = d_raw; P.rawAscii = rawAscii ? 1u : 0u; }
+  return dispatch_count<3>(P, pf, tma, flags, st);
 }
 
 // ---------------------------------------------------------------- locate --

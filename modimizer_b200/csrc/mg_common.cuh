@@ -42,7 +42,7 @@ struct MgKHasher {
   uint32_t prefilter;   // 1: low-word candidate filter usable (tz >= 3, shift + tz <= 32)
   uint32_t pfMul;       // (uint32) factor << (32 - shift - tz)
   uint32_t pfLim;       // 1 << (32 - tz)
-  uint32_t pad_;
+  uint32_t lut;         // 1: the prefilter depends on <= 4 bases per strand (shift + tz <= 8, k >= 30): table-driven scan
 };
 
 MGHD uint64_t mg_mulinv64(uint64_t a)   // a odd: Newton iteration, 5 steps double the bits 5->64
@@ -68,7 +68,7 @@ MGHD MgKHasher mg_make_khasher(int k, int d, uint64_t factor1)
   H.prefilter = (tz >= 3 && H.shift + tz <= 32) ? 1u : 0u;
   H.pfMul = H.prefilter ? (uint32_t)(factor1 << (32 - H.shift - tz)) : 0u;
   H.pfLim = H.prefilter ? (1u << (32 - tz)) : 0u;
-  H.pad_ = 0;
+  H.lut = (H.prefilter && H.shift + tz <= 8 && k >= 30) ? 1u : 0u;
   return H;
 }
 
@@ -243,6 +243,72 @@ MGHD bool mg_prefilter_candidate(const MgKHasher &H, const MgRun &R, uint32_t i)
 {
   const uint32_t pf = mg_run_fwd_lo(R, i) * H.pfMul, pr = mg_run_rc_lo(R, i) * H.pfMul;
   return (pf < pr ? pf : pr) < H.pfLim;
+}
+
+// ---- table-driven prefilter (H.lut): when the candidate test reads only the low byte of each
+// strand's k-mer (64-2k+tz <= 8), "window p is a candidate" is a function of two groups of four
+// bases: the LAST four of the window (forward k-mer, low byte = those bases) and the FIRST four
+// (reverse complement: base p+m complemented at bits 2m).  A 16 KiB table indexed by 7 consecutive
+// bases answers both questions for the 4 four-base groups starting at those bases with ONE
+// shared-memory load: bit i = group i is a reverse-complement candidate, bit 4+i = a forward one.
+// One lookup per 4 positions replaces 4 x (2 funnel shifts + 2 multiplies + min + compare + or).
+#define MG_LUT_BITS 14
+#define MG_LUT_SIZE (1u << MG_LUT_BITS)
+
+MGHD uint32_t mg_lut_entry(const MgKHasher &H, uint32_t x)    // x = 7 bases, the first in the top two bits
+{
+  uint32_t e = 0;
+  for (int i = 0; i < 4; ++i)
+    { const uint32_t B = (x >> (6 - 2 * i)) & 0xFFu;          // bases i..i+3, the low byte of a forward k-mer ending here
+      uint32_t RB = 0;                                        // the low byte of a reverse-complement k-mer starting here
+      for (int m = 0; m < 4; ++m) RB |= (3u - ((B >> (6 - 2 * m)) & 3u)) << (2 * m);
+      if (B * H.pfMul < H.pfLim) e |= 1u << (4 + i);
+      if (RB * H.pfMul < H.pfLim) e |= 1u << i;
+    }
+  return e;
+}
+
+// candidate masks of two consecutive runs (64 window starts) from the 96 bases w0:w1:w2;
+// lut = the table above (shared memory on the device).  K = 30 or 31.
+template <int K>
+MGHD void mg_lut_scan(const uint8_t *lut, uint64_t w0, uint64_t w1, uint64_t w2, uint32_t *candLo, uint32_t *candHi)
+{
+  const uint32_t S[6] = { (uint32_t)(w0 >> 32), (uint32_t)w0, (uint32_t)(w1 >> 32), (uint32_t)w1, (uint32_t)(w2 >> 32), (uint32_t)w2 };
+  uint32_t e[23];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 0; j < 23; ++j)                                // group j = bases 4j .. 4j+6
+    { const int r = j >> 2, c = j & 3;
+      uint32_t x;
+      if (c == 0) x = S[r] >> 18;
+      else if (c == 1) x = (S[r] >> 10) & 0x3FFFu;
+      else if (c == 2) x = (S[r] >> 2) & 0x3FFFu;
+      else x = mg_funnel_r(S[r + 1], S[r], 26) & 0x3FFFu;
+      e[j] = lut[x];
+    }
+  // reverse-complement bits of position q -> bit q of (rLo, rHi)
+  uint32_t rLo = 0, rHi = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 7; j >= 0; --j) { rLo = (rLo << 4) | (e[j] & 15u); rHi = (rHi << 4) | (e[j + 8] & 15u); }
+  // forward bits of the four-base group at q belong to the window starting at q - OFF; three chains of
+  // seven lookups keep the high nibble in place ((chain << 4) | (e & 0xF0) = the bits shifted left by 4)
+  constexpr int OFF = K - 4, J0 = OFF / 4;
+  uint32_t fa = 0, fb = 0, fc = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 6; j >= 0; --j)
+    { fa = (fa << 4) | (e[J0 + j] & 0xF0u);
+      fb = (fb << 4) | (e[J0 + 7 + j] & 0xF0u);
+      if (J0 + 14 + j <= 22) fc = (fc << 4) | (e[J0 + 14 + j] & 0xF0u);
+    }
+  // chain a holds q = 4 J0 .. at bit q - 4 J0 + 4, i.e. window p at bit p + OFF - 4 J0 + 4
+  constexpr int SA = OFF - 4 * J0 + 4, TB = 4 * J0 + 24 - OFF, TC = 4 * J0 + 52 - OFF;
+  *candLo = rLo | (fa >> SA) | (fb << TB);
+  *candHi = rHi | (fb >> (32 - TB)) | (fc << (TC - 32));
 }
 
 // window starts of the run at global offset p0 that may be selected at all

@@ -89,6 +89,34 @@ int64_t hm_select(int k, int d, uint64_t factor1, const uint8_t *bytes, uint64_t
   return n;
 }
 
+// table-driven prefilter (mg_lut_scan) against the arithmetic prefilter, every window of the batch;
+// returns the number of candidate-mask mismatches (-1: the table scan does not apply to these parameters)
+int64_t hm_lut_check(int k, int d, uint64_t factor1, const uint8_t *bytes, uint64_t nBases, int ascii, uint64_t *nCand)
+{
+  MgKHasher H = mg_make_khasher(k, d, factor1);
+  if (!H.lut) return -1;
+  std::vector<uint8_t> lut(MG_LUT_SIZE);
+  for (uint32_t x = 0; x < MG_LUT_SIZE; ++x) lut[x] = (uint8_t)mg_lut_entry(H, x);
+  uint64_t nWords = (nBases + 31) / 32 + 4;
+  std::vector<uint64_t> words(nWords, 0);
+  hm_pack(bytes, nBases, ascii, words.data(), nWords);
+  int64_t bad = 0;
+  *nCand = 0;
+  for (uint64_t T = 0; T * 32 < nBases; T += 2)
+    { uint32_t lo, hi, c[2] = { 0, 0 };
+      if (k == 31) mg_lut_scan<31>(lut.data(), words[T], words[T + 1], words[T + 2], &lo, &hi);
+      else mg_lut_scan<30>(lut.data(), words[T], words[T + 1], words[T + 2], &lo, &hi);
+      for (int h = 0; h < 2; ++h)
+        { MgRun R = mg_run_prepare(words[T + h], words[T + h + 1], H.k);
+          for (uint32_t i = 0; i < 32; ++i) c[h] |= (mg_prefilter_candidate(H, R, i) ? 1u : 0u) << i;
+        }
+      if (lo != c[0]) ++bad;
+      if (hi != c[1]) ++bad;
+      *nCand += __builtin_popcount(c[0]) + __builtin_popcount(c[1]);
+    }
+  return bad;
+}
+
 uint64_t hm_slot_hash(uint64_t kmer, uint32_t bits) { return mg_slot_hash(kmer, bits); }
 uint32_t hm_owner(uint64_t kmer, uint32_t n) { return mg_owner(kmer, n); }
 

@@ -33,6 +33,8 @@ def lib():
         l.hm_khasher.argtypes = [C.c_int, C.c_int, C.c_uint64, u64p]
         l.hm_divisible.restype = C.c_int
         l.hm_divisible.argtypes = [C.c_int, C.c_uint64]
+        l.hm_lut_check.restype = C.c_int64
+        l.hm_lut_check.argtypes = [C.c_int, C.c_int, C.c_uint64, u8p, C.c_uint64, C.c_int, u64p]
         l.hm_slot_hash.restype = C.c_uint64
         l.hm_slot_hash.argtypes = [C.c_uint64, C.c_uint32]
         l.hm_owner.restype = C.c_uint32
@@ -56,6 +58,14 @@ def select(k, d, factor1, data, offs, is_ascii=0, prefilter=-1):
     cnt = lib().hm_select(k, d, factor1, data if data.size else np.zeros(1, np.uint8), n, is_ascii, offs, len(offs) - 1,
                           prefilter, km, gp, isf, cap)
     return km[:cnt], gp[:cnt], isf[:cnt]
+
+
+def lut_check(k, d, factor1, data, is_ascii=0):
+    """(mismatching candidate masks, candidates) of the table-driven prefilter vs the arithmetic one; (-1, 0) if n/a"""
+    data = np.ascontiguousarray(data, np.uint8)
+    ncand = np.zeros(1, np.uint64)
+    bad = lib().hm_lut_check(k, d, factor1, data, len(data), is_ascii, ncand)
+    return int(bad), int(ncand[0])
 
 
 def genome(seed, start, n, dup_mode=0):

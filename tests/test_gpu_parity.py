@@ -194,6 +194,29 @@ def test_select_large_multi_tile(mg, torch_cuda, orc):
         assert np.array_equal(np.sort(km), np.sort(ek)), (k, d)
 
 
+def test_select_table_prefilter(mg, torch_cuda, orc):
+    """count mode with the shared-memory candidate table (k >= 30, 64-2k+tz <= 8) == oracle == arithmetic
+    prefilter (flag 64) == no prefilter (flag 8), TMA and plain loads, ragged multi-tile batches"""
+    rng = np.random.default_rng(78)
+    lens = np.concatenate([rng.integers(20, 30000, 200), [0, 1, 29, 30, 31, 32, 33, 61, 62, 63, 64, 65, 0, 95, 96, 97]])
+    rng.shuffle(lens)
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    data = rng.integers(0, 4, int(offs[-1])).astype(np.uint8)
+    data[1000:1500] = 0
+    data[70000:71000:2] = 3
+    for (k, d, seed) in ((31, 64, 17), (31, 64, 0), (31, 32, 3), (31, 8, 5), (31, 192, 17), (30, 16, 17), (30, 8, 1), (31, 128, 9)):
+        ek, ep, ef = oracle_select(orc, k, d, seed, data, offs)
+        o2 = np.lexsort((ek, ep))
+        for flags in (0, 4, 64, 8):
+            km, gp, _ = gpu_select(mg, torch_cuda, k, d, seed, data, offs, flags=flags | 2)
+            kk = km & np.uint64((1 << 62) - 1)
+            ff = (km >> np.uint64(63)).astype(np.uint8)
+            o1 = np.lexsort((kk, gp))
+            assert len(km) == len(ek), (k, d, flags)
+            assert np.array_equal(kk[o1], ek[o2]) and np.array_equal(gp[o1].astype(np.int64), ep[o2]), (k, d, flags)
+            assert np.array_equal(ff[o1], ef[o2]), (k, d, flags)
+
+
 # ------------------------------------------------------------------ modset --
 def _check_modset(mg, orc, bits, k, d, seed, data, offs, exact):
     ms = mg.Modset(bits, k, d, seed, exact_order=exact)

@@ -75,6 +75,25 @@ def test_select_matches_oracle(orc, prefilter):
         assert np.array_equal(km, ek) and np.array_equal(gp.astype(np.int64), ep) and np.array_equal(isf, ef), (k, d, seed, trial)
 
 
+@pytest.mark.parametrize("k,d", [(31, 64), (31, 32), (31, 8), (31, 192), (30, 16), (30, 8), (31, 128), (19, 32)])
+def test_table_prefilter_equals_arithmetic_prefilter(k, d):
+    """mg_lut_scan (one shared-memory lookup per 4 positions) marks exactly the windows the
+    multiplicative low-word prefilter marks, wherever the kernel would use the table"""
+    rng = np.random.default_rng(k * 1000 + d)
+    data = rng.integers(0, 4, 200000, dtype=np.uint8)
+    data[5000:5200] = 0                      # poly-A and a dinucleotide repeat
+    data[9000:9400:2] = 0
+    data[9001:9400:2] = 3
+    for f1 in (0x49308bb9003cb3ad, 0x6b8b4567327b23c7, 0xffffffffffffffff, 1):
+        bad, ncand = he.lut_check(k, d, f1, data)
+        applies = (64 - 2 * k) + (d & -d).bit_length() - 1 <= 8 and k >= 30 and (d & -d) >= 8
+        if not applies:
+            assert bad == -1
+            continue
+        assert bad == 0
+        assert ncand > 0
+
+
 def test_synth_generators_are_stable():
     """the synthetic inputs are part of the golden contract: pin a few bytes"""
     g = he.genome(12345, 0, 64, 1)
