@@ -309,6 +309,27 @@ int modgpuOwnerCount(const uint64_t *d_kmers, uint64_t n, uint32_t nOwners, uint
 int modgpuOwnerScatter(const uint64_t *d_kmers, uint64_t n, uint32_t nOwners, uint64_t *d_cursors,
                        uint64_t *d_out, void *stream);
 
+/* ------------------------------------------------- peer memory (NVLink) --
+ * The multi-GPU exchange without a copy: every rank scatters its selected k-mers
+ * into per-(owner, region) buckets in ITS OWN memory (modgpuModsetSelectBuckets*),
+ * and the owner's region build reads the buckets of all ranks directly through
+ * peer-mapped pointers (modgpuModsetBuildFromPeers) - the transfer happens inside
+ * the build kernel, bucket by bucket, and only filled entries cross NVLink.
+ * One process per GPU: buffers are shared through CUDA IPC handles (64 bytes). */
+#define MODGPU_PEER_HANDLE_BYTES 64
+#define MODGPU_MAX_PEERS 16
+void *modgpuPeerAlloc(size_t bytes);
+void modgpuPeerFree(void *d_ptr);
+int modgpuPeerExport(void *d_ptr, void *handle64);
+void *modgpuPeerOpen(const void *handle64);
+int modgpuPeerClose(void *d_ptr);
+/* d_buckets[s] / d_overflow[s]: source rank s's bucket array / overflow segment FOR THIS OWNER (peer-mapped,
+ * nRegions x bucketCap / overflowCap k-mers); d_cursors, d_ovfCounts: LOCAL copies of the fill counts,
+ * [nSrc][nRegions] and [nSrc] (the count exchange doubles as the cross-GPU barrier). */
+int modgpuModsetBuildFromPeers(ModgpuModset *ms, const uint64_t *const *d_buckets, const uint32_t *d_cursors,
+                               uint32_t bucketCap, uint32_t nSrc, const uint64_t *const *d_overflow,
+                               uint64_t overflowCap, const uint32_t *d_ovfCounts);
+
 /* ---------------------------------------------------- pinned host memory --
  * "seqio parsing stays on the host, feeding pinned buffers" */
 void *modgpuHostAlloc(size_t bytes);

@@ -84,6 +84,12 @@ _SIGS = {
     "modgpuModsetSelectBucketsDevice": (C.c_int, [vp, vp, vp, u64, u64, C.c_int, u32, vp, u32, vp, vp, u64, vp, vp]),
     "modgpuModsetSelectBucketsHost": (C.c_int, [vp, vp, vp, u64, C.c_int, u32, vp, u32, vp, vp, u64, vp, vp]),
     "modgpuModsetBuildFromBuckets": (C.c_int, [vp, vp, vp, u32, u32, vp, u64, vp]),
+    "modgpuModsetBuildFromPeers": (C.c_int, [vp, vp, vp, u32, u32, vp, u64, vp]),
+    "modgpuPeerAlloc": (vp, [C.c_size_t]),
+    "modgpuPeerFree": (None, [vp]),
+    "modgpuPeerExport": (C.c_int, [vp, vp]),
+    "modgpuPeerOpen": (vp, [C.c_char_p]),
+    "modgpuPeerClose": (C.c_int, [vp]),
     "modgpuModsetInsertSegments": (C.c_int, [vp, vp, u32, u64, vp, u64]),
     "modgpuModsetInsertDevice": (C.c_int, [vp, vp, u64]),
     "modgpuModsetClear": (C.c_int, [vp]),

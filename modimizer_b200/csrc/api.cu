@@ -493,6 +493,18 @@ extern "C" int modgpuModsetBuildFromBuckets(ModgpuModset *ms, const uint64_t *d_
   return MODGPU_OK;
 }
 
+// the same with the buckets left in the source ranks' memory: the region build reads them over NVLink
+extern "C" int modgpuModsetBuildFromPeers(ModgpuModset *ms, const uint64_t *const *d_buckets, const uint32_t *d_cursors,
+                                          uint32_t bucketCap, uint32_t nSrc, const uint64_t *const *d_overflow,
+                                          uint64_t overflowCap, const uint32_t *d_ovfCounts)
+{
+  ProfScope p(ms, MODGPU_T_INSERT, 2);
+  int rc = mg_table_build_from_peers(ms->table, d_buckets, d_cursors, bucketCap, nSrc, d_overflow, overflowCap, d_ovfCounts, ms->stream);
+  if (rc) return rc;
+  ms->dirty = true;
+  return MODGPU_OK;
+}
+
 // insert + count nSegs received segments (device counts, uint32 each) into the object's table
 extern "C" int modgpuModsetInsertSegments(ModgpuModset *ms, const uint64_t *d_segments, uint32_t nSegs, uint64_t segCap,
                                           const uint32_t *d_counts, uint64_t expectedN)

@@ -300,16 +300,32 @@ __global__ void __launch_bounds__(MG_SEL_THREADS) hash_select_ordered_kernel(con
 }
 
 // ------------------------------------------------------------------ count --
-// Count mode (order irrelevant).  One block barrier per tile; everything after the
-// tile is in shared memory is WARP-local: a warp compacts the candidates of its own
-// 2048 windows into its own queue (warp scan), spreads their full evaluation evenly
-// over its lanes, keeps up to MG_SEL_ROUNDS results per lane in registers so that
-// the atomics of a lane are all in flight together, and writes them out.
+// Count mode (order irrelevant): every WARP is autonomous.  A warp owns tiles of
+// 64 runs (2048 window starts), t = global warp, + total warps, ...
+//   - the tile (2 KiB of raw bytes, or 512 B of packed words, plus its end flags)
+//     is staged in the warp's own shared-memory buffer by TMA bulk copies
+//     (cp.async.bulk + a per-warp mbarrier; SASS UBLKCP); the copy of the NEXT tile
+//     is issued as soon as the lanes have pulled the current one into registers,
+//     so it streams in behind the whole computation of this tile;
+//   - K1 fused: a lane packs its 64 bytes into two words (pack16_dev);
+//   - candidates: table-driven (LUTK, one shared-memory lookup per 4 positions),
+//     multiplicative low-word prefilter, or full evaluation of every window;
+//   - the candidates of the warp's 2048 windows are compacted into the warp's queue
+//     (warp scan), evaluated evenly by its lanes, kept in registers (MG_SEL_ROUNDS
+//     per lane) so that the atomics of a lane are all in flight together, and written.
+// No block barrier after the prologue; the only block-shared state is the read-only
+// candidate table.
 // OUT: 0 = list, 1 = scatter into the table's region buckets, 2 = per-owner segments,
 //      3 = per-(owner, region) buckets: what the owner's region build consumes directly
-// LOAD: 0 = plain loads of the packed stream, 1 = TMA bulk staging of the packed stream,
-//       2 = raw bytes (codes or ASCII): K1 fused into the tile loader, no packed stream in HBM at all
-#define MG_WQ_CAP 512                                         // queue entries per warp (of its 2048 windows)
+// RAW: the batch as bytes (codes or ASCII, 16-byte aligned) instead of the packed stream
+#define MG_CNT_WARPS 16
+#define MG_CNT_THREADS (MG_CNT_WARPS * 32)
+#define MG_WT_RUNS 64                                          // runs per warp tile
+#define MG_WT_BASES (MG_WT_RUNS * MG_RUN)                      // 2048
+#define MG_WQ_CAP 256                                          // queue entries per warp (of its 2048 windows)
+#define MG_WS_RAW_BYTES (MG_WT_BASES + 32)                     // the tile + the overlap word's 32 bases
+#define MG_WS_PACK_BYTES (MG_WT_RUNS * 8 + 16)                 // 64 words + overlap word (+ pad to 16 B)
+#define MG_WS_ENDS_BYTES (MG_WT_RUNS * 4 + 16)                 // 64 flag words + 2 (+ pad)
 
 // 16 bytes -> 16 two-bit codes, first base in the top bits (K1 arithmetic, mg_pack4;
 // the four gathered bytes are merged with three byte permutes instead of shifts and masks)
@@ -328,6 +344,7 @@ __device__ __forceinline__ uint32_t pack16_dev(const uint4 q)
   return __byte_perm(t, u, 0x3254);
 }
 
+// 32 bases starting at b0 of the raw batch, with bounds (the ragged last tile only)
 template <bool ASCII>
 __device__ __forceinline__ uint64_t pack32_raw(const uint8_t *raw, uint64_t b0, uint64_t nBases)
 {
@@ -335,108 +352,109 @@ __device__ __forceinline__ uint64_t pack32_raw(const uint8_t *raw, uint64_t b0, 
     { const uint4 *src = reinterpret_cast<const uint4 *>(raw + b0);
       return ((uint64_t)pack16_dev<ASCII>(__ldg(src)) << 32) | pack16_dev<ASCII>(__ldg(src + 1));
     }
-  uint64_t w = 0;                                             // the ragged end of the batch, byte by byte
+  uint64_t w = 0;
   for (uint32_t j = 0; j < 32 && b0 + j < nBases; ++j)
     w |= (uint64_t)mg_code_of(raw[b0 + j], ASCII) << (62 - 2 * j);
   return w;
 }
 
-template <bool PREFILTER, int LOAD, int OUT, bool ASCII, int LUTK>
-__global__ void __launch_bounds__(MG_SEL_THREADS) hash_count_kernel(const SelectParams P)
+template <bool RAW> struct CountWarpSmem {
+  __align__(16) uint8_t stage[RAW ? MG_WS_RAW_BYTES : MG_WS_PACK_BYTES];
+  __align__(16) uint32_t ends[MG_WS_ENDS_BYTES / 4];
+  __align__(16) uint64_t words[MG_WT_RUNS + 2];                // the packed tile, read by phase 3
+  __align__(8) uint64_t bar;
+  uint16_t queue[MG_WQ_CAP];
+  uint32_t own[64];                                            // OUT == 2: per-owner counts, then bases
+};
+
+
+template <bool RAW>
+__device__ __forceinline__ void count_issue_tile(const SelectParams &P, CountWarpSmem<RAW> *S, uint64_t tile)
+{ // one elected lane: both bulk copies of a tile signal the warp's mbarrier
+  mg_mbar_expect_tx(&S->bar, (RAW ? MG_WS_RAW_BYTES : MG_WS_PACK_BYTES) + MG_WS_ENDS_BYTES);
+  if (RAW) mg_tma_load_1d(S->stage, P.raw + tile * MG_WT_BASES, MG_WS_RAW_BYTES, &S->bar);
+  else mg_tma_load_1d(S->stage, P.packed + tile * MG_WT_RUNS, MG_WS_PACK_BYTES, &S->bar);
+  mg_tma_load_1d(S->ends, P.ends + tile * MG_WT_RUNS, MG_WS_ENDS_BYTES, &S->bar);
+}
+
+template <bool PREFILTER, bool RAW, int OUT, bool ASCII, int LUTK>
+__global__ void __launch_bounds__(MG_CNT_THREADS, LUTK ? 3 : 2) hash_count_kernel(const SelectParams P)
 {
   static_assert(LUTK == 0 || PREFILTER, "the table-driven scan is a prefilter");
-  __shared__ __align__(16) uint8_t sLut[LUTK ? MG_LUT_SIZE : 16];
-  constexpr bool TMA = (LOAD == 1);
-  constexpr bool RAW = (LOAD == 2);
   constexpr bool SCATTER = (OUT == 1 || OUT == 3);
   constexpr bool OWNERS = (OUT == 2);
   constexpr bool PEER = (OUT == 3);
-  constexpr int NWARPS = MG_SEL_THREADS / 32;
-  __shared__ __align__(128) uint64_t sPack[2][MG_TILE_PACK_BYTES / 8];
-  __shared__ __align__(128) uint32_t sEnds[TMA ? 2 : 1][TMA ? (MG_TILE_ENDS_BYTES / 4) : 4];
-  __shared__ __align__(8) uint64_t sBar[2];
-  __shared__ uint16_t sQueue[NWARPS][MG_WQ_CAP];
-  __shared__ uint32_t sOwn[OWNERS ? NWARPS : 1][OWNERS ? 64 : 1];
-  __shared__ uint32_t sOwnBase[OWNERS ? NWARPS : 1][OWNERS ? 64 : 1];
-  __shared__ uint32_t sTile[2];
+  extern __shared__ __align__(128) uint8_t sDyn[];
+  uint8_t *sLut = sDyn;                                                           // MG_LUT_SIZE bytes when LUTK
+  CountWarpSmem<RAW> *S = reinterpret_cast<CountWarpSmem<RAW> *>(sDyn + (LUTK ? MG_LUT_SIZE : 0)) + (threadIdx.x >> 5);
 
   const MgKHasher &H = P.H;
   const uint32_t tid = threadIdx.x;
-  const uint32_t lane = tid & 31, warp = tid >> 5;
-  uint16_t *wq = sQueue[warp];
+  const uint32_t lane = tid & 31;
+  const uint64_t nWarps = (uint64_t)gridDim.x * MG_CNT_WARPS;
+  uint64_t tile = (uint64_t)blockIdx.x * MG_CNT_WARPS + (tid >> 5);
+  // a tile can be bulk-copied when all of it (and the overlap) lies inside the batch; the packed
+  // stream and the flags carry slack words past the end, the raw bytes do not
+  const uint64_t nBulk = RAW ? (P.nBases >= MG_WS_RAW_BYTES ? (P.nBases - MG_WS_RAW_BYTES) / MG_WT_BASES + 1 : 0) : P.nTiles;
   uint32_t nSelectedLocal = 0;                             // SCATTER: this thread's share of the total
+  uint32_t phase = 0;
 
-  if (tid == 0)
-    { if (TMA)
-        { mg_mbar_init(&sBar[0], 1);
-          mg_mbar_init(&sBar[1], 1);
-          mg_fence_barrier_init();
-          mg_fence_proxy_async();
-        }
-      uint32_t t0 = atomicAdd(P.ticket, 1u);
-      sTile[0] = t0;
-      if (TMA && t0 < P.nTiles)
-        { mg_mbar_expect_tx(&sBar[0], MG_TILE_PACK_BYTES + MG_TILE_ENDS_BYTES);
-          mg_tma_load_1d(sPack[0], P.packed + (uint64_t)t0 * MG_TILE_THREADS, MG_TILE_PACK_BYTES, &sBar[0]);
-          mg_tma_load_1d(sEnds[0], P.ends + (uint64_t)t0 * MG_TILE_THREADS, MG_TILE_ENDS_BYTES, &sBar[0]);
-        }
+  if (lane == 0)
+    { mg_mbar_init(&S->bar, 1);
+      mg_fence_barrier_init();
+      mg_fence_proxy_async();
+      if (tile < nBulk) count_issue_tile<RAW>(P, S, tile);
     }
   if (LUTK)
     { const uint4 *src = reinterpret_cast<const uint4 *>(P.lut);
       uint4 *dst = reinterpret_cast<uint4 *>(sLut);
-      for (uint32_t i = tid; i < MG_LUT_SIZE / 16; i += MG_SEL_THREADS) dst[i] = __ldg(src + i);
+      for (uint32_t i = tid; i < MG_LUT_SIZE / 16; i += MG_CNT_THREADS) dst[i] = __ldg(src + i);
     }
-  if (!TMA || LUTK) __syncthreads();
+  __syncthreads();
 
-  for (uint32_t it = 0;; ++it)
-    { const uint32_t stage = it & 1;
-      // the ONE block barrier of a tile.  TMA: at the top (everyone is done reading the buffer the next
-      // bulk copy lands in, sTile[stage] is visible); otherwise after the tile has been written to
-      // sPack[stage] (which nobody reads any more: its last readers passed the previous barrier).
-      if (TMA) __syncthreads();
-      const uint32_t tile = sTile[stage];
-      if (tile >= P.nTiles) break;
-
-      if (tid == 0)
-        { uint32_t tn = atomicAdd(P.ticket, 1u);
-          sTile[stage ^ 1] = tn;
-          if (TMA && tn < P.nTiles)
-            { mg_mbar_expect_tx(&sBar[stage ^ 1], MG_TILE_PACK_BYTES + MG_TILE_ENDS_BYTES);
-              mg_tma_load_1d(sPack[stage ^ 1], P.packed + (uint64_t)tn * MG_TILE_THREADS, MG_TILE_PACK_BYTES, &sBar[stage ^ 1]);
-              mg_tma_load_1d(sEnds[stage ^ 1], P.ends + (uint64_t)tn * MG_TILE_THREADS, MG_TILE_ENDS_BYTES, &sBar[stage ^ 1]);
-            }
-        }
-
-      // ---- this thread's two runs: words 2t, 2t+1 (+ overlap word 2t+2), 96 end flags
-      const uint32_t run0 = tid * MG_SEL_RPT;
-      const uint64_t word = (uint64_t)tile * MG_TILE_THREADS + run0;
+  for (; tile < P.nTiles; tile += nWarps)
+    { // ---- this lane's two runs: words 2l, 2l+1 (+ overlap word 2l+2), 96 end flags
+      const uint32_t run0 = lane * MG_SEL_RPT;
+      const uint64_t tileBase = tile * MG_WT_BASES;
       uint64_t w0, w1, w2;
       uint32_t e0, e1, e2;
-      if (TMA)
-        { mg_mbar_wait(&sBar[stage], (it >> 1) & 1);
-          w0 = sPack[stage][run0]; w1 = sPack[stage][run0 + 1]; w2 = sPack[stage][run0 + 2];
-          e0 = sEnds[stage][run0]; e1 = sEnds[stage][run0 + 1]; e2 = sEnds[stage][run0 + 2];
-        }
-      else
-        { e0 = __ldg(P.ends + word); e1 = __ldg(P.ends + word + 1); e2 = __ldg(P.ends + word + 2);
+      if (tile < nBulk)
+        { mg_mbar_wait(&S->bar, phase);
+          phase ^= 1;
+          e0 = S->ends[run0]; e1 = S->ends[run0 + 1]; e2 = S->ends[run0 + 2];
+          uint64_t wx = 0;                                  // the overlap word, from lanes 0 and 1
           if (RAW)
-            { // K1 fused: this thread's 64 bytes -> two packed words
-              const uint64_t b0 = word * MG_RUN;
-              w0 = pack32_raw<ASCII>(P.raw, b0, P.nBases);
-              w1 = pack32_raw<ASCII>(P.raw, b0 + 32, P.nBases);
-              // the overlap word of the tile: the first 32 bases of the next one
-              if (tid == MG_SEL_THREADS - 1) sPack[stage][MG_TILE_THREADS] = pack32_raw<ASCII>(P.raw, b0 + 64, P.nBases);
+            { const uint4 *src = reinterpret_cast<const uint4 *>(S->stage) + lane * 4;
+              const uint4 q0 = src[0], q1 = src[1], q2 = src[2], q3 = src[3];
+              w0 = ((uint64_t)pack16_dev<ASCII>(q0) << 32) | pack16_dev<ASCII>(q1);
+              w1 = ((uint64_t)pack16_dev<ASCII>(q2) << 32) | pack16_dev<ASCII>(q3);
+              uint32_t x = 0;
+              if (lane < 2) x = pack16_dev<ASCII>(reinterpret_cast<const uint4 *>(S->stage)[128 + lane]);
+              wx = ((uint64_t)__shfl_sync(0xffffffffu, x, 0) << 32) | __shfl_sync(0xffffffffu, x, 1);
             }
           else
-            { w0 = __ldg(P.packed + word); w1 = __ldg(P.packed + word + 1);
-              if (tid == MG_SEL_THREADS - 1) sPack[stage][MG_TILE_THREADS] = __ldg(P.packed + word + 2);
+            { const uint64_t *src = reinterpret_cast<const uint64_t *>(S->stage);
+              w0 = src[run0]; w1 = src[run0 + 1];
+              wx = src[MG_WT_RUNS];
             }
-          sPack[stage][run0] = w0;                         // phase 3 reads the tile from shared memory
-          sPack[stage][run0 + 1] = w1;
-          __syncthreads();
-          w2 = sPack[stage][run0 + 2];
+          S->words[run0] = w0; S->words[run0 + 1] = w1;
+          if (lane == 0) S->words[MG_WT_RUNS] = wx;
         }
-      const uint64_t tileBase = (uint64_t)tile * MG_TILE_BASES;
+      else
+        { // the ragged end of a raw batch: guarded loads
+          const uint64_t word = tile * MG_WT_RUNS + run0;
+          e0 = __ldg(P.ends + word); e1 = __ldg(P.ends + word + 1); e2 = __ldg(P.ends + word + 2);
+          w0 = pack32_raw<ASCII>(P.raw, word * MG_RUN, P.nBases);
+          w1 = pack32_raw<ASCII>(P.raw, word * MG_RUN + 32, P.nBases);
+          S->words[run0] = w0; S->words[run0 + 1] = w1;
+          if (lane == 31) S->words[MG_WT_RUNS] = pack32_raw<ASCII>(P.raw, word * MG_RUN + 64, P.nBases);
+        }
+      __syncwarp();
+      // every lane has consumed its part of the staged tile (the stores above depend on it): the buffer is
+      // free, and the next tile's copy streams in behind the whole computation of this one
+      if (lane == 0 && tile + nWarps < nBulk) count_issue_tile<RAW>(P, S, tile + nWarps);
+      w2 = S->words[run0 + 2];
+
       uint32_t m0, m1;
       { const uint64_t p0 = tileBase + (uint64_t)run0 * MG_RUN;
         if (LUTK)
@@ -451,12 +469,13 @@ __global__ void __launch_bounds__(MG_SEL_THREADS) hash_count_kernel(const Select
         m1 &= mg_run_usable((uint64_t)e1 | ((uint64_t)e2 << 32), H.k, p0 + MG_RUN, P.nBases);
       }
 
-      // ---- phase 2 (warp): queue of (run, window) of this warp's 64 runs
+      // ---- phase 2: queue of (run, window) of this warp's 64 runs
       const uint32_t cnt = __popc(m0) + __popc(m1);
       const uint32_t incl = mg_warp_incl_scan(cnt);
       const uint32_t nW = __shfl_sync(0xffffffffu, incl, 31);
-      if (nW == 0) continue;
+      if (nW == 0) { __syncwarp(); continue; }
       const bool queued = nW <= MG_WQ_CAP;                 // warp-uniform
+      uint16_t *wq = S->queue;
       if (queued)
         { uint32_t qoff = incl - cnt;
           uint32_t mm = m0;
@@ -466,8 +485,8 @@ __global__ void __launch_bounds__(MG_SEL_THREADS) hash_count_kernel(const Select
         }
       __syncwarp();
 
-      // ---- phase 3 (warp): evaluation and output
-      const uint64_t *sWords = sPack[stage];
+      // ---- phase 3: evaluation and output
+      const uint64_t *sWords = S->words;
       if (queued && nW <= MG_SEL_ROUNDS * 32)
         { // the usual case: every lane evaluates its (<= MG_SEL_ROUNDS) queue entries into registers first
           uint64_t km[MG_SEL_ROUNDS];
@@ -486,28 +505,27 @@ __global__ void __launch_bounds__(MG_SEL_THREADS) hash_count_kernel(const Select
           if (OWNERS)
             { // per-owner segments: rank inside the warp's tile through shared memory, one reservation per owner
               uint32_t own[MG_SEL_ROUNDS], rk[MG_SEL_ROUNDS];
-              sOwn[warp][lane] = 0; sOwn[warp][lane + 32] = 0;
+              S->own[lane] = 0; S->own[lane + 32] = 0;
               __syncwarp();
 #pragma unroll
               for (int r = 0; r < MG_SEL_ROUNDS; ++r)
                 if ((okMask >> r) & 1u)
                   { own[r] = mg_owner(km[r], P.nOwners);
-                    rk[r] = atomicAdd(&sOwn[warp][own[r]], 1u);
+                    rk[r] = atomicAdd(&S->own[own[r]], 1u);
                   }
               __syncwarp();
 #pragma unroll
               for (uint32_t o = lane; o < 64; o += 32)
-                { const uint32_t c = (o < P.nOwners) ? sOwn[warp][o] : 0u;
-                  sOwnBase[warp][o] = c ? atomicAdd(&P.ownerCursor[o], c) : 0u;
+                { const uint32_t c = (o < P.nOwners) ? S->own[o] : 0u;
+                  S->own[o] = c ? atomicAdd(&P.ownerCursor[o], c) : 0u;
                 }
               __syncwarp();
 #pragma unroll
               for (int r = 0; r < MG_SEL_ROUNDS; ++r)
                 if ((okMask >> r) & 1u)
-                  { const uint64_t dst = (uint64_t)sOwnBase[warp][own[r]] + rk[r];
+                  { const uint64_t dst = (uint64_t)S->own[own[r]] + rk[r];
                     if (dst < P.ownerCap) P.ownerBuf[(uint64_t)own[r] * P.ownerCap + dst] = km[r];
                   }
-              __syncwarp();
             }
           else if (SCATTER)
             { nSelectedLocal += __popc(okMask);
@@ -615,6 +633,7 @@ __global__ void __launch_bounds__(MG_SEL_THREADS) hash_count_kernel(const Select
                 }
             }
         }
+      __syncwarp();                                         // the queue and the packed tile are free again
     }
   if (SCATTER)
     { nSelectedLocal = mg_warp_sum(nSelectedLocal);
@@ -647,41 +666,46 @@ static int launch_ordered(const SelectParams &P, cudaStream_t st)
   return MODGPU_OK;
 }
 
-template <bool PF, int LOAD, int OUT, bool ASCII, int LUTK>
-static int launch_count(const SelectParams &P, cudaStream_t st)
+template <bool PF, bool RAW, int OUT, bool ASCII, int LUTK>
+static int launch_count(const SelectParams &P0, cudaStream_t st)
 {
   static int blocksPerSm = 0;
+  const size_t smem = (LUTK ? MG_LUT_SIZE : 0) + MG_CNT_WARPS * sizeof(CountWarpSmem<RAW>);
   if (!blocksPerSm)
-    { MG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, hash_count_kernel<PF, LOAD, OUT, ASCII, LUTK>, MG_SEL_THREADS, 0));
+    { MG_CUDA(cudaFuncSetAttribute(hash_count_kernel<PF, RAW, OUT, ASCII, LUTK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      MG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, hash_count_kernel<PF, RAW, OUT, ASCII, LUTK>, MG_CNT_THREADS, smem));
       if (blocksPerSm < 1) blocksPerSm = 1;
     }
+  SelectParams P = P0;
+  P.nTiles = (uint32_t)((P.nBases + MG_WT_BASES - 1) / MG_WT_BASES);         // warp tiles
   uint64_t grid = (uint64_t)mg_num_sms() * blocksPerSm;
-  if (grid > P.nTiles) grid = P.nTiles;
+  const uint64_t need = ((uint64_t)P.nTiles + MG_CNT_WARPS - 1) / MG_CNT_WARPS;
+  if (grid > need) grid = need;
   if (LUTK)
     { lut_build_kernel<<<MG_LUT_SIZE / 256, 256, 0, st>>>(P.H, const_cast<uint8_t *>(P.lut));
       MG_LAUNCH_CHECK("lut_build");
     }
-  hash_count_kernel<PF, LOAD, OUT, ASCII, LUTK><<<(unsigned)grid, MG_SEL_THREADS, 0, st>>>(P);
+  hash_count_kernel<PF, RAW, OUT, ASCII, LUTK><<<(unsigned)grid, MG_CNT_THREADS, smem, st>>>(P);
   MG_LAUNCH_CHECK("hash_count");
   return MODGPU_OK;
 }
 
-// count mode dispatch over (scan, loader) for one output mode.  scan: 0 full evaluation of every window,
+// count mode dispatch over (scan, input) for one output mode.  scan: 0 full evaluation of every window,
 // 1 multiplicative low-word prefilter, 30/31 table-driven prefilter for that k
 template <int OUT, bool PF, int LUTK>
-static int dispatch_count_load(const SelectParams &P, bool tma, cudaStream_t st)
+static int dispatch_count_load(const SelectParams &P, cudaStream_t st)
 {
-  if (P.raw) return P.rawAscii ? launch_count<PF, 2, OUT, true, LUTK>(P, st) : launch_count<PF, 2, OUT, false, LUTK>(P, st);
-  return tma ? launch_count<PF, 1, OUT, false, LUTK>(P, st) : launch_count<PF, 0, OUT, false, LUTK>(P, st);
+  if (P.raw) return P.rawAscii ? launch_count<PF, true, OUT, true, LUTK>(P, st) : launch_count<PF, true, OUT, false, LUTK>(P, st);
+  return launch_count<PF, false, OUT, false, LUTK>(P, st);
 }
 
 template <int OUT>
-static int dispatch_count(const SelectParams &P, bool pf, bool tma, int flags, cudaStream_t st)
+static int dispatch_count(const SelectParams &P, bool pf, int flags, cudaStream_t st)
 {
-  if (!pf) return dispatch_count_load<OUT, false, 0>(P, tma, st);
+  if (!pf) return dispatch_count_load<OUT, false, 0>(P, st);
   if (P.H.lut && !(flags & MODGPU_SEL_NOLUT))
-    return P.H.k == 31 ? dispatch_count_load<OUT, true, 31>(P, tma, st) : dispatch_count_load<OUT, true, 30>(P, tma, st);
-  return dispatch_count_load<OUT, true, 0>(P, tma, st);
+    return P.H.k == 31 ? dispatch_count_load<OUT, true, 31>(P, st) : dispatch_count_load<OUT, true, 30>(P, st);
+  return dispatch_count_load<OUT, true, 0>(P, st);
 }
 
 extern "C" int modgpuHashSelect(const ModgpuHasher *h, const uint64_t *d_packed, const uint32_t *d_ends,
@@ -709,7 +733,7 @@ extern "C" int modgpuHashSelect(const ModgpuHasher *h, const uint64_t *d_packed,
   const bool pf = P.H.prefilter && !(flags & MODGPU_SEL_NOPREFILTER);
   const bool ord = (flags & MODGPU_SEL_ORDERED) != 0;
   const bool tma = !(flags & MODGPU_SEL_NOTMA);
-  if (!ord) return dispatch_count<0>(P, pf, tma, flags, st);
+  if (!ord) return dispatch_count<0>(P, pf, flags, st);
   if (pf) return tma ? launch_ordered<true, true>(P, st) : launch_ordered<true, false>(P, st);
   return tma ? launch_ordered<false, true>(P, st) : launch_ordered<false, false>(P, st);
 }
@@ -740,7 +764,7 @@ int mg_hash_select_scatter(const ModgpuHasher *h, const uint64_t *d_packed, cons
   const bool pf = P.H.prefilter && !(flags & MODGPU_SEL_NOPREFILTER);
   const bool tma = !(flags & MODGPU_SEL_NOTMA);
   if (d_raw) { P.raw = d_raw; P.rawAscii = rawAscii ? 1u : 0u; }
-  return dispatch_count<1>(P, pf, tma, flags, st);
+  return dispatch_count<1>(P, pf, flags, st);
 }
 
 // K2 with the selected k-mers bucketed by owner GPU (multi-GPU count mode): segment o of d_buf
@@ -768,7 +792,7 @@ int mg_hash_select_owners(const ModgpuHasher *h, const uint64_t *d_packed, const
   MG_CUDA(cudaMemsetAsync(d_workspace, 0, 64, st));
   const bool pf = P.H.prefilter && !(flags & MODGPU_SEL_NOPREFILTER);
   const bool tma = !(flags & MODGPU_SEL_NOTMA);
-  return dispatch_count<2>(P, pf, tma, flags, st);
+  return dispatch_count<2>(P, pf, flags, st);
 }
 
 // K2 with the selected k-mers written into per-(owner, region) buckets (multi-GPU, fully fused):
@@ -805,7 +829,7 @@ int mg_hash_select_peer(const ModgpuHasher *h, const uint64_t *d_packed, const u
   const bool pf = P.H.prefilter && !(flags & MODGPU_SEL_NOPREFILTER);
   const bool tma = !(flags & MODGPU_SEL_NOTMA);
   if (d_raw) { P.raw = d_raw; P.rawAscii = rawAscii ? 1u : 0u; }
-  return dispatch_count<3>(P, pf, tma, flags, st);
+  return dispatch_count<3>(P, pf, flags, st);
 }
 
 // ---------------------------------------------------------------- locate --

@@ -24,6 +24,8 @@ int mg_hash_select_peer(const ModgpuHasher *h, const uint64_t *d_packed, const u
                         const uint8_t *d_raw, int rawAscii, cudaStream_t st);
 int mg_table_build_from_buckets(ModgpuTable *t, const uint64_t *d_buckets, const uint32_t *d_cursors, uint32_t cap, uint32_t nSrc,
                                 const uint64_t *d_overflow, uint64_t overflowCap, const uint32_t *d_ovfCounts, cudaStream_t st);
+int mg_table_build_from_peers(ModgpuTable *t, const uint64_t *const *d_buckets, const uint32_t *d_cursors, uint32_t cap, uint32_t nSrc,
+                              const uint64_t *const *d_overflow, uint64_t overflowCap, const uint32_t *d_ovfCounts, cudaStream_t st);
 uint32_t mg_table_regions(const ModgpuTable *t);
 uint32_t mg_table_slot_bits(const ModgpuTable *t);
 int mg_hash_select_owners(const ModgpuHasher *h, const uint64_t *d_packed, const uint32_t *d_ends, uint64_t nBases,

@@ -193,6 +193,162 @@ __global__ void __launch_bounds__(256) region_build_multi_kernel(MgSlot *slots, 
   if (mg_lane() == 0 && fresh) atomicAdd(entries, (unsigned long long)fresh);
 }
 
+// The same with the buckets still in the SOURCE ranks' memory (peer-mapped over NVLink): the transfer of
+// the exchange happens here, bucket by bucket, overlapped with the creation of the region in shared
+// memory, and only filled entries cross the links.  cursors = local copies of the fill counts
+// [nSrc][srcStride]; src.p[s] = source s's bucket array for this owner (nRegions x cap).
+struct MgPeerSrc { const uint64_t *p[MODGPU_MAX_PEERS]; };
+
+__device__ __forceinline__ unsigned long long mg_ld_peer(const uint64_t *p)
+{ // the data was produced by another GPU's kernel: never served from this SM's L1
+  unsigned long long v;
+  asm volatile("ld.global.cv.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+
+// Persistent and software-pipelined: a block builds regions b, b + grid, ...; while region i is being
+// built in shared memory, the k-mers of region i+1 are already in flight into registers and the fill
+// counts of region i+2 are being fetched, so neither the NVLink round trip (peer sources) nor the DRAM
+// latency (local source) sits on the critical path.  Work split: a warp owns (source, part) units - with
+// nSrc <= 8 sources every bucket is read by 8 / nSrc warps, lanes on consecutive k-mers (coalesced
+// 256-byte requests over NVLink), no search for the source of an element.  PEER: loads bypass this SM's L1.
+#define MG_PIPE_PRELOAD 3                                       // k-mers per lane and unit kept in registers
+template <bool FRESH, bool PEER, int MG_PIPE_UNITS>             // units per warp: 1 for nSrc <= 8, 2 up to 16
+__global__ void __launch_bounds__(256, 5) region_build_pipe_kernel(MgSlot *slots, uint32_t slotBits, const MgPeerSrc src,
+                                                                const uint32_t *__restrict__ cursors, uint32_t cap, uint32_t nSrc,
+                                                                uint64_t srcStride, uint32_t nRegions,
+                                                                unsigned long long *entries, uint32_t *error)
+{
+  __shared__ uint4 sR[MG_REGION_SLOTS];
+  __shared__ const uint64_t *sSrc[MODGPU_MAX_PEERS];            // (a dynamically indexed kernel parameter would live in local memory)
+  MgSlot *sS = reinterpret_cast<MgSlot *>(sR);
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t fresh = 0;
+  if (tid == 0)
+    {
+#pragma unroll
+      for (int i = 0; i < MODGPU_MAX_PEERS; ++i) sSrc[i] = src.p[i];
+    }
+  __syncthreads();
+  const uint32_t parts = nSrc >= 8 ? 1u : 8u / nSrc;            // warps per bucket
+  const uint32_t nUnits = nSrc * parts;
+  // this warp's units: u = warp, warp + 8
+  const uint64_t *uBase[MG_PIPE_UNITS];
+  const uint32_t *uCur[MG_PIPE_UNITS];
+  uint32_t uFirst[MG_PIPE_UNITS];
+  bool uOn[MG_PIPE_UNITS];
+#pragma unroll
+  for (int q = 0; q < MG_PIPE_UNITS; ++q)
+    { const uint32_t u = warp + 8 * q;
+      uOn[q] = u < nUnits;
+      const uint32_t sIdx = uOn[q] ? u % nSrc : 0u;
+      uBase[q] = sSrc[sIdx];
+      uCur[q] = cursors + sIdx * srcStride;
+      uFirst[q] = (u / nSrc) * 32 + lane;                        // first element of this lane inside the bucket
+    }
+  const uint32_t step = parts * 32;
+
+  auto count_of = [&](int q, uint32_t region) -> uint32_t {
+    uint32_t c = 0;
+    if (uOn[q] && region < nRegions) { c = __ldg(uCur[q] + region); if (c > cap) c = cap; }
+    return c;
+  };
+  auto load_key = [&](int q, uint32_t region, uint32_t j) -> unsigned long long {
+    const uint64_t *p = uBase[q] + (uint64_t)region * cap + j;
+    return (PEER ? mg_ld_peer(p) : __ldcs(reinterpret_cast<const unsigned long long *>(p))) & 0x3FFFFFFFFFFFFFFFull;
+  };
+  auto insert = [&](unsigned long long key) {
+    uint32_t sl = (uint32_t)mg_slot_hash(key, slotBits) & (MG_REGION_SLOTS - 1);
+    uint32_t probes = 0;
+    for (; probes < MG_REGION_SLOTS; ++probes, sl = (sl + 1) & (MG_REGION_SLOTS - 1))
+      { unsigned long long *kp = reinterpret_cast<unsigned long long *>(&sS[sl].key);
+        unsigned long long cu = *reinterpret_cast<volatile unsigned long long *>(kp);
+        if (cu == key) break;
+        if (cu == MG_EMPTY)
+          { unsigned long long old = atomicCAS(kp, MG_EMPTY, key);
+            if (old == MG_EMPTY) { ++fresh; break; }
+            if (old == key) break;
+          }
+      }
+    if (probes == MG_REGION_SLOTS) { atomicExch(error, 1u); return; }
+    atomicAdd(&sS[sl].count, 1u);
+  };
+
+  uint32_t region = blockIdx.x;
+  if (region >= nRegions) return;
+  // pipeline state: cnt = fills of the current region, pre = its first k-mers; cntN / cntA = one and two regions ahead
+  uint32_t cnt[MG_PIPE_UNITS], cntN[MG_PIPE_UNITS], cntA[MG_PIPE_UNITS];
+  unsigned long long pre[MG_PIPE_UNITS][MG_PIPE_PRELOAD];
+#pragma unroll
+  for (int q = 0; q < MG_PIPE_UNITS; ++q)
+    { cnt[q] = count_of(q, region);
+      cntN[q] = count_of(q, region + gridDim.x);
+      cntA[q] = count_of(q, region + 2 * gridDim.x);
+#pragma unroll
+      for (int v = 0; v < MG_PIPE_PRELOAD; ++v)
+        { const uint32_t j = uFirst[q] + v * step;
+          pre[q][v] = (j < cnt[q]) ? load_key(q, region, j) : MG_EMPTY;
+        }
+    }
+
+  for (; region < nRegions; region += gridDim.x)
+    { const uint32_t next = region + gridDim.x;
+      uint4 *g = reinterpret_cast<uint4 *>(slots) + (uint64_t)region * MG_REGION_SLOTS;
+      bool any = FRESH;
+      if (!FRESH)
+        { uint32_t c = 0;
+#pragma unroll
+          for (int q = 0; q < MG_PIPE_UNITS; ++q) c |= cnt[q];
+          any = __syncthreads_or(c != 0);                     // nothing to add: leave the region alone (block-uniform)
+        }
+      if (any)
+        { uint4 e;
+          e.x = 0xFFFFFFFFu; e.y = 0xFFFFFFFFu; e.z = 0u; e.w = MG_AUX_FRESH;
+#pragma unroll
+          for (int i = 0; i < MG_REGION_SLOTS / 256; ++i)
+            sR[i * 256 + tid] = FRESH ? e : __ldcs(g + i * 256 + tid);
+        }
+      // the next region's k-mers: in flight while this one is built
+      unsigned long long nxt[MG_PIPE_UNITS][MG_PIPE_PRELOAD];
+#pragma unroll
+      for (int q = 0; q < MG_PIPE_UNITS; ++q)
+#pragma unroll
+        for (int v = 0; v < MG_PIPE_PRELOAD; ++v)
+          { const uint32_t j = uFirst[q] + v * step;
+            nxt[q][v] = (j < cntN[q]) ? load_key(q, next, j) : MG_EMPTY;
+          }
+      uint32_t cntB[MG_PIPE_UNITS];
+#pragma unroll
+      for (int q = 0; q < MG_PIPE_UNITS; ++q) cntB[q] = count_of(q, next + 2 * gridDim.x);     // three regions ahead
+      __syncthreads();                                         // the region is initialised
+      if (any)
+        {
+#pragma unroll
+          for (int q = 0; q < MG_PIPE_UNITS; ++q)
+            {
+#pragma unroll
+              for (int v = 0; v < MG_PIPE_PRELOAD; ++v)
+                if (uFirst[q] + v * step < cnt[q]) insert(pre[q][v]);
+              for (uint32_t j = uFirst[q] + MG_PIPE_PRELOAD * step; j < cnt[q]; j += step) insert(load_key(q, region, j));
+            }
+        }
+      __syncthreads();                                         // the region is complete
+      if (any)
+        {
+#pragma unroll
+          for (int i = 0; i < MG_REGION_SLOTS / 256; ++i) __stcs(g + i * 256 + tid, sR[i * 256 + tid]);
+        }
+#pragma unroll
+      for (int q = 0; q < MG_PIPE_UNITS; ++q)
+        { cnt[q] = cntN[q]; cntN[q] = cntA[q]; cntA[q] = cntB[q];
+#pragma unroll
+          for (int v = 0; v < MG_PIPE_PRELOAD; ++v) pre[q][v] = nxt[q][v];
+        }
+    }
+  fresh = mg_warp_sum(fresh);
+  if (mg_lane() == 0 && fresh) atomicAdd(entries, (unsigned long long)fresh);
+}
+
 template <bool FRESH, int PRELOAD>
 __global__ void __launch_bounds__(256) region_build_kernel(MgSlot *slots, uint32_t slotBits, const uint64_t *__restrict__ buckets,
                                                               const uint32_t *__restrict__ cursors, uint32_t cap,
@@ -481,7 +637,25 @@ int mg_table_bulk_finish(ModgpuTable *t, const MgBulk *b, cudaStream_t st)
   static int variant = -1;
   if (variant < 0) { const char *v = getenv("MODGPU_BUILD_VARIANT"); variant = v ? atoi(v) : 0; }
 #define MG_BUILD_LAUNCH(FR, PL) region_build_kernel<FR, PL><<<b->nRegions, 256, 0, st>>>(t->slots, t->slotBits, b->buckets, b->cursors, b->cap, t->dEntries, t->dError)
-  if (t->clearPending)
+  if (variant == 3)
+    { // persistent, software-pipelined build (the kernel of the peer-memory exchange, one local source)
+      static int blocksPerSm = 0;
+      if (!blocksPerSm)
+        { MG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, region_build_pipe_kernel<true, false, 1>, 256, 0));
+          if (blocksPerSm < 1) blocksPerSm = 1;
+        }
+      uint32_t grid = (uint32_t)mg_num_sms() * (uint32_t)blocksPerSm;
+      if (grid > b->nRegions) grid = b->nRegions;
+      MgPeerSrc src;
+      for (uint32_t s2 = 0; s2 < MODGPU_MAX_PEERS; ++s2) src.p[s2] = b->buckets;
+      if (t->clearPending)
+        { region_build_pipe_kernel<true, false, 1><<<grid, 256, 0, st>>>(t->slots, t->slotBits, src, b->cursors, b->cap, 1, b->nRegions, b->nRegions, t->dEntries, t->dError);
+          t->clearPending = false;
+        }
+      else
+        region_build_pipe_kernel<false, false, 1><<<grid, 256, 0, st>>>(t->slots, t->slotBits, src, b->cursors, b->cap, 1, b->nRegions, b->nRegions, t->dEntries, t->dError);
+    }
+  else if (t->clearPending)
     { if (variant == 1) MG_BUILD_LAUNCH(true, 4); else if (variant == 2) MG_BUILD_LAUNCH(true, 2); else MG_BUILD_LAUNCH(true, 0);
       t->clearPending = false;
     }
@@ -546,6 +720,42 @@ int mg_table_build_from_buckets(ModgpuTable *t, const uint64_t *d_buckets, const
       MG_CUDA(cudaMemsetAsync(wide, 0, 8, st));
       MG_CUDA(cudaMemcpyAsync(wide, d_ovfCounts + s, 4, cudaMemcpyDeviceToDevice, st));
       table_insert_kernel<false><<<grid_for(65536, 4), 256, 0, st>>>(t->slots, t->slotBits, d_overflow + (uint64_t)s * overflowCap, wide,
+                                                                     overflowCap, nullptr, t->dEntries, t->dError);
+      MG_LAUNCH_CHECK("overflow_insert");
+    }
+  return MODGPU_OK;
+}
+
+// build every region from the buckets in nSrc ranks' memory (peer-mapped) + their overflow segments
+int mg_table_build_from_peers(ModgpuTable *t, const uint64_t *const *d_buckets, const uint32_t *d_cursors, uint32_t cap, uint32_t nSrc,
+                              const uint64_t *const *d_overflow, uint64_t overflowCap, const uint32_t *d_ovfCounts, cudaStream_t st)
+{
+  if (nSrc < 1 || nSrc > MODGPU_MAX_PEERS) { mg_set_error("build from peers: %u sources out of range 1..%d", nSrc, MODGPU_MAX_PEERS); return MODGPU_EINVAL; }
+  const uint32_t nRegions = (uint32_t)(t->nSlots >> MG_REGION_BITS);
+  MgPeerSrc src;
+  for (uint32_t s = 0; s < MODGPU_MAX_PEERS; ++s) src.p[s] = d_buckets[s < nSrc ? s : 0];
+  static int blocksPerSm = 0;
+  if (!blocksPerSm)
+    { MG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, region_build_pipe_kernel<true, true, 1>, 256, 0));
+      if (blocksPerSm < 1) blocksPerSm = 1;
+    }
+  uint32_t grid = (uint32_t)mg_num_sms() * (uint32_t)blocksPerSm;
+  if (grid > nRegions) grid = nRegions;
+#define MG_PIPE_LAUNCH(FR, UN) region_build_pipe_kernel<FR, true, UN><<<grid, 256, 0, st>>>(t->slots, t->slotBits, src, d_cursors, cap, nSrc, nRegions, nRegions, t->dEntries, t->dError)
+  if (t->clearPending)
+    { if (nSrc <= 8) MG_PIPE_LAUNCH(true, 1); else MG_PIPE_LAUNCH(true, 2);
+      t->clearPending = false;
+    }
+  else
+    { if (nSrc <= 8) MG_PIPE_LAUNCH(false, 1); else MG_PIPE_LAUNCH(false, 2); }
+#undef MG_PIPE_LAUNCH
+  MG_LAUNCH_CHECK("region_build_peer");
+  // the (rare) k-mers that did not fit their bucket at the sender: direct inserts reading the peer's segment
+  for (uint32_t s = 0; d_overflow && s < nSrc; ++s)
+    { unsigned long long *wide = t->dEntries + 4 + (s & 3);
+      MG_CUDA(cudaMemsetAsync(wide, 0, 8, st));
+      MG_CUDA(cudaMemcpyAsync(wide, d_ovfCounts + s, 4, cudaMemcpyDeviceToDevice, st));
+      table_insert_kernel<false><<<grid_for(65536, 4), 256, 0, st>>>(t->slots, t->slotBits, d_overflow[s], wide,
                                                                      overflowCap, nullptr, t->dEntries, t->dError);
       MG_LAUNCH_CHECK("overflow_insert");
     }

@@ -103,3 +103,39 @@ extern "C" void *modgpuHostAlloc(size_t bytes)
 }
 
 extern "C" void modgpuHostFree(void *p) { if (p) cudaFreeHost(p); }
+
+// ---- peer memory (multi-GPU exchange over NVLink): buffers another rank's kernels read directly.
+// One process per GPU, so the mapping goes through CUDA IPC; cudaIpcOpenMemHandle enables peer
+// access between the two devices on first use.
+extern "C" void *modgpuPeerAlloc(size_t bytes)
+{
+  void *p = nullptr;
+  if (mg_check_cuda(cudaMalloc(&p, bytes ? bytes : 256), "cudaMalloc (peer buffer)", __FILE__, __LINE__)) return nullptr;
+  return p;
+}
+
+extern "C" void modgpuPeerFree(void *p) { if (p) cudaFree(p); }
+
+extern "C" int modgpuPeerExport(void *d_ptr, void *handle64)
+{
+  static_assert(sizeof(cudaIpcMemHandle_t) == MODGPU_PEER_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  MG_CUDA(cudaIpcGetMemHandle(&h, d_ptr));
+  memcpy(handle64, &h, sizeof(h));
+  return MODGPU_OK;
+}
+
+extern "C" void *modgpuPeerOpen(const void *handle64)
+{
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  void *p = nullptr;
+  if (mg_check_cuda(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle", __FILE__, __LINE__)) return nullptr;
+  return p;
+}
+
+extern "C" int modgpuPeerClose(void *d_ptr)
+{
+  if (d_ptr) MG_CUDA(cudaIpcCloseMemHandle(d_ptr));
+  return MODGPU_OK;
+}

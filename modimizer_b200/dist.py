@@ -60,9 +60,13 @@ class ShardedModset:
         # fused, sync-free exchange (default for world > 1): per-owner segments straight out of hash_select,
         # equal-split all-to-all, bulk insert of the received segments with device-side counts
         self.fused = True
-        # fused flavour: "peer" = per-(owner, region) buckets consumed directly by the owner's region build
+        # fused flavour: "p2p"  = per-(owner, region) buckets stay in the selecting rank's memory; the owner's region
+        #                         build reads them through peer-mapped pointers over NVLink (no payload collective,
+        #                         no host sync: the fill-count all-to-all doubles as the cross-GPU barrier)
+        #                "peer" = the same buckets moved with an equal-split NCCL all-to-all, then a local build
         #                "segments" = per-owner segments + a scatter pass at the receiver
-        self.fused_mode = "peer"
+        self.fused_mode = "p2p"
+        self._p2p = None
         self._peer_cap = 0
         self._seg_cap = 0
         self._sel_pending = 0
@@ -70,7 +74,107 @@ class ShardedModset:
         self._ovf_acc = torch.zeros(1, dtype=torch.int32, device=self.dev)
 
     def close(self):
+        self._p2p_release()
         self.local.close()
+
+    # ---- peer-memory exchange (fused_mode "p2p") -----------------------------
+    def _p2p_release(self):
+        st = self._p2p
+        self._p2p = None
+        if not st:
+            return
+        torch.cuda.synchronize()
+        if dist.is_initialized() and self.world > 1:
+            dist.barrier(group=self.group)              # nobody still reads my buffers
+        for p in st["opened"]:
+            self._lib.modgpuPeerClose(C.c_void_p(p))
+        for p in st["mine"]:
+            self._lib.modgpuPeerFree(C.c_void_p(p))
+
+    def reserve(self, max_bases_per_batch):
+        """COLLECTIVE: size and map the peer buckets for batches of up to max_bases_per_batch bases per rank.
+        Called implicitly by the first add; call it again (on every rank) before feeding larger batches -
+        a batch larger than reserved still works, its surplus travels in the overflow segments."""
+        import math
+        lib, G = self._lib, self.world
+        R = int(lib.modgpuModsetRegions(self.local._p))
+        t = torch.tensor([int(max_bases_per_batch)], dtype=torch.int64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        nb = int(t.item())
+        expected = nb // max(self.w, 1) + 1
+        mean = expected / float(G * R)
+        cap = (int(1.1 * mean + 4.0 * math.sqrt(mean) + 8) + 1) & ~1
+        ovf_cap = max(65536, expected // 4)
+        self._p2p_release()
+        mine, opened, ok = [], [], 1
+        sb, so = [], []
+        for b in range(2):                               # double buffered: one barrier per batch suffices
+            p1 = lib.modgpuPeerAlloc(G * R * cap * 8)
+            p2 = lib.modgpuPeerAlloc(G * ovf_cap * 8)
+            if not p1 or not p2:
+                ok = 0
+            sb.append(p1 or 0); so.append(p2 or 0)
+            mine += [x for x in (p1, p2) if x]
+        handles = []
+        for ptr in sb + so:
+            h = (C.c_ubyte * 64)()
+            if not ptr or lib.modgpuPeerExport(C.c_void_p(ptr), h) != 0:
+                ok = 0
+            handles.append(bytes(h))
+        allh = [None] * G
+        dist.all_gather_object(allh, (ok, handles), group=self.group)
+        ok = min(x[0] for x in allh)
+        # peer pointers, already offset to THIS owner's part of every source's arrays
+        bptr = [(C.c_void_p * G)() for _ in range(2)]
+        optr = [(C.c_void_p * G)() for _ in range(2)]
+        if ok:
+            for s_rank in range(G):
+                ptrs = []
+                for i, hb in enumerate(allh[s_rank][1]):
+                    if s_rank == self.rank:
+                        ptrs.append((sb + so)[i])
+                    else:
+                        q = lib.modgpuPeerOpen(hb)
+                        if not q:
+                            ok = 0
+                            q = 0
+                        else:
+                            opened.append(q)
+                        ptrs.append(q)
+                for b in range(2):
+                    bptr[b][s_rank] = ptrs[b] + self.rank * R * cap * 8
+                    optr[b][s_rank] = ptrs[2 + b] + self.rank * ovf_cap * 8
+        t = torch.tensor([ok], dtype=torch.int64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        self._p2p = {"mine": mine, "opened": opened}
+        if not int(t.item()):                            # some rank could not map a peer: everybody uses NCCL
+            self._p2p_release()
+            self.fused_mode = "peer"
+            return False
+        self._p2p.update(cap=cap, ovf_cap=ovf_cap, R=R, sb=sb, so=so, bptr=bptr, optr=optr, batch=0,
+                         sc=torch.zeros(G * R, dtype=torch.int32, device=self.dev),
+                         rc=torch.zeros(G * R, dtype=torch.int32, device=self.dev),
+                         soc=torch.zeros(G, dtype=torch.int32, device=self.dev),
+                         roc=torch.zeros(G, dtype=torch.int32, device=self.dev),
+                         cnt=torch.zeros(1, dtype=torch.int64, device=self.dev))
+        return True
+
+    def _p2p_add(self, select, nbases):
+        """select(sb, cap, sc, so, ovf_cap, soc, cnt) launches this rank's hash/select into bucket set `sb`"""
+        if self._p2p is None and not self.reserve(nbases):
+            return False
+        st, g, G = self._p2p, self.group, self.world
+        b = st["batch"] & 1
+        st["batch"] += 1
+        select(st["sb"][b], st["cap"], st["sc"], st["so"][b], st["ovf_cap"], st["soc"], st["cnt"])
+        # fill counts to the owners; completing these two small collectives also means every rank's select is done
+        dist.all_to_all_single(st["rc"], st["sc"], group=g)
+        dist.all_to_all_single(st["roc"], st["soc"], group=g)
+        check(self._lib.modgpuModsetBuildFromPeers(self.local._p, st["bptr"][b], C.c_void_p(st["rc"].data_ptr()), st["cap"], G,
+                                                   st["optr"][b], st["ovf_cap"], C.c_void_p(st["roc"].data_ptr())), "buildFromPeers")
+        self._sel_acc += st["cnt"]
+        self._ovf_acc = torch.maximum(self._ovf_acc, (st["soc"].max() > st["ovf_cap"]).to(torch.int32).reshape(1))
+        return True
 
     def clear(self):
         check(self._lib.modgpuModsetClear(self.local._p), "modsetClear")
@@ -180,6 +284,14 @@ class ShardedModset:
             n = self.local.add_device(d_bases, d_offsets, nseq, nbases, is_ascii)
             self.total_selected += n
             return n
+        if self.fused and self.fused_mode == "p2p":
+            def sel(sb, cap, sc, so, oc, soc, cnt):
+                check(self._lib.modgpuModsetSelectBucketsDevice(self.local._p, C.c_void_p(d_bases), C.c_void_p(d_offsets), nseq, nbases,
+                                                                is_ascii, self.world, C.c_void_p(sb), cap, C.c_void_p(sc.data_ptr()),
+                                                                C.c_void_p(so), oc, C.c_void_p(soc.data_ptr()),
+                                                                C.c_void_p(cnt.data_ptr())), "selectBuckets")
+            if self._p2p_add(sel, nbases):
+                return 0                         # the count comes from synchronize()
         if self.fused and self.fused_mode == "peer":
             self._ensure_peer(nbases)
             check(self._lib.modgpuModsetSelectBucketsDevice(self.local._p, C.c_void_p(d_bases), C.c_void_p(d_offsets), nseq, nbases,
@@ -220,6 +332,14 @@ class ShardedModset:
             return n
         if self.fused and nbases is None:
             nbases = int((C.c_uint64 * (nseq + 1)).from_address(offsets_ptr)[nseq])
+        if self.fused and self.fused_mode == "p2p":
+            def sel(sb, cap, sc, so, oc, soc, cnt):
+                check(self._lib.modgpuModsetSelectBucketsHost(self.local._p, C.c_void_p(host_ptr), C.c_void_p(offsets_ptr), nseq,
+                                                              is_ascii, self.world, C.c_void_p(sb), cap, C.c_void_p(sc.data_ptr()),
+                                                              C.c_void_p(so), oc, C.c_void_p(soc.data_ptr()),
+                                                              C.c_void_p(cnt.data_ptr())), "selectBuckets")
+            if self._p2p_add(sel, nbases):
+                return 0
         if self.fused and self.fused_mode == "peer":
             self._ensure_peer(nbases)
             check(self._lib.modgpuModsetSelectBucketsHost(self.local._p, C.c_void_p(host_ptr), C.c_void_p(offsets_ptr), nseq,

@@ -77,7 +77,7 @@ def test_sizes_and_owner_are_host_callable():
     lib = mg.load()
     assert lib.modgpuPackedWords(0) == 256 + 8
     assert lib.modgpuPackedWords(8192) == 256 + 8 and lib.modgpuPackedWords(8193) == 512 + 8
-    assert lib.modgpuHashSelectWorkspace(8192 * 3) == 64 + 3 * 8
+    assert lib.modgpuHashSelectWorkspace(8192 * 3) == 64 + 16384 + 3 * 8       # ticket, candidate table, descriptors
     import hostemul as he
     rng = np.random.default_rng(4)
     for v in rng.integers(0, 2**62, 200, dtype=np.uint64):

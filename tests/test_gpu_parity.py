@@ -686,6 +686,10 @@ def _sharded_worker(rank, world, port, tmpdir):
     sm.add_device(d_b.data_ptr(), d_o.data_ptr(), per, len(data))        # device path, same data again
     n2 = sm.synchronize()
     assert n1 == n2 and n1 > 0
+    p2p = sm.fused_mode == "p2p"                              # peer-memory exchange really in use (CUDA IPC worked)
+    sm.fused_mode = "peer"                                    # the same buckets through an NCCL all-to-all
+    sm.add_device(d_b.data_ptr(), d_o.data_ptr(), per, len(data))
+    assert sm.synchronize() == n1
     sm.fused_mode = "segments"                                # per-owner segments + scatter at the receiver
     sm.add_device(d_b.data_ptr(), d_o.data_ptr(), per, len(data))
     assert sm.synchronize() == n1
@@ -696,13 +700,14 @@ def _sharded_worker(rank, world, port, tmpdir):
     h = sm.histogram()
     gmax = sm.global_max()
     if rank == 0:
-        np.savez(os.path.join(tmpdir, "sharded.npz"), v=v, d=d, h=h, gmax=gmax, sel=n1)
+        np.savez(os.path.join(tmpdir, "sharded.npz"), v=v, d=d, h=h, gmax=gmax, sel=n1, p2p=p2p)
     sm.close()
     dist.destroy_process_group()
 
 
 def test_sharded_modset_two_gpus(mg, torch_cuda, orc, tmp_path):
-    """hash-sharded table over 2 GPUs, NCCL all-to-all: union == single-GPU == oracle"""
+    """hash-sharded table over 2 GPUs - peer-memory exchange (region build reading the other rank's buckets over
+    NVLink), NCCL bucket all-to-all, per-owner segments, list exchange: union == single-GPU == oracle"""
     if torch_cuda.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import os
@@ -714,7 +719,8 @@ def test_sharded_modset_two_gpus(mg, torch_cuda, orc, tmp_path):
     data = he.reads(sp, 0, 600)
     offs = np.arange(601, dtype=np.uint64) * np.uint64(5000)
     oms = orc.modset_new(22, 19, 31, 17)
-    for _ in range(4):                                        # every rank added its chunk four times
+    assert bool(r["p2p"]), "the peer-memory exchange fell back to NCCL"
+    for _ in range(5):                                        # every rank added its chunk five times
         orc.modset_add(oms, data, offs)
     ov, od, _ = orc.modset_sorted(oms)
     assert np.array_equal(r["v"], ov) and np.array_equal(r["d"], od)
