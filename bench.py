@@ -3,8 +3,9 @@
 
 Workload (config.workload): BASELINE configs[1] - synthetic 3.1 Gb genome, 24
 records, k=31 d=64, table bits 28: one STEP = one modset build + count over the
-whole genome from an empty table (clear -> K1 pack2bit -> K2 hash/select ->
-K3 insert/count -> entries readback).
+whole genome from an empty table: clear -> hash_count_kernel (K1 pack2bit fused
+into the tile loader + K2 hash/select + the bucket scatter of K3) -> region build
+(K3 insert/count in shared memory) -> entries readback.
 
   value     whole-job Gbases/s with the bases already resident in HBM
   e2e       the same through the reference-facing C-ABI call on HOST buffers
@@ -17,8 +18,10 @@ K3 insert/count -> entries readback).
             oracle port) on a bounded sample of the same genome, 1 core
 
 N > 1 (torchrun, one rank per GPU): weak scaling - every rank builds from its own
-3.1 Gb shard, selected k-mers are exchanged to their owner GPU with one NCCL
-all-to-all per batch, the table is sharded by k-mer hash.
+3.1 Gb shard, the table is sharded by k-mer hash, and the selected k-mers reach
+their owner GPU through peer memory: they are scattered into per-(owner, region)
+buckets in the selecting rank's HBM and the owner's region build reads them over
+NVLink (two small NCCL all-to-alls carry the fill counts and act as the barrier).
 
 --impl reference: the reference's CPU implementation of the same path on the
 host cores (all threads it can use: independent modsets on disjoint chunks, the
@@ -197,7 +200,8 @@ def workload_config(args, per_gpu_bases):
     return {"workload": "modset build+count, synthetic genome, k=%d d=%d seed=%d tableBits=%d (BASELINE configs[1])" % (K, D, HSEED, args.bits),
             "bases_per_gpu": int(per_gpu_bases), "records_per_gpu": args.records,
             "l2": "inputs (%.1f GB codes per step) larger than the 126 MB L2" % (per_gpu_bases / 1e9),
-            "parallelism": "table sharded by k-mer hash, reads by input chunk, 1 all-to-all per batch" if args.gpus > 1 else "single GPU"}
+            "parallelism": ("table sharded by k-mer hash, reads by input chunk; peer-memory exchange: the owner's region build "
+                            "reads every rank's buckets over NVLink, NCCL only for the fill counts") if args.gpus > 1 else "single GPU"}
 
 
 # ------------------------------------------------------------------ our arm --
@@ -289,28 +293,36 @@ def run_ours(args):
     sm.local.profile(False)
     peak, peak_src = measured_peak()
     n_ins = hashes                                          # inserts this rank issued per step (world 1)
-    alg = {"pack": nb * 1.25, "select": nb * (0.25 + 8.0 / D), "insert": n_ins * 20.0}
+    # algorithmic bytes: K1 is fused into K2's tile loader, so the select pass reads the raw bytes
+    # (1 B/base) and writes the selected k-mers (8/d B/base): 1 + 8/d; the "pack" scope only holds the end-flag
+    # marking (1 bit per base written); insert = 20 B per selected k-mer
+    alg = {"pack": nb * 0.125, "select": nb * (1.0 + 8.0 / D), "insert": n_ins * 20.0}
     kern = {}
     for name in ("pack", "select", "insert"):
         ms_k = times[name][0] / prof_steps
         kern[name] = {"ms_per_step": ms_k, "alg_bytes_per_step": alg[name],
                       "achieved_gbs": (alg[name] / (ms_k * 1e-3) / 1e9) if ms_k > 0 else None}
+    kern["pack"]["what"] = "mark_ends_kernel + memset of the flag words (K1 itself runs inside the select kernel)"
+    kern["select"]["what"] = "lut_build_kernel + hash_count_kernel: fused K1 pack2bit + K2 hash/select + K3 bucket scatter"
+    kern["insert"]["what"] = "region build in shared memory (+ overflow inserts)" + (", reading peer buckets over NVLink" if world > 1 else "")
     dom = max(("pack", "select", "insert"), key=lambda n: kern[n]["ms_per_step"])
     launches_per_step = sum(times[n][1] for n in times) // prof_steps
     traffic = None
+    kname = {"pack": "mark_ends_kernel", "select": "hash_count_kernel",
+             "insert": "region_build_pipe_kernel" if world > 1 else "region_build_kernel"}
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
-        key = {"pack": "pack2bit_kernel", "select": "hash_select_kernel", "insert": "region_build_kernel"}[dom]
-        if abs(nb - 3.1e9) < 1e8 and world == 1:
-            traffic = tr.get(key)           # dram bytes per launch from the committed ncu --set full capture of this config
+        if abs(nb - 3.1e9) < 1e8 and world == 1 and args.flags == 0:
+            traffic = tr.get(kname[dom])    # dram bytes per launch from the committed ncu --set full capture of this config
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": {"pack": "pack2bit_kernel", "select": "hash_select_kernel", "insert": "table_insert_kernel"}[dom],
+    roofline = {"bound": "hbm", "kernel": kname[dom],
                 "achieved": kern[dom]["achieved_gbs"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": (kern[dom]["achieved_gbs"] / peak) if kern[dom]["achieved_gbs"] else None,
                 "traffic": traffic, "kernels": kern,
-                "note": "hash_select is integer-ALU bound (ncu: ALU pipe 84 %, issue 83 %, DRAM 12 %), not HBM bound; "
-                        "insert = fused bucket scatter + shared-memory region build; see DESIGN.md section 3 and profiles/"}
+                "note": "hash_count_kernel (fused pack + hash/select + scatter) is bound by instruction issue and the shared-memory "
+                        "pipe, not by HBM (ncu r01 v5: issue 67 %, ALU pipe 61 %, shared-memory wavefronts ~60 %, DRAM 29 %); "
+                        "1 + 8/d algorithmic bytes per base; see DESIGN.md section 3 and profiles/"}
 
     # ---- e2e: host buffers through the C ABI, H2D inside the timed region
     e2e = None

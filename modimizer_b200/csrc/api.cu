@@ -141,7 +141,7 @@ int mg_modset_select_chunk(ModgpuModset *ms, const uint8_t *d_bases, const uint6
   for (int attempt = 0; attempt < 2; ++attempt)
     { if ((rc = ms->kmers.ensure(cap * 8))) return rc;
       if (wantPos && (rc = ms->gpos.ensure(cap * 4))) return rc;
-      { ProfScope p(ms, MODGPU_T_SELECT, 1);
+      { ProfScope p(ms, MODGPU_T_SELECT, mg_select_launches(&ms->hasher, ms->selFlags | (ms->exactOrder ? MODGPU_SEL_ORDERED : 0)));
         if ((rc = modgpuHashSelect(&ms->hasher, (const uint64_t *)ms->packed.p, (const uint32_t *)ms->ends.p, nBases,
                                    (uint64_t *)ms->kmers.p, wantPos ? (uint32_t *)ms->gpos.p : nullptr, cap, dCount,
                                    ms->work.p, flags, st)))
@@ -209,7 +209,7 @@ static int add_chunk_fused(ModgpuModset *ms, const uint8_t *d_bases, const uint6
   if ((rc = mg_table_bulk_begin(ms->table, expected, 2 * expected + 65536, &b, st))) return rc;
   uint64_t *dCount = (uint64_t *)ms->misc.p;
   volatile uint64_t *hCount = (volatile uint64_t *)ms->hMisc.p;
-  { ProfScope p(ms, MODGPU_T_SELECT, 1);
+  { ProfScope p(ms, MODGPU_T_SELECT, mg_select_launches(&ms->hasher, ms->selFlags | (ms->exactOrder ? MODGPU_SEL_ORDERED : 0)));
     if ((rc = mg_hash_select_scatter(&ms->hasher, (const uint64_t *)ms->packed.p, (const uint32_t *)ms->ends.p, nBases, dCount,
                                      ms->work.p, ms->selFlags, b.slotBits, b.regionBits, b.cap, b.cursors, b.buckets,
                                      b.overflow, b.overflowCap, fusePack ? d_bases : nullptr, isAscii, st)))
@@ -416,7 +416,7 @@ extern "C" int modgpuModsetSelectOwnersDevice(ModgpuModset *ms, const uint8_t *d
     if ((rc = modgpuPack2bit(d_bases, nBases, isAscii, (uint64_t *)ms->packed.p, st))) return rc;
     if ((rc = modgpuMarkEnds(d_offs, nSeq, nBases, (uint32_t *)ms->ends.p, st))) return rc;
   }
-  ProfScope p(ms, MODGPU_T_SELECT, 1);
+  ProfScope p(ms, MODGPU_T_SELECT, mg_select_launches(&ms->hasher, ms->selFlags | (ms->exactOrder ? MODGPU_SEL_ORDERED : 0)));
   return mg_hash_select_owners(&ms->hasher, (const uint64_t *)ms->packed.p, (const uint32_t *)ms->ends.p, nBases, ms->work.p,
                                ms->selFlags, nOwners, d_counts, d_segments, segCap, st);
 }
@@ -458,7 +458,7 @@ extern "C" int modgpuModsetSelectBucketsDevice(ModgpuModset *ms, const uint8_t *
     if (!fusePack && (rc = modgpuPack2bit(d_bases, nBases, isAscii, (uint64_t *)ms->packed.p, st))) return rc;
     if ((rc = modgpuMarkEnds(d_offs, nSeq, nBases, (uint32_t *)ms->ends.p, st))) return rc;
   }
-  ProfScope p(ms, MODGPU_T_SELECT, 1);
+  ProfScope p(ms, MODGPU_T_SELECT, mg_select_launches(&ms->hasher, ms->selFlags | (ms->exactOrder ? MODGPU_SEL_ORDERED : 0)));
   return mg_hash_select_peer(&ms->hasher, (const uint64_t *)ms->packed.p, (const uint32_t *)ms->ends.p, nBases, d_count, ms->work.p,
                              ms->selFlags, mg_table_slot_bits(ms->table), 11, nOwners, bucketCap, d_cursors, d_buckets,
                              d_overflow, overflowCap, d_ovfCounts, fusePack ? d_bases : nullptr, isAscii, st);

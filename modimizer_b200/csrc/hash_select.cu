@@ -320,6 +320,7 @@ __global__ void __launch_bounds__(MG_SEL_THREADS) hash_select_ordered_kernel(con
 // RAW: the batch as bytes (codes or ASCII, 16-byte aligned) instead of the packed stream
 #define MG_CNT_WARPS 16
 #define MG_CNT_THREADS (MG_CNT_WARPS * 32)
+#define MG_CNT_CHUNK 4                                          // warp tiles per scheduling chunk (power of two)
 #define MG_WT_RUNS 64                                          // runs per warp tile
 #define MG_WT_BASES (MG_WT_RUNS * MG_RUN)                      // 2048
 #define MG_WQ_CAP 256                                          // queue entries per warp (of its 2048 windows)
@@ -391,8 +392,13 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, LUTK ? 3 : 2) hash_count_kerne
   const MgKHasher &H = P.H;
   const uint32_t tid = threadIdx.x;
   const uint32_t lane = tid & 31;
-  const uint64_t nWarps = (uint64_t)gridDim.x * MG_CNT_WARPS;
-  uint64_t tile = (uint64_t)blockIdx.x * MG_CNT_WARPS + (tid >> 5);
+  // tile schedule: chunks of MG_CNT_CHUNK consecutive warp tiles; a warp's first chunk is its global index, the
+  // following ones come from an atomic ticket requested a whole chunk ahead (its latency never shows), so that
+  // warps on faster SMs take more of the work (a static split left 20 % of the warp slots idle at the tail)
+  const uint32_t nWarps = gridDim.x * MG_CNT_WARPS;
+  uint64_t tile = (uint64_t)(blockIdx.x * MG_CNT_WARPS + (tid >> 5)) * MG_CNT_CHUNK, tileNext = 0;
+  uint32_t pendingChunk = 0;
+  if (lane == 0) pendingChunk = nWarps + atomicAdd(P.ticket, 1u);
   // a tile can be bulk-copied when all of it (and the overlap) lies inside the batch; the packed
   // stream and the flags carry slack words past the end, the raw bytes do not
   const uint64_t nBulk = RAW ? (P.nBases >= MG_WS_RAW_BYTES ? (P.nBases - MG_WS_RAW_BYTES) / MG_WT_BASES + 1 : 0) : P.nTiles;
@@ -412,7 +418,7 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, LUTK ? 3 : 2) hash_count_kerne
     }
   __syncthreads();
 
-  for (; tile < P.nTiles; tile += nWarps)
+  for (; tile < P.nTiles; tile = tileNext)
     { // ---- this lane's two runs: words 2l, 2l+1 (+ overlap word 2l+2), 96 end flags
       const uint32_t run0 = lane * MG_SEL_RPT;
       const uint64_t tileBase = tile * MG_WT_BASES;
@@ -424,10 +430,17 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, LUTK ? 3 : 2) hash_count_kerne
           e0 = S->ends[run0]; e1 = S->ends[run0 + 1]; e2 = S->ends[run0 + 2];
           uint64_t wx = 0;                                  // the overlap word, from lanes 0 and 1
           if (RAW)
-            { const uint4 *src = reinterpret_cast<const uint4 *>(S->stage) + lane * 4;
-              const uint4 q0 = src[0], q1 = src[1], q2 = src[2], q3 = src[3];
-              w0 = ((uint64_t)pack16_dev<ASCII>(q0) << 32) | pack16_dev<ASCII>(q1);
-              w1 = ((uint64_t)pack16_dev<ASCII>(q2) << 32) | pack16_dev<ASCII>(q3);
+            { // a lane's 64 bytes are four 16-byte chunks at a 64-byte stride: read in lane order they would hit the
+              // same banks four ways.  Lane pairs start at a rotated chunk instead (conflict-free), and the four
+              // packed values are rotated back with two rounds of selects.
+              const uint4 *src = reinterpret_cast<const uint4 *>(S->stage) + lane * 4;
+              const uint32_t rot = (lane >> 1) & 3u;
+              const uint32_t t0 = pack16_dev<ASCII>(src[rot]), t1 = pack16_dev<ASCII>(src[(rot + 1) & 3u]),
+                             t2 = pack16_dev<ASCII>(src[(rot + 2) & 3u]), t3 = pack16_dev<ASCII>(src[(rot + 3) & 3u]);
+              const bool r1 = rot & 1u, r2 = rot & 2u;
+              const uint32_t u0 = r1 ? t3 : t0, u1 = r1 ? t0 : t1, u2 = r1 ? t1 : t2, u3 = r1 ? t2 : t3;
+              w0 = ((uint64_t)(r2 ? u2 : u0) << 32) | (r2 ? u3 : u1);
+              w1 = ((uint64_t)(r2 ? u0 : u2) << 32) | (r2 ? u1 : u3);
               uint32_t x = 0;
               if (lane < 2) x = pack16_dev<ASCII>(reinterpret_cast<const uint4 *>(S->stage)[128 + lane]);
               wx = ((uint64_t)__shfl_sync(0xffffffffu, x, 0) << 32) | __shfl_sync(0xffffffffu, x, 1);
@@ -452,7 +465,12 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, LUTK ? 3 : 2) hash_count_kerne
       __syncwarp();
       // every lane has consumed its part of the staged tile (the stores above depend on it): the buffer is
       // free, and the next tile's copy streams in behind the whole computation of this one
-      if (lane == 0 && tile + nWarps < nBulk) count_issue_tile<RAW>(P, S, tile + nWarps);
+      tileNext = tile + 1;
+      if ((tileNext & (MG_CNT_CHUNK - 1)) == 0)
+        { tileNext = (uint64_t)__shfl_sync(0xffffffffu, pendingChunk, 0) * MG_CNT_CHUNK;
+          if (lane == 0 && tileNext < P.nTiles) pendingChunk = nWarps + atomicAdd(P.ticket, 1u);
+        }
+      if (lane == 0 && tileNext < nBulk) count_issue_tile<RAW>(P, S, tileNext);
       w2 = S->words[run0 + 2];
 
       uint32_t m0, m1;
@@ -651,6 +669,14 @@ extern "C" uint64_t modgpuHashSelectWorkspace(uint64_t nBases)
 
 MgKHasher mg_khasher_from(const ModgpuHasher *h) { return mg_make_khasher(h->k, h->w, h->factor1); }
 
+// count mode with the table-driven prefilter launches lut_build_kernel + hash_count_kernel, everything else one kernel
+int mg_select_launches(const ModgpuHasher *h, int flags)
+{
+  const MgKHasher H = mg_khasher_from(h);
+  const bool lut = H.lut && !(flags & (MODGPU_SEL_ORDERED | MODGPU_SEL_NOPREFILTER | MODGPU_SEL_NOLUT));
+  return lut ? 2 : 1;
+}
+
 template <bool PF, bool TMA>
 static int launch_ordered(const SelectParams &P, cudaStream_t st)
 {
@@ -679,7 +705,7 @@ static int launch_count(const SelectParams &P0, cudaStream_t st)
   SelectParams P = P0;
   P.nTiles = (uint32_t)((P.nBases + MG_WT_BASES - 1) / MG_WT_BASES);         // warp tiles
   uint64_t grid = (uint64_t)mg_num_sms() * blocksPerSm;
-  const uint64_t need = ((uint64_t)P.nTiles + MG_CNT_WARPS - 1) / MG_CNT_WARPS;
+  const uint64_t need = ((uint64_t)P.nTiles + MG_CNT_WARPS * MG_CNT_CHUNK - 1) / (MG_CNT_WARPS * MG_CNT_CHUNK);
   if (grid > need) grid = need;
   if (LUTK)
     { lut_build_kernel<<<MG_LUT_SIZE / 256, 256, 0, st>>>(P.H, const_cast<uint8_t *>(P.lut));

@@ -7,6 +7,7 @@
 #include "mg_device.cuh"
 
 MgKHasher mg_khasher_from(const ModgpuHasher *h);
+int mg_select_launches(const ModgpuHasher *h, int flags);      // kernels one hash/select call launches
 int mg_table_insert_dev(ModgpuTable *t, const uint64_t *d_kmers, const uint64_t *d_n, uint64_t nMax,
                         uint32_t *d_slot, int exactOrder, cudaStream_t st);
 int mg_table_lookup_dev(const ModgpuTable *t, const uint64_t *d_kmers, const uint64_t *d_n, uint64_t nMax,
