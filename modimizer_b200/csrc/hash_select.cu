@@ -373,9 +373,9 @@ template <bool RAW>
 __device__ __forceinline__ void count_issue_tile(const SelectParams &P, CountWarpSmem<RAW> *S, uint64_t tile)
 { // one elected lane: both bulk copies of a tile signal the warp's mbarrier
   mg_mbar_expect_tx(&S->bar, (RAW ? MG_WS_RAW_BYTES : MG_WS_PACK_BYTES) + MG_WS_ENDS_BYTES);
-  if (RAW) mg_tma_load_1d(S->stage, P.raw + tile * MG_WT_BASES, MG_WS_RAW_BYTES, &S->bar);
-  else mg_tma_load_1d(S->stage, P.packed + tile * MG_WT_RUNS, MG_WS_PACK_BYTES, &S->bar);
-  mg_tma_load_1d(S->ends, P.ends + tile * MG_WT_RUNS, MG_WS_ENDS_BYTES, &S->bar);
+  if (RAW) mg_tma_load_1d_hint(S->stage, P.raw + tile * MG_WT_BASES, MG_WS_RAW_BYTES, &S->bar, MG_L2_EVICT_FIRST);
+  else mg_tma_load_1d_hint(S->stage, P.packed + tile * MG_WT_RUNS, MG_WS_PACK_BYTES, &S->bar, MG_L2_EVICT_FIRST);
+  mg_tma_load_1d_hint(S->ends, P.ends + tile * MG_WT_RUNS, MG_WS_ENDS_BYTES, &S->bar, MG_L2_EVICT_FIRST);
 }
 
 template <bool PREFILTER, bool RAW, int OUT, bool ASCII, int LUTK>
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, LUTK ? 3 : 2) hash_count_kerne
 #pragma unroll
               for (int r = 0; r < MG_SEL_ROUNDS; ++r)
                 if ((okMask >> r) & 1u)
-                  { if (pos[r] < P.bucketCap) P.buckets[(uint64_t)region[r] * P.bucketCap + pos[r]] = km[r];
+                  { if (pos[r] < P.bucketCap) mg_st_keep(P.buckets + (uint64_t)region[r] * P.bucketCap + pos[r], km[r]);
                     else if (PEER)
                       { const uint32_t ow = region[r] / P.nRegions;
                         const uint32_t o = atomicAdd(&P.ownerCursor[ow], 1u);
@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, LUTK ? 3 : 2) hash_count_kerne
                       const uint32_t ow = PEER ? mg_owner(km, P.nOwners) : 0u;
                       if (PEER) region += ow * P.nRegions;
                       const uint32_t pos = atomicAdd(&P.cursors[region], 1u);
-                      if (pos < P.bucketCap) P.buckets[(uint64_t)region * P.bucketCap + pos] = km;
+                      if (pos < P.bucketCap) mg_st_keep(P.buckets + (uint64_t)region * P.bucketCap + pos, km);
                       else if (PEER)
                         { const uint32_t o = atomicAdd(&P.ownerCursor[ow], 1u);
                           if (o < P.overflowCap) P.overflow[(uint64_t)ow * P.overflowCap + o] = km;

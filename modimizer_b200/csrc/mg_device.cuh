@@ -167,4 +167,25 @@ __device__ __forceinline__ void mg_tma_load_1d(void *dst, const void *src, uint3
       : "memory");
 }
 
+// L2 eviction-priority policies (the createpolicy.fractional encodings CUTLASS ships as TMA::CacheHintSm90)
+#define MG_L2_EVICT_FIRST 0x12F0000000000000ull
+#define MG_L2_EVICT_LAST  0x14F0000000000000ull
+
+// the same bulk copy with an L2 cache hint: streaming input is marked evict-first so that it does not push
+// the half-filled tail sectors of the output buckets out of L2
+__device__ __forceinline__ void mg_tma_load_1d_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy)
+{
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(mg_smem_addr(dst)),
+      "l"(src), "r"(bytes), "r"(mg_smem_addr(bar)), "l"(policy)
+      : "memory");
+}
+
+// 8-byte store that asks L2 to keep the line (bucket tails are written 8 bytes at a time: a sector evicted
+// before its four k-mers arrived costs DRAM a read-modify-write)
+__device__ __forceinline__ void mg_st_keep(uint64_t *p, uint64_t v)
+{
+  asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(MG_L2_EVICT_LAST) : "memory");
+}
+
 #endif  // __CUDACC__
