@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(256) region_build_multi_kernel(MgSlot *slots, 
         { const unsigned long long key = b[j] & 0x3FFFFFFFFFFFFFFFull;
           uint32_t s = (uint32_t)mg_slot_hash(key, slotBits) & (MG_REGION_SLOTS - 1);
           uint32_t probes = 0;
+#pragma unroll 1
           for (; probes < MG_REGION_SLOTS; ++probes, s = (s + 1) & (MG_REGION_SLOTS - 1))
             { unsigned long long *kp = reinterpret_cast<unsigned long long *>(&sS[s].key);
               unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(kp);
@@ -260,8 +261,15 @@ __global__ void __launch_bounds__(256, 5) region_build_pipe_kernel(MgSlot *slots
   auto insert = [&](unsigned long long key) {
     uint32_t sl = (uint32_t)mg_slot_hash(key, slotBits) & (MG_REGION_SLOTS - 1);
     uint32_t probes = 0;
+#pragma unroll 1
     for (; probes < MG_REGION_SLOTS; ++probes, sl = (sl + 1) & (MG_REGION_SLOTS - 1))
       { unsigned long long *kp = reinterpret_cast<unsigned long long *>(&sS[sl].key);
+        if (FRESH)
+          { const unsigned long long old = atomicCAS(kp, MG_EMPTY, key);     // see region_build_kernel
+            if (old == MG_EMPTY) { ++fresh; break; }
+            if (old == key) break;
+            continue;
+          }
         unsigned long long cu = *reinterpret_cast<volatile unsigned long long *>(kp);
         if (cu == key) break;
         if (cu == MG_EMPTY)
@@ -387,8 +395,18 @@ __global__ void __launch_bounds__(256) region_build_kernel(MgSlot *slots, uint32
       else key = b[j];
       uint32_t s = (uint32_t)mg_slot_hash(key, slotBits) & (MG_REGION_SLOTS - 1);
       uint32_t probes = 0;
+#pragma unroll 1
       for (; probes < MG_REGION_SLOTS; ++probes, s = (s + 1) & (MG_REGION_SLOTS - 1))
         { unsigned long long *kp = reinterpret_cast<unsigned long long *>(&sS[s].key);
+          if (FRESH)
+            { // a region that starts empty: the slot is probably free, claim it without reading it first (one
+              // shared-memory operation instead of two for every new k-mer; measured 0.64 -> 0.58 ms on the
+              // genome build, +3 % on a 30x readset where most k-mers repeat)
+              const unsigned long long old = atomicCAS(kp, MG_EMPTY, key);
+              if (old == MG_EMPTY) { ++fresh; break; }
+              if (old == key) break;
+              continue;
+            }
           unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(kp);
           if (cur == key) break;
           if (cur == MG_EMPTY)

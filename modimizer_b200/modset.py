@@ -283,6 +283,10 @@ class Modset:
             for j in range(len(v)):
                 f.write("%d\t%s\t%d\t%d\n" % (j + 1, kmer_string(v[j], self.k), d[j], i[j]))
 
+    def clear(self):
+        """empty the set (the table is rewritten lazily by the next bulk build)"""
+        check(self._lib.modgpuModsetClear(self._p), "modsetClear")
+
     # ---- profiling -------------------------------------------------------
     def profile(self, on=True):
         check(self._lib.modgpuModsetProfile(self._p, 1 if on else 0), "profile")
