@@ -314,6 +314,38 @@ def test_insert_paths_agree(mg, orc, mode):
         ms.close(); orc._modset_free(oms)
 
 
+@pytest.mark.parametrize("k,d", [(31, 64), (30, 16), (31, 8)])
+def test_fused_pass_table_scan_ascii_and_ragged(mg, torch_cuda, orc, k, d):
+    """the bench path end to end - raw bytes -> fused K1 + table-driven K2 + bucket scatter -> region build - on
+    ASCII text (mixed case, N) and on codes, ragged batches whose last warp tile is partial, device pointers that
+    are and are not 16-byte aligned (the unaligned one takes the separate pack kernel + packed-stream loader)"""
+    rng = np.random.default_rng(k * 100 + d)
+    lens = np.concatenate([rng.integers(1, 9000, 150), [0, k - 1, k, k + 1, 2047, 2048, 2049, 2080, 4096 + 31]])
+    rng.shuffle(lens)
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    codes = rng.integers(0, 4, int(offs[-1])).astype(np.uint8)
+    asc = np.frombuffer(b"ACGT", np.uint8)[codes].copy()
+    asc[::5] |= 0x20
+    asc[7000:7300] = ord("n"); codes[7000:7300] = 0
+    oms = orc.modset_new(22, k, d, 17)
+    otot = orc.modset_add(oms, codes, offs)
+    ov, od, _ = orc.modset_sorted(oms)
+    dev = torch_cuda.device("cuda:0")
+    d_offs = torch_cuda.from_numpy(offs.view(np.int64)).to(dev)
+    try:
+        for (buf, is_ascii) in ((codes, 0), (asc, 1)):
+            for shift in (0, 16, 5):                      # device pointer alignment
+                ms = mg.Modset(22, k, d, 17)
+                ms.set_flags(255 << 8)                    # force the bulk (fused) insert path at this small size
+                d_b = torch_cuda.from_numpy(np.concatenate([np.zeros(shift, np.uint8), buf, np.zeros(64, np.uint8)])).to(dev)
+                assert ms.add_device(d_b.data_ptr() + shift, d_offs.data_ptr(), len(lens), len(buf), is_ascii) == otot
+                gv, gd, _ = ms.sorted_dump()
+                assert np.array_equal(gv, ov) and np.array_equal(gd, od), (is_ascii, shift)
+                ms.close()
+    finally:
+        orc._modset_free(oms)
+
+
 def test_modset_edge_cases(mg, orc):
     rng = np.random.default_rng(3)
     # empty batch, empty reads, len<k, len==k, palindromes, d = 1 (every k-mer), k = 1
