@@ -83,6 +83,17 @@ __device__ __forceinline__ bool eval_entry(const MgKHasher &H, const uint64_t *s
   return mg_eval_single(H, sWords[src], sWords[src + 1], bit, km, isF);
 }
 
+// LUTK != 0: k = LUTK at compile time; when d is also a power of two (kernel-uniform) the specialised
+// evaluation applies (constant shifts, masked-product comparison, no odd-part test)
+template <int LUTK>
+__device__ __forceinline__ bool eval_entry_k(const MgKHasher &H, const uint64_t *sWords, uint32_t e,
+                                             uint64_t *km, bool *isF)
+{
+  const uint32_t src = e >> 5, bit = e & 31u;
+  if (LUTK != 0 && H.oddInv == 1) return mg_eval_single_pow2<LUTK ? LUTK : 31>(H, sWords[src], sWords[src + 1], bit, km, isF);
+  return mg_eval_single(H, sWords[src], sWords[src + 1], bit, km, isF);
+}
+
 // One tile (256 runs = 8192 window starts) in three phases, by 128 threads
 // owning two consecutive runs each (halves the per-run bookkeeping):
 //  1. every thread scans its runs into bit masks: with the PREFILTER the
@@ -517,7 +528,7 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, LUTK ? 3 : 2) hash_count_kerne
               if (q < nW)
                 { bool isF;
                   ent[r] = wq[q];
-                  if (eval_entry(H, sWords, ent[r], &km[r], &isF)) { okMask |= 1u << r; if (isF) fMask |= 1u << r; }
+                  if (eval_entry_k<LUTK>(H, sWords, ent[r], &km[r], &isF)) { okMask |= 1u << r; if (isF) fMask |= 1u << r; }
                 }
             }
           if (OWNERS)
@@ -608,7 +619,7 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, LUTK ? 3 : 2) hash_count_kerne
                   if (own0) { uint32_t i = __ffs(own0) - 1; own0 &= own0 - 1; e = (run0 << 5) | i; }
                   else if (own1) { uint32_t i = __ffs(own1) - 1; own1 &= own1 - 1; e = ((run0 + 1) << 5) | i; }
                 }
-              if (have) ok = eval_entry(H, sWords, e, &km, &isF);
+              if (have) ok = eval_entry_k<LUTK>(H, sWords, e, &km, &isF);
               const uint32_t ballot = __ballot_sync(0xffffffffu, ok);
               if (!ballot) continue;
               if (OWNERS)

@@ -197,6 +197,26 @@ MGHD bool mg_eval_single(const MgKHasher &H, uint64_t w0, uint64_t w1, uint32_t 
   return lowOk && oddOk;
 }
 
+// The same for the table-driven scan's parameter range (K = 30 or 31 known at compile time, d a power of two
+// with 64-2K+tz <= 8): the shifts are constants, the two hashes are compared as masked products (h = P >> S is
+// monotone in P & ~(2^S - 1)), "hash % d == 0" is one AND on the low product word, and no odd-part test is needed.
+template <int K>
+MGHD bool mg_eval_single_pow2(const MgKHasher &H, uint64_t w0, uint64_t w1, uint32_t i, uint64_t *kmer, bool *isF)
+{
+  constexpr uint32_t S = 64 - 2 * K;
+  constexpr uint64_t MASK = (((uint64_t)1) << (2 * K)) - 1;
+  const uint32_t sl = 2 * i;                                   // the window starts 2i bits below the top of w0:w1
+  const uint64_t top = sl ? ((w0 << sl) | (w1 >> (64 - sl))) : w0;
+  const uint64_t f = (top >> S) & MASK;
+  const uint64_t r = (~mg_pairrev64(f)) >> S;
+  const uint64_t pf = (f * H.factor) & ~(uint64_t)((1u << S) - 1u), pr = (r * H.factor) & ~(uint64_t)((1u << S) - 1u);
+  const bool fw = pf < pr;                                     // hashF < hashR (ties go reverse, seqhash.c:66-67)
+  const uint64_t pm = fw ? pf : pr;
+  *kmer = fw ? f : r;
+  *isF = fw;
+  return ((uint32_t)pm & (((1u << H.tz) - 1u) << S)) == 0u;    // the tz low hash bits are zero
+}
+
 // power-of-two prefilter (H.prefilter): a window can only be selected if the tz
 // low bits of hash(fwd) or of hash(rc) are zero, and with 64-2k+tz <= 32 those
 // bits live in the LOW 32-bit word of the product, which depends only on the low

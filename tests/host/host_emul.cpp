@@ -112,6 +112,16 @@ int64_t hm_lut_check(int k, int d, uint64_t factor1, const uint8_t *bytes, uint6
         }
       if (lo != c[0]) ++bad;
       if (hi != c[1]) ++bad;
+      if (H.oddInv == 1)                                    // d a power of two: the specialised evaluation == the generic one
+        for (int h = 0; h < 2; ++h)
+          for (uint32_t i = 0; i < 32; ++i)
+            if (c[h] >> i & 1)
+              { uint64_t k1, k2; bool f1, f2;
+                bool a = mg_eval_single(H, words[T + h], words[T + h + 1], i, &k1, &f1);
+                bool b = (k == 31) ? mg_eval_single_pow2<31>(H, words[T + h], words[T + h + 1], i, &k2, &f2)
+                                   : mg_eval_single_pow2<30>(H, words[T + h], words[T + h + 1], i, &k2, &f2);
+                if (a != b || k1 != k2 || f1 != f2) ++bad;
+              }
       *nCand += __builtin_popcount(c[0]) + __builtin_popcount(c[1]);
     }
   return bad;
