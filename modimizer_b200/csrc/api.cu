@@ -112,6 +112,27 @@ extern "C" int modgpuModsetTimes(ModgpuModset *ms, double ms_out[MODGPU_T_N], ui
   return MODGPU_OK;
 }
 
+// End flags with a clean-buffer invariant: between batches ms->ends is all zero, so a batch only pays for its own
+// nSeq flags - set before the select, cleared right after it - instead of a 1-bit-per-base memset (0.06 ms per
+// 3.1 Gbases).  Any early return between the two leaves endsCleanCap at 0 and the next batch clears the buffer.
+static int ends_mark(ModgpuModset *ms, const uint64_t *d_offs, uint64_t nSeq, uint64_t nBases, cudaStream_t st)
+{
+  int rc = ms->ends.ensure(modgpuEndsWords(nBases) * 4);
+  if (rc) return rc;
+  if (ms->endsCleanCap != ms->ends.cap) MG_CUDA(cudaMemsetAsync(ms->ends.p, 0, ms->ends.cap, st));
+  ms->endsCleanCap = 0;
+  return mg_ends_sparse(d_offs, nSeq, (uint32_t *)ms->ends.p, 1, st);
+}
+
+static int ends_unmark(ModgpuModset *ms, const uint64_t *d_offs, uint64_t nSeq, cudaStream_t st)
+{
+  ProfScope p(ms, MODGPU_T_PACK, 1);
+  int rc = mg_ends_sparse(d_offs, nSeq, (uint32_t *)ms->ends.p, 0, st);
+  if (rc) return rc;
+  ms->endsCleanCap = ms->ends.cap;
+  return MODGPU_OK;
+}
+
 // ----------------------------------------------------------------- chunks --
 // K1 + K2 over one device-resident chunk; leaves the selected k-mers (and, if
 // wantPos, their global offsets) in ms->kmers / ms->gpos and returns the count.
@@ -130,7 +151,7 @@ int mg_modset_select_chunk(ModgpuModset *ms, const uint8_t *d_bases, const uint6
     return rc;
   { ProfScope p(ms, MODGPU_T_PACK, 2);
     if ((rc = modgpuPack2bit(d_bases, nBases, isAscii, (uint64_t *)ms->packed.p, st))) return rc;
-    if ((rc = modgpuMarkEnds(d_offs, nSeq, nBases, (uint32_t *)ms->ends.p, st))) return rc;
+    if ((rc = ends_mark(ms, d_offs, nSeq, nBases, st))) return rc;
   }
   const uint64_t d = (uint64_t)ms->hasher.w;
   uint64_t cap = (d <= 2) ? nBases : (nBases / d + nBases / (4 * d) + 65536);
@@ -152,6 +173,7 @@ int mg_modset_select_chunk(ModgpuModset *ms, const uint8_t *d_bases, const uint6
       if (*hCount <= cap) break;
       cap = *hCount;                                     // denser than expected: redo with the exact size
     }
+  if ((rc = ends_unmark(ms, d_offs, nSeq, st))) return rc;
   *nSelected = *hCount;
   return MODGPU_OK;
 }
@@ -203,9 +225,10 @@ static int add_chunk_fused(ModgpuModset *ms, const uint8_t *d_bases, const uint6
     return rc;
   { ProfScope p(ms, MODGPU_T_PACK, fusePack ? 1 : 2);
     if (!fusePack && (rc = modgpuPack2bit(d_bases, nBases, isAscii, (uint64_t *)ms->packed.p, st))) return rc;
-    if ((rc = modgpuMarkEnds(d_offs, nSeq, nBases, (uint32_t *)ms->ends.p, st))) return rc;
+    if ((rc = ends_mark(ms, d_offs, nSeq, nBases, st))) return rc;
   }
   MgBulk b;
+  const bool wasPending = mg_table_clear_pending(ms->table);
   if ((rc = mg_table_bulk_begin(ms->table, expected, 2 * expected + 65536, &b, st))) return rc;
   uint64_t *dCount = (uint64_t *)ms->misc.p;
   volatile uint64_t *hCount = (volatile uint64_t *)ms->hMisc.p;
@@ -215,15 +238,21 @@ static int add_chunk_fused(ModgpuModset *ms, const uint8_t *d_bases, const uint6
                                      b.overflow, b.overflowCap, fusePack ? d_bases : nullptr, isAscii, st)))
       return rc;
   }
+  // the build follows without a host round trip: its kernels check on the device that the overflow list was
+  // large enough and leave the table untouched otherwise (skewed batch: the caller falls back to the list path)
+  { ProfScope p(ms, MODGPU_T_INSERT, 2);
+    if ((rc = mg_table_bulk_finish(ms->table, &b, st))) return rc;
+  }
+  if ((rc = ends_unmark(ms, d_offs, nSeq, st))) return rc;
   MG_CUDA(cudaMemcpyAsync((void *)hCount, dCount, 8, cudaMemcpyDeviceToHost, st));
   MG_CUDA(cudaMemcpyAsync((void *)(hCount + 1), mg_table_bulk_overflow_count(ms->table), 4, cudaMemcpyDeviceToHost, st));
   MG_CUDA(cudaStreamSynchronize(st));
   const uint64_t overflowed = hCount[1] & 0xFFFFFFFFull;
-  if (overflowed > b.overflowCap) return 1;              // skewed batch: buckets and overflow list too small
+  if (overflowed > b.overflowCap)                        // buckets and overflow list too small: nothing was applied
+    { mg_table_bulk_abort(ms->table, wasPending);
+      return 1;
+    }
   *nHashes = hCount[0];
-  { ProfScope p(ms, MODGPU_T_INSERT, 2);
-    if ((rc = mg_table_bulk_finish(ms->table, &b, st))) return rc;
-  }
   ms->dirty = true;
   return MODGPU_OK;
 }
@@ -414,11 +443,14 @@ extern "C" int modgpuModsetSelectOwnersDevice(ModgpuModset *ms, const uint8_t *d
     return rc;
   { ProfScope p(ms, MODGPU_T_PACK, 2);
     if ((rc = modgpuPack2bit(d_bases, nBases, isAscii, (uint64_t *)ms->packed.p, st))) return rc;
-    if ((rc = modgpuMarkEnds(d_offs, nSeq, nBases, (uint32_t *)ms->ends.p, st))) return rc;
+    if ((rc = ends_mark(ms, d_offs, nSeq, nBases, st))) return rc;
   }
-  ProfScope p(ms, MODGPU_T_SELECT, mg_select_launches(&ms->hasher, ms->selFlags | (ms->exactOrder ? MODGPU_SEL_ORDERED : 0)));
-  return mg_hash_select_owners(&ms->hasher, (const uint64_t *)ms->packed.p, (const uint32_t *)ms->ends.p, nBases, ms->work.p,
-                               ms->selFlags, nOwners, d_counts, d_segments, segCap, st);
+  { ProfScope p(ms, MODGPU_T_SELECT, mg_select_launches(&ms->hasher, ms->selFlags | (ms->exactOrder ? MODGPU_SEL_ORDERED : 0)));
+    if ((rc = mg_hash_select_owners(&ms->hasher, (const uint64_t *)ms->packed.p, (const uint32_t *)ms->ends.p, nBases, ms->work.p,
+                                    ms->selFlags, nOwners, d_counts, d_segments, segCap, st)))
+      return rc;
+  }
+  return ends_unmark(ms, d_offs, nSeq, st);
 }
 
 extern "C" int modgpuModsetSelectOwnersHost(ModgpuModset *ms, const char *bases, const uint64_t *offs, uint64_t nSeq,
@@ -456,12 +488,15 @@ extern "C" int modgpuModsetSelectBucketsDevice(ModgpuModset *ms, const uint8_t *
     return rc;
   { ProfScope p(ms, MODGPU_T_PACK, fusePack ? 1 : 2);
     if (!fusePack && (rc = modgpuPack2bit(d_bases, nBases, isAscii, (uint64_t *)ms->packed.p, st))) return rc;
-    if ((rc = modgpuMarkEnds(d_offs, nSeq, nBases, (uint32_t *)ms->ends.p, st))) return rc;
+    if ((rc = ends_mark(ms, d_offs, nSeq, nBases, st))) return rc;
   }
-  ProfScope p(ms, MODGPU_T_SELECT, mg_select_launches(&ms->hasher, ms->selFlags | (ms->exactOrder ? MODGPU_SEL_ORDERED : 0)));
-  return mg_hash_select_peer(&ms->hasher, (const uint64_t *)ms->packed.p, (const uint32_t *)ms->ends.p, nBases, d_count, ms->work.p,
-                             ms->selFlags, mg_table_slot_bits(ms->table), 11, nOwners, bucketCap, d_cursors, d_buckets,
-                             d_overflow, overflowCap, d_ovfCounts, fusePack ? d_bases : nullptr, isAscii, st);
+  { ProfScope p(ms, MODGPU_T_SELECT, mg_select_launches(&ms->hasher, ms->selFlags | (ms->exactOrder ? MODGPU_SEL_ORDERED : 0)));
+    if ((rc = mg_hash_select_peer(&ms->hasher, (const uint64_t *)ms->packed.p, (const uint32_t *)ms->ends.p, nBases, d_count, ms->work.p,
+                                  ms->selFlags, mg_table_slot_bits(ms->table), 11, nOwners, bucketCap, d_cursors, d_buckets,
+                                  d_overflow, overflowCap, d_ovfCounts, fusePack ? d_bases : nullptr, isAscii, st)))
+      return rc;
+  }
+  return ends_unmark(ms, d_offs, nSeq, st);
 }
 
 extern "C" int modgpuModsetSelectBucketsHost(ModgpuModset *ms, const char *bases, const uint64_t *offs, uint64_t nSeq,

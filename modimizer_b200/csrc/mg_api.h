@@ -7,6 +7,9 @@
 #include "mg_device.cuh"
 
 MgKHasher mg_khasher_from(const ModgpuHasher *h);
+int mg_ends_sparse(const uint64_t *d_offs, uint64_t nSeq, uint32_t *d_ends, int set, cudaStream_t st);
+bool mg_table_clear_pending(const ModgpuTable *t);
+void mg_table_bulk_abort(ModgpuTable *t, bool wasPending);
 int mg_select_launches(const ModgpuHasher *h, int flags);      // kernels one hash/select call launches
 int mg_table_insert_dev(ModgpuTable *t, const uint64_t *d_kmers, const uint64_t *d_n, uint64_t nMax,
                         uint32_t *d_slot, int exactOrder, cudaStream_t st);
@@ -92,6 +95,7 @@ struct ModgpuModset {
   bool depthIsZero = false;         // modmap-built sets keep ms->depth at 0
   bool dirty = false;               // entries inserted since the last numbering
   DevBuf bases[2], offs[2], packed, ends, kmers, kmers2, gpos, slot, work, misc, expo;
+  size_t endsCleanCap = 0;          // ms->ends is all zero over this capacity (0: unknown / flags of a batch still set)
   int regionBits = -1;              // -1 auto: partition inserts by table region when the table exceeds L2
   PinBuf hOffs[2], hMisc;
   cudaEvent_t evCopied[2] = { nullptr, nullptr }, evFree[2] = { nullptr, nullptr };

@@ -62,6 +62,31 @@ __global__ void __launch_bounds__(256) mark_ends_kernel(const uint64_t *__restri
     }
 }
 
+// the same flags cleared again (every touched word becomes 0: with the clean-buffer invariant of api.cu the
+// whole array is zero again afterwards, without a 1-bit-per-base memset per batch)
+__global__ void __launch_bounds__(256) unmark_ends_kernel(const uint64_t *__restrict__ offs, uint64_t nSeq,
+                                                          uint32_t *__restrict__ ends)
+{
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nSeq; r += stride)
+    { uint64_t a = offs[r], b = offs[r + 1];
+      if (b > a) ends[(b - 1) >> 5] = 0u;
+    }
+}
+
+// set (1) or clear (0) the end flags of nSeq sequences in a buffer that is otherwise all zero
+int mg_ends_sparse(const uint64_t *d_offs, uint64_t nSeq, uint32_t *d_ends, int set, cudaStream_t st)
+{
+  if (!nSeq) return MODGPU_OK;
+  uint64_t blocks = (nSeq + 255) / 256;
+  uint64_t maxBlocks = (uint64_t)mg_num_sms() * 8;
+  if (blocks > maxBlocks) blocks = maxBlocks;
+  if (set) mark_ends_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_offs, nSeq, d_ends);
+  else unmark_ends_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_offs, nSeq, d_ends);
+  MG_LAUNCH_CHECK("mark_ends");
+  return MODGPU_OK;
+}
+
 extern "C" uint64_t modgpuPackedWords(uint64_t nBases)
 {
   uint64_t words = (nBases + 31) / 32;

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) table_clear_kernel(MgSlot *slots, uint64_
 
 // n is read from device memory (the count hash_select just produced) so that no
 // host round trip sits between select and insert; nHost bounds it (the cap).
-template <bool EXACT>
+template <bool EXACT, bool STRICT = false>       // STRICT: a device count beyond the capacity means "incomplete list": do nothing
 __global__ void __launch_bounds__(256) table_insert_kernel(MgSlot *slots, uint32_t slotBits,
                                                            const uint64_t *__restrict__ kmers,
                                                            const unsigned long long *__restrict__ nDev, uint64_t nHost,
@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(256) table_insert_kernel(MgSlot *slots, uint32
                                                            unsigned long long *entries, uint32_t *error)
 {
   uint64_t n = nDev ? (uint64_t)*nDev : nHost;
+  if (STRICT && n > nHost) return;
   if (n > nHost) n = nHost;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   uint32_t fresh = 0;
@@ -360,9 +361,13 @@ __global__ void __launch_bounds__(256, 5) region_build_pipe_kernel(MgSlot *slots
 template <bool FRESH, int PRELOAD>
 __global__ void __launch_bounds__(256) region_build_kernel(MgSlot *slots, uint32_t slotBits, const uint64_t *__restrict__ buckets,
                                                               const uint32_t *__restrict__ cursors, uint32_t cap,
-                                                              unsigned long long *entries, uint32_t *error)
+                                                              unsigned long long *entries, uint32_t *error,
+                                                              const uint32_t *__restrict__ guard, uint32_t guardLimit)
 {
   __shared__ uint4 sR[MG_REGION_SLOTS];
+  // the scatter that filled the buckets ran out of overflow space: the batch is incomplete, touch nothing
+  // (the host learns it from the same counter after the launch and repeats the batch through the list path)
+  if (guard && __ldg(guard) > guardLimit) return;
   const uint32_t region = blockIdx.x;
   uint4 *g = reinterpret_cast<uint4 *>(slots) + (uint64_t)region * MG_REGION_SLOTS;
   uint32_t cnt = cursors[region];
@@ -654,26 +659,9 @@ int mg_table_bulk_finish(ModgpuTable *t, const MgBulk *b, cudaStream_t st)
 {
   static int variant = -1;
   if (variant < 0) { const char *v = getenv("MODGPU_BUILD_VARIANT"); variant = v ? atoi(v) : 0; }
-#define MG_BUILD_LAUNCH(FR, PL) region_build_kernel<FR, PL><<<b->nRegions, 256, 0, st>>>(t->slots, t->slotBits, b->buckets, b->cursors, b->cap, t->dEntries, t->dError)
-  if (variant == 3)
-    { // persistent, software-pipelined build (the kernel of the peer-memory exchange, one local source)
-      static int blocksPerSm = 0;
-      if (!blocksPerSm)
-        { MG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, region_build_pipe_kernel<true, false, 1>, 256, 0));
-          if (blocksPerSm < 1) blocksPerSm = 1;
-        }
-      uint32_t grid = (uint32_t)mg_num_sms() * (uint32_t)blocksPerSm;
-      if (grid > b->nRegions) grid = b->nRegions;
-      MgPeerSrc src;
-      for (uint32_t s2 = 0; s2 < MODGPU_MAX_PEERS; ++s2) src.p[s2] = b->buckets;
-      if (t->clearPending)
-        { region_build_pipe_kernel<true, false, 1><<<grid, 256, 0, st>>>(t->slots, t->slotBits, src, b->cursors, b->cap, 1, b->nRegions, b->nRegions, t->dEntries, t->dError);
-          t->clearPending = false;
-        }
-      else
-        region_build_pipe_kernel<false, false, 1><<<grid, 256, 0, st>>>(t->slots, t->slotBits, src, b->cursors, b->cap, 1, b->nRegions, b->nRegions, t->dEntries, t->dError);
-    }
-  else if (t->clearPending)
+  const uint32_t guardLimit = b->overflowCap > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)b->overflowCap;
+#define MG_BUILD_LAUNCH(FR, PL) region_build_kernel<FR, PL><<<b->nRegions, 256, 0, st>>>(t->slots, t->slotBits, b->buckets, b->cursors, b->cap, t->dEntries, t->dError, b->cursors + b->nRegions, guardLimit)
+  if (t->clearPending)
     { if (variant == 1) MG_BUILD_LAUNCH(true, 4); else if (variant == 2) MG_BUILD_LAUNCH(true, 2); else MG_BUILD_LAUNCH(true, 0);
       t->clearPending = false;
     }
@@ -683,7 +671,7 @@ int mg_table_bulk_finish(ModgpuTable *t, const MgBulk *b, cudaStream_t st)
   MG_LAUNCH_CHECK("region_build");
   // stragglers of over-full buckets go straight into HBM; their number is only known on the device:
   // the insert kernel reads it as the 64-bit word {cursors[nRegions], cursors[nRegions+1] == 0}
-  table_insert_kernel<false><<<grid_for(65536, 4), 256, 0, st>>>(
+  table_insert_kernel<false, true><<<grid_for(65536, 4), 256, 0, st>>>(
       t->slots, t->slotBits, b->overflow, reinterpret_cast<const unsigned long long *>(b->cursors + b->nRegions),
       b->overflowCap, nullptr, t->dEntries, t->dError);
   MG_LAUNCH_CHECK("overflow_insert");
@@ -779,6 +767,10 @@ int mg_table_build_from_peers(ModgpuTable *t, const uint64_t *const *d_buckets, 
     }
   return MODGPU_OK;
 }
+
+bool mg_table_clear_pending(const ModgpuTable *t) { return t->clearPending; }
+// the guarded build kernels of mg_table_bulk_finish did nothing (overflow list too small): undo the host bookkeeping
+void mg_table_bulk_abort(ModgpuTable *t, bool wasPending) { t->clearPending = wasPending; }
 
 void mg_table_counters(ModgpuTable *t, unsigned long long **entries, uint32_t **error) { *entries = t->dEntries; *error = t->dError; }
 uint32_t mg_table_regions(const ModgpuTable *t) { return (uint32_t)(t->nSlots >> MG_REGION_BITS); }
