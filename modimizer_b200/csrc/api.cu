@@ -240,6 +240,9 @@ static int add_chunk_fused(ModgpuModset *ms, const uint8_t *d_bases, const uint6
   }
   // the build follows without a host round trip: its kernels check on the device that the overflow list was
   // large enough and leave the table untouched otherwise (skewed batch: the caller falls back to the list path)
+  { static int gap = -1; if (gap < 0) { const char *v = getenv("MODGPU_GAP"); gap = v ? atoi(v) : 0; }
+    if (gap) MG_CUDA(cudaStreamSynchronize(st));
+  }
   { ProfScope p(ms, MODGPU_T_INSERT, 2);
     if ((rc = mg_table_bulk_finish(ms->table, &b, st))) return rc;
   }

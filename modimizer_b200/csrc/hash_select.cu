@@ -25,6 +25,7 @@
 // Integer-issue bound, not HBM bound (0.25 + 8/d algorithmic bytes per base
 // against ~9-28 instructions per base) - see DESIGN.md for the roofline.
 #include <string.h>
+#include <stdlib.h>
 #include "mg_device.cuh"
 
 #define MG_TILE_PACK_BYTES (MG_TILE_THREADS * 8 + 16)     // 256 words + overlap word, 16 B multiple (258 words)
@@ -61,6 +62,7 @@ struct SelectParams {
   uint32_t rawAscii;
   // LUTK != 0: the 16 KiB candidate table of mg_lut_entry (built per launch into the workspace)
   const uint8_t *lut;
+  uint32_t keepBuckets;        // 1: bucket stores ask L2 to keep the line (evict-last)
 };
 
 // workspace layout: [0, 64) ticket and scratch counters, [64, 64 + MG_LUT_SIZE) candidate table, then the
@@ -494,8 +496,13 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, LUTK ? 3 : 2) hash_count_kerne
             const MgRun RB = mg_run_prepare(w1, w2, H.k);
             m1 = scan_run<PREFILTER>(H, RB);
           }
-        m0 &= mg_run_usable((uint64_t)e0 | ((uint64_t)e1 << 32), H.k, p0, P.nBases);
-        m1 &= mg_run_usable((uint64_t)e1 | ((uint64_t)e2 << 32), H.k, p0 + MG_RUN, P.nBases);
+        // windows that would span two sequences or run off the batch are not usable; a tile with no sequence end
+        // in sight that lies inside the batch (nearly all of them on long sequences) skips the whole computation
+        const bool plain = tileBase + MG_WT_BASES + MG_RUN <= P.nBases && !__any_sync(0xffffffffu, (e0 | e1 | e2) != 0u);
+        if (!plain)
+          { m0 &= mg_run_usable((uint64_t)e0 | ((uint64_t)e1 << 32), H.k, p0, P.nBases);
+            m1 &= mg_run_usable((uint64_t)e1 | ((uint64_t)e2 << 32), H.k, p0 + MG_RUN, P.nBases);
+          }
       }
 
       // ---- phase 2: queue of (run, window) of this warp's 64 runs
@@ -569,7 +576,7 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, LUTK ? 3 : 2) hash_count_kerne
 #pragma unroll
               for (int r = 0; r < MG_SEL_ROUNDS; ++r)
                 if ((okMask >> r) & 1u)
-                  { if (pos[r] < P.bucketCap) mg_st_keep(P.buckets + (uint64_t)region[r] * P.bucketCap + pos[r], km[r]);
+                  { if (pos[r] < P.bucketCap) { uint64_t *bp = P.buckets + (uint64_t)region[r] * P.bucketCap + pos[r]; if (P.keepBuckets) mg_st_keep(bp, km[r]); else *bp = km[r]; }
                     else if (PEER)
                       { const uint32_t ow = region[r] / P.nRegions;
                         const uint32_t o = atomicAdd(&P.ownerCursor[ow], 1u);
@@ -637,7 +644,7 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, LUTK ? 3 : 2) hash_count_kerne
                       const uint32_t ow = PEER ? mg_owner(km, P.nOwners) : 0u;
                       if (PEER) region += ow * P.nRegions;
                       const uint32_t pos = atomicAdd(&P.cursors[region], 1u);
-                      if (pos < P.bucketCap) mg_st_keep(P.buckets + (uint64_t)region * P.bucketCap + pos, km);
+                      if (pos < P.bucketCap) { uint64_t *bp = P.buckets + (uint64_t)region * P.bucketCap + pos; if (P.keepBuckets) mg_st_keep(bp, km); else *bp = km; }
                       else if (PEER)
                         { const uint32_t o = atomicAdd(&P.ownerCursor[ow], 1u);
                           if (o < P.overflowCap) P.overflow[(uint64_t)ow * P.overflowCap + o] = km;
@@ -797,6 +804,7 @@ int mg_hash_select_scatter(const ModgpuHasher *h, const uint64_t *d_packed, cons
   P.lut = (const uint8_t *)d_workspace + MG_WS_LUT;
   P.slotBits = slotBits; P.regionBits = regionBits; P.nRegions = 1u << (slotBits - regionBits); P.bucketCap = bucketCap;
   P.cursors = d_cursors; P.buckets = d_buckets; P.overflow = d_overflow; P.overflowCap = overflowCap;
+  { static int keep = -1; if (keep < 0) { const char *v = getenv("MODGPU_KEEP_BUCKETS"); keep = v ? atoi(v) : 0; } P.keepBuckets = (uint32_t)keep; }
   MG_CUDA(cudaMemsetAsync(d_workspace, 0, 64, st));
   const bool pf = P.H.prefilter && !(flags & MODGPU_SEL_NOPREFILTER);
   const bool tma = !(flags & MODGPU_SEL_NOTMA);
@@ -862,6 +870,7 @@ int mg_hash_select_peer(const ModgpuHasher *h, const uint64_t *d_packed, const u
   P.slotBits = slotBits; P.regionBits = regionBits; P.nRegions = nRegions; P.bucketCap = bucketCap;
   P.cursors = d_cursors; P.buckets = d_buckets; P.overflow = d_overflow; P.overflowCap = overflowCap;
   P.nOwners = nOwners; P.ownerCursor = d_ovfCounts;
+  P.keepBuckets = 1u;                                  // many small buckets: their tail sectors must survive in L2
   MG_CUDA(cudaMemsetAsync(d_workspace, 0, 64, st));
   const bool pf = P.H.prefilter && !(flags & MODGPU_SEL_NOPREFILTER);
   const bool tma = !(flags & MODGPU_SEL_NOTMA);

@@ -219,9 +219,12 @@ template <bool FRESH, bool PEER, int MG_PIPE_UNITS>             // units per war
 __global__ void __launch_bounds__(256, 5) region_build_pipe_kernel(MgSlot *slots, uint32_t slotBits, const MgPeerSrc src,
                                                                 const uint32_t *__restrict__ cursors, uint32_t cap, uint32_t nSrc,
                                                                 uint64_t srcStride, uint32_t nRegions,
-                                                                unsigned long long *entries, uint32_t *error)
+                                                                unsigned long long *entries, uint32_t *error,
+                                                                const uint32_t *__restrict__ guard = nullptr, uint32_t guardLimit = 0)
 {
   __shared__ uint4 sR[MG_REGION_SLOTS];
+  // the scatter that filled the buckets ran out of overflow space: the batch is incomplete, touch nothing
+  if (guard && __ldg(guard) > guardLimit) return;
   __shared__ const uint64_t *sSrc[MODGPU_MAX_PEERS];            // (a dynamically indexed kernel parameter would live in local memory)
   MgSlot *sS = reinterpret_cast<MgSlot *>(sR);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -660,6 +663,30 @@ int mg_table_bulk_finish(ModgpuTable *t, const MgBulk *b, cudaStream_t st)
   static int variant = -1;
   if (variant < 0) { const char *v = getenv("MODGPU_BUILD_VARIANT"); variant = v ? atoi(v) : 0; }
   const uint32_t guardLimit = b->overflowCap > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)b->overflowCap;
+  if (variant == 0)
+    { // default: the persistent, software-pipelined build (the kernel of the peer-memory exchange) on the one local
+      // source.  Same speed as the one-block-per-region kernel when that one is at its best (0.53-0.55 ms), but it
+      // stays there: the block-per-region kernel was measured at 1.1 ms on some boxes / days with nothing else changed
+      static int blocksPerSm = 0;
+      if (!blocksPerSm)
+        { MG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, region_build_pipe_kernel<true, false, 1>, 256, 0));
+          if (blocksPerSm < 1) blocksPerSm = 1;
+        }
+      uint32_t grid = (uint32_t)mg_num_sms() * (uint32_t)blocksPerSm;
+      if (grid > b->nRegions) grid = b->nRegions;
+      MgPeerSrc src;
+      for (uint32_t s2 = 0; s2 < MODGPU_MAX_PEERS; ++s2) src.p[s2] = b->buckets;
+      if (t->clearPending)
+        { region_build_pipe_kernel<true, false, 1><<<grid, 256, 0, st>>>(t->slots, t->slotBits, src, b->cursors, b->cap, 1, b->nRegions, b->nRegions,
+                                                                        t->dEntries, t->dError, b->cursors + b->nRegions, guardLimit);
+          t->clearPending = false;
+        }
+      else
+        region_build_pipe_kernel<false, false, 1><<<grid, 256, 0, st>>>(t->slots, t->slotBits, src, b->cursors, b->cap, 1, b->nRegions, b->nRegions,
+                                                                       t->dEntries, t->dError, b->cursors + b->nRegions, guardLimit);
+    }
+  else
+    {
 #define MG_BUILD_LAUNCH(FR, PL) region_build_kernel<FR, PL><<<b->nRegions, 256, 0, st>>>(t->slots, t->slotBits, b->buckets, b->cursors, b->cap, t->dEntries, t->dError, b->cursors + b->nRegions, guardLimit)
   if (t->clearPending)
     { if (variant == 1) MG_BUILD_LAUNCH(true, 4); else if (variant == 2) MG_BUILD_LAUNCH(true, 2); else MG_BUILD_LAUNCH(true, 0);
@@ -668,6 +695,7 @@ int mg_table_bulk_finish(ModgpuTable *t, const MgBulk *b, cudaStream_t st)
   else
     { if (variant == 1) MG_BUILD_LAUNCH(false, 4); else if (variant == 2) MG_BUILD_LAUNCH(false, 2); else MG_BUILD_LAUNCH(false, 0); }
 #undef MG_BUILD_LAUNCH
+    }
   MG_LAUNCH_CHECK("region_build");
   // stragglers of over-full buckets go straight into HBM; their number is only known on the device:
   // the insert kernel reads it as the 64-bit word {cursors[nRegions], cursors[nRegions+1] == 0}
