@@ -204,6 +204,26 @@ def workload_config(args, per_gpu_bases):
                             "reads every rank's buckets over NVLink, NCCL only for the fill counts") if args.gpus > 1 else "single GPU"}
 
 
+def bind_to_gpu_numa_node(torch, index):
+    """run this rank (and allocate its pinned staging buffer) on the CPUs next to its GPU: with 4 or 8 ranks
+    feeding their GPUs from host memory, buffers on the wrong socket halve the PCIe rate of the e2e path"""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        cpus = open("/sys/bus/pci/devices/%s/local_cpulist" % bus).read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------ our arm --
 def run_ours(args):
     import numpy as np
@@ -225,6 +245,7 @@ def run_ours(args):
     mg.require_device()
     lib = _lib.load()
     _lib.check(lib.modgpuSetDevice(local_rank if world > 1 else 0))
+    numa = bind_to_gpu_numa_node(torch, local_rank if world > 1 else 0)
     dev = torch.device("cuda", torch.cuda.current_device())
     stream = torch.cuda.current_stream()
 
@@ -368,7 +389,7 @@ def run_ours(args):
         wall = float(tt.item())
         e2e = {"value": world * nb * args.steps / wall / 1e9, "unit": "Gbases/s",
                "h2d_bytes_per_step": int(nb + 8 * (args.records + len(groups))), "d2h_bytes_per_step": 24 * len(groups) + 16,
-               "ms_per_step": 1e3 * wall / args.steps,
+               "ms_per_step": 1e3 * wall / args.steps, "host_cpus": numa,
                "timing": "host wall clock around the C-ABI calls (they synchronise), max over ranks"}
         assert state["hashes_e2e"] == hashes and state["entries_e2e"] == entries, "host path and device path disagree"
         lib.modgpuHostFree(h_ptr)
