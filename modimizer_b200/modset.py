@@ -123,7 +123,8 @@ class Modset:
             data, offsets, auto = concat(data)
         else:
             data = np.ascontiguousarray(data, np.uint8)
-            auto = 1 if (data.size and data.max() > 3) else 0
+            # (a scan of the whole batch: only when the caller did not say what the bytes are)
+            auto = (1 if (data.size and data.max() > 3) else 0) if is_ascii is None else 0
         if is_ascii is None:
             is_ascii = auto
         offsets = np.ascontiguousarray(offsets, np.uint64)
@@ -256,7 +257,8 @@ class Modset:
             data, offsets, auto = concat(data)
         else:
             data = np.ascontiguousarray(data, np.uint8)
-            auto = 1 if (data.size and data.max() > 3) else 0
+            # (a scan of the whole batch: only when the caller did not say what the bytes are)
+            auto = (1 if (data.size and data.max() > 3) else 0) if is_ascii is None else 0
         if is_ascii is None:
             is_ascii = auto
         offsets = np.ascontiguousarray(offsets, np.uint64)
@@ -308,7 +310,8 @@ class Reference:
             data, offsets, auto = concat(data)
         else:
             data = np.ascontiguousarray(data, np.uint8)
-            auto = 1 if (data.size and data.max() > 3) else 0
+            # (a scan of the whole batch: only when the caller did not say what the bytes are)
+            auto = (1 if (data.size and data.max() > 3) else 0) if is_ascii is None else 0
         if is_ascii is None:
             is_ascii = auto
         offsets = np.ascontiguousarray(offsets, np.uint64)
@@ -363,7 +366,8 @@ class Reference:
             data, offsets, auto = concat(data)
         else:
             data = np.ascontiguousarray(data, np.uint8)
-            auto = 1 if (data.size and data.max() > 3) else 0
+            # (a scan of the whole batch: only when the caller did not say what the bytes are)
+            auto = (1 if (data.size and data.max() > 3) else 0) if is_ascii is None else 0
         if is_ascii is None:
             is_ascii = auto
         offsets = np.ascontiguousarray(offsets, np.uint64)
