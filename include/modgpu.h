@@ -168,6 +168,7 @@ typedef struct ModgpuModset ModgpuModset;
 ModgpuModset *modgpuModsetCreate(int bits, int k, int w, int seed);   /* modsetCreate, modset.c:15-31 */
 void modgpuModsetDestroy(ModgpuModset *ms);
 const ModgpuHasher *modgpuModsetHasher(const ModgpuModset *ms);
+int modgpuModsetBits(const ModgpuModset *ms);                          /* ms->tableBits */
 ModgpuTable *modgpuModsetTable(ModgpuModset *ms);
 /* use the caller's stream (e.g. torch's current stream) for all work */
 int modgpuModsetSetStream(ModgpuModset *ms, void *stream);
@@ -299,6 +300,18 @@ uint64_t modgpuReferenceQuery(ModgpuReference *r, const char *bases, const uint6
                               uint32_t *seedIndex, uint32_t *seedPos,
                               uint32_t *hitId, uint32_t *hitOffset,
                               int32_t *counters, uint64_t cap);
+
+/* -------------------------------------------------------------- scanner --
+ * modRCiterator / modRCnext (seqhash.c:154-196) for a batch of sequences with HOST buffers on both sides:
+ * every modimizer in (sequence, position) order - k-mer with bit 63 = isForward (seqhash.c:184), its start
+ * position inside its sequence, and seqOff[r] .. seqOff[r+1] = the results of sequence r (nSeq+1 entries).
+ * Returns the total (results beyond cap are not stored), UINT64_MAX on error.  include/modshim.h wraps it
+ * under the reference's own names. */
+typedef struct ModgpuScanner ModgpuScanner;
+ModgpuScanner *modgpuScannerCreate(const ModgpuHasher *h);
+void modgpuScannerDestroy(ModgpuScanner *sc);
+uint64_t modgpuScannerScan(ModgpuScanner *sc, const char *bases, const uint64_t *offs, uint64_t nSeq, int isAscii,
+                           uint64_t *kmers, uint32_t *pos, uint64_t *seqOff, uint64_t cap);
 
 /* ------------------------------------------------ multi-GPU partitioning --
  * owner of a k-mer in a table sharded over nOwners GPUs (independent of the

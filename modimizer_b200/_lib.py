@@ -63,6 +63,7 @@ _SIGS = {
     "modgpuModsetDestroy": (None, [vp]),
     "modgpuModsetHasher": (C.POINTER(Hasher), [vp]),
     "modgpuModsetTable": (vp, [vp]),
+    "modgpuModsetBits": (C.c_int, [vp]),
     "modgpuModsetSetStream": (C.c_int, [vp, vp]),
     "modgpuModsetSetFlags": (C.c_int, [vp, C.c_int]),
     "modgpuModsetSetExactOrder": (C.c_int, [vp, C.c_int]),
@@ -110,6 +111,9 @@ _SIGS = {
     "modgpuReferenceMax": (u32, [vp]),
     "modgpuReferenceExport": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "modgpuReferenceQuery": (u64, [vp, vp, vp, u64, C.c_int, vp, vp, vp, vp, vp, vp, u64]),
+    "modgpuScannerCreate": (vp, [C.POINTER(Hasher)]),
+    "modgpuScannerDestroy": (None, [vp]),
+    "modgpuScannerScan": (u64, [vp, vp, vp, u64, C.c_int, vp, vp, vp, u64]),
     "modgpuHostAlloc": (vp, [C.c_size_t]),
     "modgpuHostFree": (None, [vp]),
     "modgpuSynthGenome": (C.c_int, [u64, u64, u64, C.c_int, vp, vp]),

@@ -431,6 +431,73 @@ extern "C" int modgpuModsetSelectHost(ModgpuModset *ms, const char *bases, const
   return modgpuModsetSelectDevice(ms, (const uint8_t *)ms->bases[0].p, (const uint64_t *)ms->offs[0].p, nSeq, nb, isAscii, d_kmers, nSelected);
 }
 
+// ------------------------------------------------------------ scanner --
+// modRCiterator / modRCnext over a batch of sequences (seqhash.c:154-196) with HOST buffers on both sides:
+// the modimizers of every sequence in (sequence, position) order - k-mer (bit 63 = isForward), position inside
+// its sequence, and seqOff[r] .. seqOff[r+1] = the results of sequence r.  Returns the total, UINT64_MAX on error;
+// when the total exceeds cap only the first cap results are stored.
+struct ModgpuScanner { ModgpuModset *ms; DevBuf id, pos; };
+
+extern "C" ModgpuScanner *modgpuScannerCreate(const ModgpuHasher *h)
+{
+  ModgpuModset *ms = modgpuModsetCreateWithHasher(20, h);        // only its hasher, stream and scratch buffers are used
+  if (!ms) return nullptr;
+  ModgpuScanner *sc = new ModgpuScanner();
+  sc->ms = ms;
+  return sc;
+}
+
+extern "C" void modgpuScannerDestroy(ModgpuScanner *sc)
+{
+  if (!sc) return;
+  sc->id.release(); sc->pos.release();
+  modgpuModsetDestroy(sc->ms);
+  delete sc;
+}
+
+extern "C" uint64_t modgpuScannerScan(ModgpuScanner *sc, const char *bases, const uint64_t *offs, uint64_t nSeq, int isAscii,
+                                      uint64_t *kmers, uint32_t *pos, uint64_t *seqOff, uint64_t cap)
+{
+  const uint64_t FAIL = 0xFFFFFFFFFFFFFFFFull;
+  ModgpuModset *ms = sc->ms;
+  cudaStream_t st = ms->stream;
+  if (seqOff) for (uint64_t r = 0; r <= nSeq; ++r) seqOff[r] = 0;
+  if (!nSeq) return 0;
+  if (check_offsets(offs, nSeq)) return FAIL;
+  const uint64_t nb = offs[nSeq];
+  if (nb >= (1ull << 32)) { mg_set_error("modgpuScannerScan: batch exceeds 2^32-1 bases"); return FAIL; }
+  if (!nb) return 0;
+  if (ms->bases[0].ensure(nb + 64) || ms->offs[0].ensure((nSeq + 1) * 8)) return FAIL;
+  if (mg_check_cuda(cudaMemcpyAsync(ms->bases[0].p, bases, nb, cudaMemcpyHostToDevice, st), "H2D bases", __FILE__, __LINE__) ||
+      mg_check_cuda(cudaMemcpyAsync(ms->offs[0].p, offs, (nSeq + 1) * 8, cudaMemcpyHostToDevice, st), "H2D offsets", __FILE__, __LINE__))
+    return FAIL;
+  uint64_t n = 0;
+  if (mg_modset_select_chunk(ms, (const uint8_t *)ms->bases[0].p, (const uint64_t *)ms->offs[0].p, nSeq, nb, isAscii, true,
+                             MODGPU_SEL_ORDERED | MODGPU_SEL_STRAND, &n))
+    return FAIL;
+  const uint64_t m = n < cap ? n : cap;
+  if (m)
+    { if (sc->id.ensure(n * 4) || sc->pos.ensure(n * 4)) return FAIL;
+      // global offset -> (sequence, position in sequence)
+      if (modgpuLocate((const uint32_t *)ms->gpos.p, n, (const uint64_t *)ms->offs[0].p, nSeq, (uint32_t *)sc->id.p, (uint32_t *)sc->pos.p, st))
+        return FAIL;
+      if (kmers && mg_check_cuda(cudaMemcpyAsync(kmers, ms->kmers.p, m * 8, cudaMemcpyDeviceToHost, st), "D2H kmers", __FILE__, __LINE__)) return FAIL;
+      if (pos && mg_check_cuda(cudaMemcpyAsync(pos, sc->pos.p, m * 4, cudaMemcpyDeviceToHost, st), "D2H pos", __FILE__, __LINE__)) return FAIL;
+    }
+  std::vector<uint32_t> id;
+  if (seqOff && n)
+    { id.resize(n);
+      if (mg_check_cuda(cudaMemcpyAsync(id.data(), sc->id.p, n * 4, cudaMemcpyDeviceToHost, st), "D2H ids", __FILE__, __LINE__)) return FAIL;
+    }
+  if (mg_check_cuda(cudaStreamSynchronize(st), "cudaStreamSynchronize", __FILE__, __LINE__)) return FAIL;
+  if (seqOff && n)
+    { // results are in sequence order: a counting pass gives the per-sequence ranges
+      for (uint64_t i = 0; i < n; ++i) ++seqOff[id[i] + 1];
+      for (uint64_t r = 0; r < nSeq; ++r) seqOff[r + 1] += seqOff[r];
+    }
+  return n;
+}
+
 // multi-GPU, sync-free: K1 + K2 with the selected k-mers written into nOwners segments of the caller's
 // send buffer (segment o = k-mers owned by rank o), counts in d_counts (uint32 per owner)
 extern "C" int modgpuModsetSelectOwnersDevice(ModgpuModset *ms, const uint8_t *d_bases, const uint64_t *d_offs,
@@ -588,6 +655,7 @@ static int ensure_numbered(ModgpuModset *ms)
 
 int mg_modset_ensure_numbered(ModgpuModset *ms) { return ensure_numbered(ms); }
 void mg_modset_mark(ModgpuModset *ms, bool dirty, bool depthIsZero) { ms->dirty = dirty; ms->depthIsZero = depthIsZero; }
+extern "C" int modgpuModsetBits(const ModgpuModset *ms) { return ms->bits; }
 cudaStream_t mg_modset_stream(ModgpuModset *ms) { return ms->stream; }
 void *mg_modset_kmers(ModgpuModset *ms) { return ms->kmers.p; }
 void *mg_modset_gpos(ModgpuModset *ms) { return ms->gpos.p; }
