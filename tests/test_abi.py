@@ -101,3 +101,28 @@ def test_fails_loudly_without_a_gpu():
     src = "".join(open(os.path.join(ROOT, "modimizer_b200", f)).read() for f in os.listdir(os.path.join(ROOT, "modimizer_b200")) if f.endswith(".py"))
     assert "oracle" not in src.replace("the oracle side", "").replace("oracle's ref_query", "") or True
     assert "liboracle" not in src and "harness" not in src
+
+
+def test_shim_exports_the_reference_names(orc):
+    """libmodshim.so (built against the reference's headers where /root/reference exists): the unchanged seqhash.h
+    symbols are there, and the host-only ones work without a GPU"""
+    import ctypes as C
+    path = os.path.join(ROOT, "modimizer_b200", "libmodshim.so")
+    if not os.path.exists(path):
+        pytest.skip("libmodshim.so not built (no /root/reference on this box)")
+    lib = C.CDLL(path)
+    for name in ("seqhashCreate", "seqhashWrite", "seqhashRead", "seqhashReport", "modRCiterator", "modRCnext",
+                 "minimizerRCiterator", "minimizerRCnext", "seqString", "modshimScanner"):
+        assert hasattr(lib, name), name
+    lib.seqhashCreate.restype = C.c_void_p
+    sh = lib.seqhashCreate(19, 31, 17)
+    raw = (C.c_ubyte * 80).from_address(sh)
+    o = orc.hasher(19, 31, 17)
+    import struct
+    seed, k, w = struct.unpack_from("<iii", bytes(raw), 0)
+    mask, = struct.unpack_from("<Q", bytes(raw), 16)
+    f1, f2 = struct.unpack_from("<QQ", bytes(raw), 32)
+    assert (seed, k, w, mask, f1, f2) == (17, 19, 31, o["mask"], o["factor1"], o["factor2"])
+    lib.seqString.restype = C.c_char_p
+    lib.seqString.argtypes = [C.c_uint64, C.c_int]
+    assert lib.seqString(0x3e4e58c9c9, 19) == b"ttgcatgccgatagctagc"              # SURVEY section 4
