@@ -315,22 +315,23 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     n_ins = hashes                                          # inserts this rank issued per step (world 1)
     # algorithmic bytes: K1 is fused into K2's tile loader, so the select pass reads the raw bytes
-    # (1 B/base) and writes the selected k-mers (8/d B/base): 1 + 8/d; the "pack" scope only holds the end-flag
-    # marking (1 bit per base written); insert = 20 B per selected k-mer
-    alg = {"pack": nb * 0.125, "select": nb * (1.0 + 8.0 / D), "insert": n_ins * 20.0}
+    # (1 B/base) and writes the selected k-mers (8/d B/base): 1 + 8/d; the "pack" scope only holds the sparse
+    # end-flag marking (two offsets read, one flag word touched, per sequence); insert = 20 B per selected k-mer
+    alg = {"pack": 2.0 * args.records * 20.0, "select": nb * (1.0 + 8.0 / D), "insert": n_ins * 20.0}
     kern = {}
     for name in ("pack", "select", "insert"):
         ms_k = times[name][0] / prof_steps
         kern[name] = {"ms_per_step": ms_k, "alg_bytes_per_step": alg[name],
                       "achieved_gbs": (alg[name] / (ms_k * 1e-3) / 1e9) if ms_k > 0 else None}
-    kern["pack"]["what"] = "mark_ends_kernel + memset of the flag words (K1 itself runs inside the select kernel)"
+    kern["pack"]["what"] = "mark_ends_kernel + unmark_ends_kernel: one flag per sequence set and cleared again (K1 itself runs inside the select kernel)"
     kern["select"]["what"] = "lut_build_kernel + hash_count_kernel: fused K1 pack2bit + K2 hash/select + K3 bucket scatter"
-    kern["insert"]["what"] = "region build in shared memory (+ overflow inserts)" + (", reading peer buckets over NVLink" if world > 1 else "")
+    kern["insert"]["what"] = ("region_build_pipe_kernel: persistent, pipelined region build in shared memory (+ overflow inserts)" +
+                              (", reading every rank's buckets over NVLink" if world > 1 else "; writes the 2 GiB table once"))
     dom = max(("pack", "select", "insert"), key=lambda n: kern[n]["ms_per_step"])
     launches_per_step = sum(times[n][1] for n in times) // prof_steps
     traffic = None
     kname = {"pack": "mark_ends_kernel", "select": "hash_count_kernel",
-             "insert": "region_build_pipe_kernel" if world > 1 else "region_build_kernel"}
+             "insert": "region_build_pipe_kernel"}
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
         if abs(nb - 3.1e9) < 1e8 and world == 1 and args.flags == 0:
@@ -342,7 +343,7 @@ def run_ours(args):
                 "frac": (kern[dom]["achieved_gbs"] / peak) if kern[dom]["achieved_gbs"] else None,
                 "traffic": traffic, "kernels": kern,
                 "note": "hash_count_kernel (fused pack + hash/select + scatter) is bound by instruction issue and the shared-memory "
-                        "pipe, not by HBM (ncu r01 v5: issue 67 %, ALU pipe 61 %, shared-memory wavefronts ~60 %, DRAM 29 %); "
+                        "pipe, not by HBM (ncu r01 v6: issue 74 %, ALU pipe 62 %, shared-memory pipe ~65 %, DRAM 34 %, 12.8 inst/base); "
                         "1 + 8/d algorithmic bytes per base; see DESIGN.md section 3 and profiles/"}
 
     # ---- e2e: host buffers through the C ABI, H2D inside the timed region
