@@ -17,7 +17,7 @@ int mg_table_lookup_dev(const ModgpuTable *t, const uint64_t *d_kmers, const uin
                         uint32_t *d_out, cudaStream_t st);
 uint64_t mg_table_numbered(const ModgpuTable *t);
 int mg_table_insert_bulk(ModgpuTable *t, const uint64_t *d_kmers, uint64_t n, cudaStream_t st);
-struct MgBulk { uint32_t slotBits, regionBits, nRegions, cap; uint32_t *cursors; uint64_t *buckets, *overflow; uint64_t overflowCap; };
+struct MgBulk { uint32_t slotBits, regionBits, nRegions, cap; uint32_t *cursors; uint64_t *buckets, *overflow; uint64_t overflowCap; uint64_t expected; };
 int mg_table_bulk_begin(ModgpuTable *t, uint64_t expectedN, uint64_t maxN, MgBulk *b, cudaStream_t st);
 const uint32_t *mg_table_bulk_overflow_count(const ModgpuTable *t);
 int mg_table_bulk_finish(ModgpuTable *t, const MgBulk *b, cudaStream_t st);

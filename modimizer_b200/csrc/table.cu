@@ -626,7 +626,7 @@ extern "C" int modgpuTableClear(ModgpuTable *t, void *stream)
 //   mg_table_bulk_begin   size + zero the per-region buckets for ~expectedN k-mers
 //   (scatter)             bucket_scatter_kernel on a list, or hash_select<SCATTER>
 //   mg_table_bulk_finish  build every region in shared memory, then the overflow
-struct MgBulk { uint32_t slotBits, regionBits, nRegions, cap; uint32_t *cursors; uint64_t *buckets, *overflow; uint64_t overflowCap; };
+struct MgBulk { uint32_t slotBits, regionBits, nRegions, cap; uint32_t *cursors; uint64_t *buckets, *overflow; uint64_t overflowCap; uint64_t expected; };
 
 int mg_table_bulk_begin(ModgpuTable *t, uint64_t expectedN, uint64_t maxN, MgBulk *b, cudaStream_t st)
 {
@@ -651,6 +651,7 @@ int mg_table_bulk_begin(ModgpuTable *t, uint64_t expectedN, uint64_t maxN, MgBul
     }
   MG_CUDA(cudaMemsetAsync(t->dCursors, 0, ((size_t)nRegions + 16) * sizeof(uint32_t), st));
   b->slotBits = t->slotBits; b->regionBits = MG_REGION_BITS; b->nRegions = nRegions; b->cap = (uint32_t)cap64;
+  b->expected = expectedN;
   b->cursors = t->dCursors; b->buckets = t->dBuckets; b->overflow = t->dOverflow; b->overflowCap = t->overflowCap;
   return MODGPU_OK;
 }
@@ -663,7 +664,11 @@ int mg_table_bulk_finish(ModgpuTable *t, const MgBulk *b, cudaStream_t st)
   static int variant = -1;
   if (variant < 0) { const char *v = getenv("MODGPU_BUILD_VARIANT"); variant = v ? atoi(v) : 0; }
   const uint32_t guardLimit = b->overflowCap > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)b->overflowCap;
-  if (variant == 0)
+  // a fresh table goes through the persistent pipelined kernel (one streaming write of the table); regions of a
+  // populated table are read-modify-written by the block-per-region kernel, whose many short blocks hide the region
+  // loads better (93 Gbases in 3-Gbase chunks into an 8 GiB table: 144 ms against 178 ms with the persistent kernel;
+  // probing the populated table in place, bucket by bucket, was slower still: 190 ms)
+  if (variant == 0 && t->clearPending)
     { // default: the persistent, software-pipelined build (the kernel of the peer-memory exchange) on the one local
       // source.  Same speed as the one-block-per-region kernel when that one is at its best (0.53-0.55 ms), but it
       // stays there: the block-per-region kernel was measured at 1.1 ms on some boxes / days with nothing else changed
