@@ -5,6 +5,7 @@ oracle/_ref/libmodref.so (the unmodified reference objects behind the same API).
 Neither is ever imported by the product package.
 """
 import ctypes as C
+import gzip
 import os
 import subprocess
 import numpy as np
@@ -211,3 +212,94 @@ def write_fasta(path, seqs, names=None, width=0):
                     f.write(txt[j:j + width] + "\n")
             else:
                 f.write(txt + "\n")
+
+
+def modmap_case(d, seed=33):
+    """g.fa / r.fa for the modmap driver tests: three reference sequences with a two-copy, a three-copy and an
+    inverted segment; reads of both strands with 3 % substitutions, plus a long two-copy read, len < k, empty
+    and an unrelated read"""
+    rng = np.random.default_rng(seed)
+    genome = rng.integers(0, 4, 400000).astype(np.uint8)
+    genome[300000:330000] = genome[50000:80000]
+    genome[120000:126000] = genome[50000:56000]
+    genome[350000:358000] = (3 - genome[10000:18000])[::-1]
+    chrom = [genome[:100000], genome[100000:250000], genome[250000:]]
+    reads = []
+    for _ in range(400):
+        s = int(rng.integers(0, len(genome) - 6000)); L = int(rng.integers(300, 6000))
+        r = genome[s:s + L].copy()
+        if rng.integers(0, 2):
+            r = (3 - r)[::-1]
+        e = rng.random(len(r)) < 0.03
+        r[e] = (r[e] + rng.integers(1, 4, int(e.sum()))) & 3
+        reads.append(r)
+    reads += [genome[299000:331000].copy(), genome[49000:57000].copy(), (3 - genome[349000:359000])[::-1].copy(),
+              genome[:18], genome[7:7], rng.integers(0, 4, 3000).astype(np.uint8)]
+    write_fasta(os.path.join(d, "g.fa"), chrom, names=["chrA", "chrB", "chrC"], width=60)
+    write_fasta(os.path.join(d, "r.fa"), reads, width=0)
+
+
+def stable_lines(text):
+    """the lines of a tool's output that do not carry rusage numbers (utils.c:176-204)"""
+    return [l for l in text.splitlines() if not l.startswith("user\t") and not l.startswith("total resources used")]
+
+
+def ref_file_masked(raw):
+    """a .ref file (modmap.c:136-156) with the heap pointers that arrayWrite and dictWrite dump zeroed: locates the
+    trailing Array (32-byte struct, base pointer at 8) and DICT (dim, max, table[1<<dim], names[max+1] pointers, strings)
+    from the end of the U32 arrays by scanning for the Array magic"""
+    b = bytearray(raw)
+    assert b[:8] == b"RFMSHv1\0"
+    n = int(np.frombuffer(raw[8:12], np.uint32)[0])
+    # index/offset/id/rev have n entries, depth/loc have m: the Array struct follows; its dim/size/max are at +16/+20/+24
+    at = None
+    for m in range(1, n + 2):
+        o = 16 + 16 * n + 8 * m
+        if o + 32 <= len(b) and np.frombuffer(raw[o + 20:o + 24], np.int32)[0] == 4 and 0 < np.frombuffer(raw[o + 16:o + 20], np.int32)[0] < (1 << 24) \
+                and np.frombuffer(raw[o + 24:o + 28], np.int32)[0] <= np.frombuffer(raw[o + 16:o + 20], np.int32)[0]:
+            dim = int(np.frombuffer(raw[o + 16:o + 20], np.int32)[0])
+            do = o + 32 + 4 * dim
+            if do + 8 <= len(b):
+                ddim, dmax = [int(x) for x in np.frombuffer(raw[do:do + 8], np.int32)]
+                if 0 < ddim < 30 and 0 < dmax < (1 << ddim) and do + 8 + 4 * (1 << ddim) + 8 * (dmax + 1) <= len(b):
+                    at = (o, do, ddim, dmax)
+                    break
+    assert at, "no Array / DICT tail found in the .ref file"
+    o, do, ddim, dmax = at
+    b[o + 8:o + 16] = bytes(8)
+    p = do + 8 + 4 * (1 << ddim)
+    b[p:p + 8 * (dmax + 1)] = bytes(8 * (dmax + 1))
+    return bytes(b)
+
+
+def modmap_driver_vs_stock(stock, driver, d, check_mod):
+    """runs the stock modmap and a driver with the same command lines in directory d and compares everything"""
+    def run(tool, args):
+        r = subprocess.run([tool] + args, cwd=d, capture_output=True, text=True)
+        assert r.returncode == 0, (tool, args, r.stdout[-500:], r.stderr[-500:])
+        return r
+    def rd(name, mode="r"):
+        with open(os.path.join(d, name), mode) as f:
+            return f.read()
+    for (k, w) in ((19, 31), (31, 64), (15, 8)):
+        par = ["-K", str(k), "-W", str(w), "-B", "20"]
+        a = run(stock, ["-o", "a.out"] + par + ["-f", "g.fa", "-w", "a", "-v", "-q", "r.fa"])
+        b = run(driver, ["-o", "b.out"] + par + ["-f", "g.fa", "-w", "b", "-v", "-q", "r.fa"])
+        oa, ob = stable_lines(rd("a.out")), stable_lines(rd("b.out"))
+        assert oa == ob, (k, w)
+        assert any(l.startswith("M\t") for l in oa) and any(l.startswith("Q\t") for l in oa), (k, w)
+        assert stable_lines(a.stdout) == stable_lines(b.stdout), (k, w)             # the -v seed lines
+        assert any(l.startswith("  ") and "\t" in l for l in a.stdout.splitlines()), (k, w)
+        # everything on one stream: seed lines and M lines interleave exactly as in the stock tool
+        assert stable_lines(run(stock, par + ["-f", "g.fa", "-v", "-q", "r.fa"]).stdout) == \
+               stable_lines(run(driver, par + ["-f", "g.fa", "-v", "-q", "r.fa"]).stdout), (k, w)
+        # the index files (gzip streams, utils.c:108-139): same content - first-occurrence numbering, the reference's
+        # probe order, packed arrays.  arrayWrite / dictWrite dump heap pointers (array.c:215, dict.c:95): masked.
+        ra, rb = ref_file_masked(gzip.decompress(rd("a.ref", "rb"))), ref_file_masked(gzip.decompress(rd("b.ref", "rb")))
+        assert ra == rb, (k, w, "ref")
+        if check_mod:
+            assert gzip.decompress(rd("a.mod", "rb")) == gzip.decompress(rd("b.mod", "rb")), (k, w, "mod")
+        if check_mod:                          # and the stock modmap maps from the files written by the driver
+            run(stock, ["-o", "c.out", "-r", "b", "-q", "r.fa"])
+            pick = lambda ls: [l for l in ls if l[:2] in ("Q\t", "M\t")]
+            assert pick(stable_lines(rd("c.out"))) == pick(oa), (k, w)

@@ -3,6 +3,8 @@
   * modimizer_b200/modutils_gpu - a C modutils (our own command interpreter) in which the reference's seqio parses the
     files and libmodgpu does the rest - against the STOCK modutils (oracle/_ref/modutils) on the same files: every file
     they write and every stable line they print must be byte-identical, and each reads the other's .mod files;
+  * modimizer_b200/modmap_gpu - a C modmap over libmodgpu (index build, .mod/.ref writer, Q / seed / M lines) - against
+    the STOCK modmap: same output bytes, same .mod and .ref bytes, and the stock tool maps from the files written here;
   * modimizer_b200/libmodshim.so - the reference's own seqhash symbols (seqhashCreate, modRCiterator, modRCnext,
     seqString) served by the GPU - against the oracle, through the reference's own struct layouts.
 
@@ -19,6 +21,7 @@ import harness as H
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GPU_CLI = os.path.join(ROOT, "modimizer_b200", "modutils_gpu")
+GPU_MODMAP = os.path.join(ROOT, "modimizer_b200", "modmap_gpu")
 SHIM = os.path.join(ROOT, "modimizer_b200", "libmodshim.so")
 
 
@@ -85,6 +88,14 @@ def test_c_modutils_matches_stock_modutils(tmp_path):
         pa = run(stock, ["-r", "a.mod", "-P", "g.fa"], d).stdout
         pb = run(GPU_CLI, ["-r", "a.mod", "-P", "g.fa"], d).stdout
         assert stable(pa) == stable(pb) and any(l.startswith("  ") for l in pa.splitlines()), (k, w)
+
+
+def test_c_modmap_matches_stock_modmap(tmp_path):
+    stock = H.ref_cli("modmap")
+    if not stock or not os.path.exists(GPU_MODMAP):
+        pytest.skip("stock modmap / modmap_gpu not built (no /root/reference in the build container)")
+    H.modmap_case(str(tmp_path))
+    H.modmap_driver_vs_stock(stock, GPU_MODMAP, str(tmp_path), check_mod=True)
 
 
 class Seqhash(C.Structure):                      # reference seqhash.h:15-23
