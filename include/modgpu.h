@@ -247,6 +247,15 @@ int modgpuModsetInsertSegments(ModgpuModset *ms, const uint64_t *d_segments, uin
 /* insert + count a device list of k-mers into the object's table */
 int modgpuModsetInsertDevice(ModgpuModset *ms, const uint64_t *d_kmers, uint64_t n);
 int modgpuModsetClear(ModgpuModset *ms);
+/* Deferred build for streaming many batches into one set (new; the reference's loop has no counterpart: it pays one
+ * random probe per k-mer, addSequence modutils.c:19-31).  With nChunks > 1 the selected k-mers of up to nChunks device
+ * chunks wait in the table's per-region buckets and the regions are built once for all of them - a populated table is
+ * read and written once per nChunks chunks instead of once per chunk.  Results are identical.  What changes is when a
+ * full table (modset.c:58, the reference dies) is reported: by modgpuModsetFlush or by the first call that reads the
+ * set (every reader flushes first), not by the modgpuModsetAdd* call that overfilled it.  nChunks <= 1: default. */
+int modgpuModsetSetAccumulate(ModgpuModset *ms, int nChunks);
+/* apply what is waiting; MODGPU_EFULL when the table is over its capacity */
+int modgpuModsetFlush(ModgpuModset *ms);
 
 /* ------------------------------------------------ whole-set operations --
  * modsetDepthPrune (modset.c:64-77): keep entries with min <= depth < max

@@ -94,6 +94,8 @@ _SIGS = {
     "modgpuModsetInsertSegments": (C.c_int, [vp, vp, u32, u64, vp, u64]),
     "modgpuModsetInsertDevice": (C.c_int, [vp, vp, u64]),
     "modgpuModsetClear": (C.c_int, [vp]),
+    "modgpuModsetSetAccumulate": (C.c_int, [vp, C.c_int]),
+    "modgpuModsetFlush": (C.c_int, [vp]),
     "modgpuOwnerOf": (u32, [u64, u32]),
     "modgpuOwnerCount": (C.c_int, [vp, u64, u32, vp, vp]),
     "modgpuOwnerScatter": (C.c_int, [vp, u64, u32, vp, vp, vp]),

@@ -228,8 +228,11 @@ static int add_chunk_fused(ModgpuModset *ms, const uint8_t *d_bases, const uint6
     if ((rc = ends_mark(ms, d_offs, nSeq, nBases, st))) return rc;
   }
   MgBulk b;
+  const bool deferred = ms->accumulate > 1;              // the buckets stay open over several chunks
   const bool wasPending = mg_table_clear_pending(ms->table);
-  if ((rc = mg_table_bulk_begin(ms->table, expected, 2 * expected + 65536, &b, st))) return rc;
+  if ((rc = deferred ? mg_table_bulk_open(ms->table, expected, ms->accumulate, &b, st)
+                     : mg_table_bulk_begin(ms->table, expected, 2 * expected + 65536, &b, st)))
+    return rc;
   uint64_t *dCount = (uint64_t *)ms->misc.p;
   volatile uint64_t *hCount = (volatile uint64_t *)ms->hMisc.p;
   { ProfScope p(ms, MODGPU_T_SELECT, mg_select_launches(&ms->hasher, ms->selFlags | (ms->exactOrder ? MODGPU_SEL_ORDERED : 0)));
@@ -243,18 +246,25 @@ static int add_chunk_fused(ModgpuModset *ms, const uint8_t *d_bases, const uint6
   { static int gap = -1; if (gap < 0) { const char *v = getenv("MODGPU_GAP"); gap = v ? atoi(v) : 0; }
     if (gap) MG_CUDA(cudaStreamSynchronize(st));
   }
-  { ProfScope p(ms, MODGPU_T_INSERT, 2);
-    if ((rc = mg_table_bulk_finish(ms->table, &b, st))) return rc;
-  }
+  if (!deferred)
+    { ProfScope p(ms, MODGPU_T_INSERT, 2);
+      if ((rc = mg_table_bulk_finish(ms->table, &b, st))) return rc;
+    }
   if ((rc = ends_unmark(ms, d_offs, nSeq, st))) return rc;
   MG_CUDA(cudaMemcpyAsync((void *)hCount, dCount, 8, cudaMemcpyDeviceToHost, st));
   MG_CUDA(cudaMemcpyAsync((void *)(hCount + 1), mg_table_bulk_overflow_count(ms->table), 4, cudaMemcpyDeviceToHost, st));
   MG_CUDA(cudaStreamSynchronize(st));
-  const uint64_t overflowed = hCount[1] & 0xFFFFFFFFull;
+  const uint64_t overflowed = hCount[1] & 0xFFFFFFFFull;  // deferred: cumulative over the chunks waiting in the buckets
   if (overflowed > b.overflowCap)                        // buckets and overflow list too small: nothing was applied
-    { mg_table_bulk_abort(ms->table, wasPending);
+    { if (deferred)
+        { ProfScope p(ms, MODGPU_T_INSERT, 2);
+          if ((rc = mg_table_bulk_rollback(ms->table, st))) return rc;    // builds what was waiting before this chunk
+          ms->dirty = true;
+        }
+      else mg_table_bulk_abort(ms->table, wasPending);
       return 1;
     }
+  if (deferred) mg_table_bulk_commit(ms->table, expected, overflowed);
   *nHashes = hCount[0];
   ms->dirty = true;
   return MODGPU_OK;
@@ -363,7 +373,7 @@ extern "C" uint64_t modgpuModsetAdd(ModgpuModset *ms, const char *bases, const u
       total += n;
     }
   ms->totalHashes += total;
-  if (modgpuTableEntries(ms->table, ms->stream) == FAIL) return FAIL;      // reference: die() on overflow
+  if (ms->accumulate <= 1 && modgpuTableEntries(ms->table, ms->stream) == FAIL) return FAIL;      // reference: die() on overflow
   return total;
 }
 
@@ -401,7 +411,7 @@ extern "C" uint64_t modgpuModsetAddDevice(ModgpuModset *ms, const uint8_t *d_bas
         }
     }
   ms->totalHashes += total;
-  if (modgpuTableEntries(ms->table, ms->stream) == FAIL) return FAIL;
+  if (ms->accumulate <= 1 && modgpuTableEntries(ms->table, ms->stream) == FAIL) return FAIL;     // deferred: modgpuModsetFlush reports
   return total;
 }
 
@@ -633,6 +643,32 @@ extern "C" int modgpuModsetInsertDevice(ModgpuModset *ms, const uint64_t *d_kmer
   ms->dirty = true;
   ms->totalHashes += n;
   return MODGPU_OK;
+}
+
+// Deferred build for streaming many batches into one set: the selected k-mers of up to nChunks device chunks wait in
+// the table's region buckets and the regions are built once for all of them.  Results are identical (counts are sums);
+// what changes is WHEN a full table is reported: by modgpuModsetFlush, or by the first call that reads the set (every
+// reader flushes), instead of by the modgpuModsetAdd* call that overfilled it.  nChunks <= 1 restores the default.
+extern "C" int modgpuModsetSetAccumulate(ModgpuModset *ms, int nChunks)
+{
+  if (!ms) { mg_set_error("modgpuModsetSetAccumulate: null modset"); return MODGPU_EINVAL; }
+  if (nChunks > 64) nChunks = 64;
+  if (nChunks <= 1)
+    { int rc = mg_table_bulk_close(ms->table, ms->stream);
+      if (rc) return rc;
+    }
+  ms->accumulate = nChunks > 1 ? (uint32_t)nChunks : 1u;
+  return MODGPU_OK;
+}
+
+extern "C" int modgpuModsetFlush(ModgpuModset *ms)
+{
+  if (!ms) { mg_set_error("modgpuModsetFlush: null modset"); return MODGPU_EINVAL; }
+  { ProfScope p(ms, MODGPU_T_INSERT, mg_table_bulk_is_open(ms->table) ? 2 : 0);
+    int rc = mg_table_bulk_close(ms->table, ms->stream);
+    if (rc) return rc;
+  }
+  return modgpuTableEntries(ms->table, ms->stream) == 0xFFFFFFFFFFFFFFFFull ? MODGPU_EFULL : MODGPU_OK;
 }
 
 extern "C" int modgpuModsetClear(ModgpuModset *ms)

@@ -21,6 +21,12 @@ struct MgBulk { uint32_t slotBits, regionBits, nRegions, cap; uint32_t *cursors;
 int mg_table_bulk_begin(ModgpuTable *t, uint64_t expectedN, uint64_t maxN, MgBulk *b, cudaStream_t st);
 const uint32_t *mg_table_bulk_overflow_count(const ModgpuTable *t);
 int mg_table_bulk_finish(ModgpuTable *t, const MgBulk *b, cudaStream_t st);
+// deferred build: buckets kept open over several chunks (table.cu)
+int mg_table_bulk_open(ModgpuTable *t, uint64_t expected, uint32_t accum, MgBulk *b, cudaStream_t st);
+void mg_table_bulk_commit(ModgpuTable *t, uint64_t expected, uint64_t ovfSeen);
+int mg_table_bulk_rollback(ModgpuTable *t, cudaStream_t st);
+int mg_table_bulk_close(ModgpuTable *t, cudaStream_t st);
+bool mg_table_bulk_is_open(const ModgpuTable *t);
 int mg_hash_select_peer(const ModgpuHasher *h, const uint64_t *d_packed, const uint32_t *d_ends, uint64_t nBases,
                         uint64_t *d_count, void *d_workspace, int flags, uint32_t slotBits, uint32_t regionBits,
                         uint32_t nOwners, uint32_t bucketCap, uint32_t *d_cursors, uint64_t *d_buckets,
@@ -100,6 +106,7 @@ struct ModgpuModset {
   PinBuf hOffs[2], hMisc;
   cudaEvent_t evCopied[2] = { nullptr, nullptr }, evFree[2] = { nullptr, nullptr };
   uint64_t totalHashes = 0;
+  uint32_t accumulate = 1;          // > 1: deferred build, up to this many chunks share one region build
   // profiling
   bool profile = false;
   std::vector<TimedSpan> spans;

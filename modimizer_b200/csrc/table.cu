@@ -23,6 +23,8 @@
 #include "mg_scan.cuh"
 #include "mg_table.cuh"
 
+struct MgBulk { uint32_t slotBits, regionBits, nRegions, cap; uint32_t *cursors; uint64_t *buckets, *overflow; uint64_t overflowCap; uint64_t expected; };
+
 struct ModgpuTable {
   MgSlot *slots;
   int bits;                  // reference tableBits
@@ -41,6 +43,13 @@ struct ModgpuTable {
   uint32_t *dCursors;        // bulk insert: per-region fill counts (+ overflow count at [nRegions])
   uint64_t *dOverflow;       // k-mers that did not fit their bucket
   uint64_t overflowCap;
+  // deferred build: the buckets stay open over several scattered chunks and the regions are built once
+  // (mg_table_bulk_open / _commit / _rollback / _close); every reader of the table closes them first
+  bool bulkOpen;
+  MgBulk bulk;
+  uint64_t bulkRoom, bulkUsed;    // expected k-mers the open buckets were sized for / scattered so far
+  uint64_t bulkOvfSeen;           // overflow-list entries in use after the last committed chunk (host copy)
+  uint32_t *dCursorSnap;          // the fill counts before the chunk in flight (rollback of a skewed chunk)
 };
 
 // ------------------------------------------------------------------ kernels
@@ -577,6 +586,7 @@ extern "C" ModgpuTable *modgpuTableCreate(int bits, void *stream)
   t->numbered = 0;
   t->slots = nullptr; t->dEntries = nullptr; t->dError = nullptr; t->dScratch = nullptr; t->hPinned = nullptr;
   t->clearPending = false; t->dBuckets = nullptr; t->bucketBytes = 0; t->dCursors = nullptr; t->dOverflow = nullptr; t->overflowCap = 0;
+  t->bulkOpen = false; t->bulkRoom = t->bulkUsed = t->bulkOvfSeen = 0; t->dCursorSnap = nullptr;
   t->scratchWords = t->nSlots / MG_CP_CHUNK + 1024;
   if (mg_check_cuda(cudaMalloc(&t->slots, t->nSlots * sizeof(MgSlot)), "cudaMalloc(table)", __FILE__, __LINE__) ||
       mg_check_cuda(cudaMalloc(&t->dEntries, 64), "cudaMalloc", __FILE__, __LINE__) ||
@@ -598,14 +608,19 @@ extern "C" void modgpuTableDestroy(ModgpuTable *t)
   if (t->dBuckets) cudaFree(t->dBuckets);
   if (t->dCursors) cudaFree(t->dCursors);
   if (t->dOverflow) cudaFree(t->dOverflow);
+  if (t->dCursorSnap) cudaFree(t->dCursorSnap);
   delete t;
 }
 
 // The clear is lazy: a bulk insert into a logically empty table creates every
 // region itself (region_build_kernel<true>), so the separate 16 B/slot clearing
 // pass only runs when something else touches the table first.
+int mg_table_bulk_close(ModgpuTable *t, cudaStream_t st);
+
+// ... and k-mers still waiting in open buckets (deferred build) are applied before anything reads the table
 static int ensure_cleared(ModgpuTable *t, cudaStream_t st)
 {
+  if (t->bulkOpen) { int rc = mg_table_bulk_close(t, st); if (rc) return rc; }
   if (!t->clearPending) return MODGPU_OK;
   table_clear_kernel<<<grid_for(t->nSlots, 16), 256, 0, st>>>(t->slots, t->nSlots);
   MG_LAUNCH_CHECK("table_clear");
@@ -619,6 +634,7 @@ extern "C" int modgpuTableClear(ModgpuTable *t, void *stream)
   MG_CUDA(cudaMemsetAsync(t->dEntries, 0, 64, st));
   t->numbered = 0;
   t->clearPending = true;
+  t->bulkOpen = false;                                   // k-mers waiting in open buckets are dropped with the rest
   return MODGPU_OK;
 }
 
@@ -626,10 +642,11 @@ extern "C" int modgpuTableClear(ModgpuTable *t, void *stream)
 //   mg_table_bulk_begin   size + zero the per-region buckets for ~expectedN k-mers
 //   (scatter)             bucket_scatter_kernel on a list, or hash_select<SCATTER>
 //   mg_table_bulk_finish  build every region in shared memory, then the overflow
-struct MgBulk { uint32_t slotBits, regionBits, nRegions, cap; uint32_t *cursors; uint64_t *buckets, *overflow; uint64_t overflowCap; uint64_t expected; };
+int mg_table_bulk_close(ModgpuTable *t, cudaStream_t st);
 
 int mg_table_bulk_begin(ModgpuTable *t, uint64_t expectedN, uint64_t maxN, MgBulk *b, cudaStream_t st)
 {
+  if (t->bulkOpen) { int rc = mg_table_bulk_close(t, st); if (rc) return rc; }    // the buckets are about to be reused
   const uint32_t nRegions = (uint32_t)(t->nSlots >> MG_REGION_BITS);
   uint64_t cap64 = expectedN / nRegions + expectedN / (4ull * nRegions) + 64;
   cap64 = (cap64 + 1) & ~1ull;
@@ -711,6 +728,56 @@ int mg_table_bulk_finish(ModgpuTable *t, const MgBulk *b, cudaStream_t st)
   return MODGPU_OK;
 }
 
+// ---- deferred build (modgpuModsetSetAccumulate): the buckets stay open over up to `accum` chunks of about
+// `expected` k-mers each, so that a populated table is read-modify-written once per `accum` chunks instead of once per
+// chunk (93 Gbases into an 8 GiB table: the per-chunk build moved 16 GiB for 0.4 GB of new k-mers).
+//   open      reuse the open buckets when the chunk fits (bucket room and worst-case overflow room), else build what
+//             is waiting and start new buckets; snapshots the fill counts so that the chunk can be taken back
+//   commit    the chunk is in (the host has seen its overflow counter)
+//   rollback  the chunk overflowed the overflow list (pathological skew): restore the fill counts, build what was
+//             there before; the caller repeats the chunk through the list path
+//   close     build the regions from whatever is waiting
+static uint64_t bulk_ovf_need(uint64_t expected) { return 2 * expected + 65536; }
+
+int mg_table_bulk_open(ModgpuTable *t, uint64_t expected, uint32_t accum, MgBulk *b, cudaStream_t st)
+{
+  const size_t curBytes = ((size_t)(t->nSlots >> MG_REGION_BITS) + 16) * sizeof(uint32_t);
+  if (t->bulkOpen && t->bulkUsed + expected <= t->bulkRoom && t->bulkOvfSeen + bulk_ovf_need(expected) <= t->bulk.overflowCap)
+    { if (!t->dCursorSnap) MG_CUDA(cudaMalloc(&t->dCursorSnap, curBytes));
+      MG_CUDA(cudaMemcpyAsync(t->dCursorSnap, t->dCursors, curBytes, cudaMemcpyDeviceToDevice, st));
+      *b = t->bulk;
+      return MODGPU_OK;
+    }
+  if (t->bulkOpen) { int rc = mg_table_bulk_close(t, st); if (rc) return rc; }
+  if (accum < 1) accum = 1;
+  const uint64_t room = expected * accum;
+  int rc = mg_table_bulk_begin(t, room, bulk_ovf_need(expected) + room / 8, b, st);
+  if (rc) return rc;
+  t->bulk = *b; t->bulkOpen = true; t->bulkRoom = room; t->bulkUsed = 0; t->bulkOvfSeen = 0;
+  return MODGPU_OK;
+}
+
+void mg_table_bulk_commit(ModgpuTable *t, uint64_t expected, uint64_t ovfSeen) { t->bulkUsed += expected; t->bulkOvfSeen = ovfSeen; }
+
+int mg_table_bulk_rollback(ModgpuTable *t, cudaStream_t st)
+{
+  if (!t->bulkOpen) return MODGPU_OK;
+  if (!t->bulkUsed) { t->bulkOpen = false; return MODGPU_OK; }          // nothing was waiting before this chunk
+  const size_t curBytes = ((size_t)(t->nSlots >> MG_REGION_BITS) + 16) * sizeof(uint32_t);
+  MG_CUDA(cudaMemcpyAsync(t->dCursors, t->dCursorSnap, curBytes, cudaMemcpyDeviceToDevice, st));
+  return mg_table_bulk_close(t, st);
+}
+
+int mg_table_bulk_close(ModgpuTable *t, cudaStream_t st)
+{
+  if (!t->bulkOpen) return MODGPU_OK;
+  t->bulkOpen = false;
+  if (!t->bulkUsed) return MODGPU_OK;
+  return mg_table_bulk_finish(t, &t->bulk, st);
+}
+
+bool mg_table_bulk_is_open(const ModgpuTable *t) { return t->bulkOpen; }
+
 // Bulk find-or-insert + count of a long list (count mode, any order): 8 B read +
 // 8 B written per k-mer for the scatter, then one streaming pass over the table.
 int mg_table_insert_bulk(ModgpuTable *t, const uint64_t *d_kmers, uint64_t n, cudaStream_t st)
@@ -744,6 +811,7 @@ int mg_table_build_from_buckets(ModgpuTable *t, const uint64_t *d_buckets, const
                                 const uint64_t *d_overflow, uint64_t overflowCap, const uint32_t *d_ovfCounts, cudaStream_t st)
 {
   const uint32_t nRegions = (uint32_t)(t->nSlots >> MG_REGION_BITS);
+  if (t->bulkOpen) { int rc = mg_table_bulk_close(t, st); if (rc) return rc; }
   if (t->clearPending)
     { region_build_multi_kernel<true><<<nRegions, 256, 0, st>>>(t->slots, t->slotBits, d_buckets, d_cursors, cap, nSrc, nRegions, t->dEntries, t->dError);
       t->clearPending = false;
@@ -770,6 +838,7 @@ int mg_table_build_from_peers(ModgpuTable *t, const uint64_t *const *d_buckets, 
                               const uint64_t *const *d_overflow, uint64_t overflowCap, const uint32_t *d_ovfCounts, cudaStream_t st)
 {
   if (nSrc < 1 || nSrc > MODGPU_MAX_PEERS) { mg_set_error("build from peers: %u sources out of range 1..%d", nSrc, MODGPU_MAX_PEERS); return MODGPU_EINVAL; }
+  if (t->bulkOpen) { int rc = mg_table_bulk_close(t, st); if (rc) return rc; }
   const uint32_t nRegions = (uint32_t)(t->nSlots >> MG_REGION_BITS);
   MgPeerSrc src;
   for (uint32_t s = 0; s < MODGPU_MAX_PEERS; ++s) src.p[s] = d_buckets[s < nSrc ? s : 0];
@@ -814,7 +883,7 @@ uint64_t mg_table_bulk_threshold(const ModgpuTable *t) { return t->nSlots / 8; }
 extern "C" uint64_t modgpuTableSlots(const ModgpuTable *t) { return t->nSlots; }
 extern "C" void *modgpuTableDevicePtr(const ModgpuTable *t)
 {
-  if (t->clearPending)
+  if (t->clearPending || t->bulkOpen)
     { ensure_cleared(const_cast<ModgpuTable *>(t), 0);
       cudaStreamSynchronize(0);
     }
@@ -849,6 +918,7 @@ extern "C" int modgpuTableInsert(ModgpuTable *t, const uint64_t *d_kmers, uint64
 extern "C" uint64_t modgpuTableEntries(ModgpuTable *t, void *stream)
 {
   cudaStream_t st = (cudaStream_t)stream;
+  if (t->bulkOpen && mg_table_bulk_close(t, st)) return 0xFFFFFFFFFFFFFFFFull;
   if (mg_check_cuda(cudaMemcpyAsync(t->hPinned, t->dEntries, 16, cudaMemcpyDeviceToHost, st), "entries readback", __FILE__, __LINE__) ||
       mg_check_cuda(cudaStreamSynchronize(st), "cudaStreamSynchronize", __FILE__, __LINE__))
     return 0xFFFFFFFFFFFFFFFFull;

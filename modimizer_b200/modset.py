@@ -285,6 +285,15 @@ class Modset:
             for j in range(len(v)):
                 f.write("%d\t%s\t%d\t%d\n" % (j + 1, kmer_string(v[j], self.k), d[j], i[j]))
 
+    def set_accumulate(self, n_chunks):
+        """deferred build: up to n_chunks device chunks share one region build (include/modgpu.h); a full table is
+        then reported by flush() or by the first reader instead of by add*()"""
+        check(self._lib.modgpuModsetSetAccumulate(self._p, int(n_chunks)), "modsetSetAccumulate")
+
+    def flush(self):
+        """apply the k-mers waiting in the buckets; raises when the table is over its capacity"""
+        check(self._lib.modgpuModsetFlush(self._p), "modsetFlush")
+
     def clear(self):
         """empty the set (the table is rewritten lazily by the next bulk build)"""
         check(self._lib.modgpuModsetClear(self._p), "modsetClear")

@@ -360,6 +360,67 @@ def test_modset_edge_cases(mg, orc):
     ms.close()
 
 
+@pytest.mark.parametrize("accum", [2, 3, 16])
+def test_deferred_build_accumulates_chunks(mg, orc, accum):
+    """modgpuModsetSetAccumulate: the k-mers of several chunks wait in the region buckets and the regions are built once.
+    Same set as the oracle whatever the grouping: reader-triggered flush, explicit flush, a skewed chunk that overflows
+    the overflow list in the middle (rolled back, what was waiting is built, the chunk repeats through the list path),
+    clear with k-mers waiting, back to the immediate mode"""
+    sp = he.read_spec(777, 300000, 42, 3000, 2000)
+    nreads = 2500
+    data = he.reads(sp, 0, nreads)
+    offs = np.arange(nreads + 1, dtype=np.uint64) * np.uint64(3000)
+    skew = np.zeros(400000, np.uint8)                     # poly-A: one k-mer 400k times, 4x what the chunk announces
+    skew[100000:100050] = 1
+    ms = mg.Modset(22, 19, 4, 17)
+    ms.set_flags(255 << 8)                                # always the bucket path
+    ms.set_accumulate(accum)
+    oms = orc.modset_new(22, 19, 4, 17)
+    try:
+        parts = [(data[:3000 * 700], offs[:701]), (data[3000 * 700:3000 * 1500], offs[700:1501] - offs[700]),
+                 (data, offs), (skew, np.array([0, 400000], np.uint64)), (data[:3000 * 900], offs[:901]),
+                 (data[3000 * 1500:], offs[1500:] - offs[1500]), (data, offs)]
+        for i, (d_, o_) in enumerate(parts):
+            assert ms.add(d_, o_, is_ascii=0) == orc.modset_add(oms, d_, o_), i
+            if i == 4:
+                assert ms.max == orc._modset_max(oms)     # a reader in the middle: applies what is waiting
+        ms.flush()
+        gv, gd, gi = ms.sorted_dump(); ov, od, oi = orc.modset_sorted(oms)
+        assert np.array_equal(gv, ov) and np.array_equal(gd, od)
+        assert np.array_equal(ms.histogram(), orc.modset_hist(oms))
+        # k-mers waiting when the set is cleared are dropped with it
+        ms.add(data, offs, is_ascii=0)
+        ms.clear()
+        assert ms.max == 0
+        # a reader without flush(), then back to the immediate mode with k-mers waiting
+        d_, o_ = parts[1]
+        o2 = orc.modset_new(22, 19, 4, 17)
+        assert ms.add(d_, o_, is_ascii=0) == orc.modset_add(o2, d_, o_)
+        assert np.array_equal(ms.histogram(), orc.modset_hist(o2))
+        assert ms.add(d_, o_, is_ascii=0) == orc.modset_add(o2, d_, o_)
+        ms.set_accumulate(1)
+        assert ms.add(data, offs, is_ascii=0) == orc.modset_add(o2, data, offs)
+        gv, gd, gi = ms.sorted_dump(); ov, od, oi = orc.modset_sorted(o2)
+        assert np.array_equal(gv, ov) and np.array_equal(gd, od)
+        orc._modset_free(o2)
+    finally:
+        ms.close(); orc._modset_free(oms)
+
+
+def test_deferred_build_reports_a_full_table_at_the_flush(mg):
+    """deferred mode moves the reference's die() (modset.c:58) from the add to the flush / first reader"""
+    rng = np.random.default_rng(9)
+    n = 2000000
+    data = rng.integers(0, 4, n).astype(np.uint8)
+    ms = mg.Modset(20, 19, 4, 17)          # capacity 2^18 - 2 entries, ~500k distinct modimizers
+    ms.set_flags(255 << 8)
+    ms.set_accumulate(4)
+    ms.add(data, np.array([0, n], np.uint64), is_ascii=0)
+    with pytest.raises(mg.ModgpuError):
+        ms.flush()
+    ms.close()
+
+
 def test_depth_saturation(mg, orc):
     """depth is U16 saturating at 65535 (modutils.c:26): poly-A read, d = 1"""
     n = 70000 + 18

@@ -24,10 +24,14 @@ from modimizer_b200 import synth
 dev = torch.device("cuda:0")
 
 
+ACCUMULATE = 1
+
+
 def count_reads(name, spec, n_reads, k, d, bits, chunk_reads, ont=False):
     """modset build + count of a synthetic readset, chunk by chunk from device memory"""
     L = spec.readLen
     ms = mg.Modset(bits, k, d, 17)
+    ms.set_accumulate(ACCUMULATE)          # > 1: deferred build, several chunks share one pass over the table
     buf = torch.empty(chunk_reads * L + 64, dtype=torch.uint8, device=dev)
     offs = (torch.arange(chunk_reads + 1, dtype=torch.int64, device=dev) * L)
     tot, gpu_ms, bases = 0, 0.0, 0
@@ -40,12 +44,17 @@ def count_reads(name, spec, n_reads, k, d, bits, chunk_reads, ont=False):
         tot += ms.add_device(buf.data_ptr(), offs.data_ptr(), n, n * L)
         e1.record(); torch.cuda.synchronize()
         gpu_ms += e0.elapsed_time(e1); bases += n * L
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ms.flush()                             # what is still waiting in the buckets: part of the timed work
+    e1.record(); torch.cuda.synchronize()
+    gpu_ms += e0.elapsed_time(e1)
     t0 = time.perf_counter()
     h = ms.histogram()
     hist_ms = 1e3 * (time.perf_counter() - t0)
     out = {"config": name, "k": k, "d": d, "tableBits": bits, "bases": bases, "reads": n_reads, "hashes": int(tot),
            "distinct": int(ms.max), "ms": gpu_ms, "gbases_per_s": bases / gpu_ms / 1e6, "histogram_ms": hist_ms,
-           "modal_depth": int(np.argmax(h[2:]) + 2)}
+           "accumulate": ACCUMULATE, "modal_depth": int(np.argmax(h[2:]) + 2)}
     ms.close()
     return out
 
@@ -54,7 +63,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--only", default="0,1,2,3,4")
+    ap.add_argument("--accumulate", type=int, default=8, help="chunks per region build for the read sets (1 = build after every chunk)")
     a = ap.parse_args()
+    global ACCUMULATE
+    ACCUMULATE = a.accumulate
     only = {int(x) for x in a.only.split(",")}
     mg.require_device()
     G = int(3_100_000_000 * a.scale)
