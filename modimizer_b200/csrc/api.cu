@@ -346,6 +346,44 @@ static int stage_chunk(ModgpuModset *ms, const char *bases, const uint64_t *offs
   return MODGPU_OK;
 }
 
+// The same double-buffered staging for the modmap entry points (refmap.cu): chunk c+1 crosses PCIe on the copy stream
+// while the kernels of chunk c run.  begin plans the chunks and starts the first copy; chunk(c) starts the copy of
+// c+1, makes the compute stream wait for c and hands out its device buffers; release(c) marks the buffers reusable.
+struct MgFeed { const char *bases; const uint64_t *offs; std::vector<uint64_t> cuts; };
+
+MgFeed *mg_feed_begin(ModgpuModset *ms, const char *bases, const uint64_t *offs, uint64_t nSeq, uint64_t limit, size_t *nChunks)
+{
+  MgFeed *f = new MgFeed();
+  f->bases = bases; f->offs = offs;
+  plan_chunks(offs, nSeq, limit, f->cuts);
+  *nChunks = f->cuts.size() - 1;
+  if (*nChunks && stage_chunk(ms, bases, offs, f->cuts, 0)) { delete f; return nullptr; }
+  return f;
+}
+
+int mg_feed_chunk(ModgpuModset *ms, MgFeed *f, size_t c, const uint8_t **d_bases, const uint64_t **d_offs, uint64_t *r0, uint64_t *r1)
+{
+  const int b = (int)(c & 1);
+  int rc;
+  if (c + 2 < f->cuts.size() && (rc = stage_chunk(ms, f->bases, f->offs, f->cuts, c + 1))) return rc;
+  MG_CUDA(cudaStreamWaitEvent(ms->stream, ms->evCopied[b], 0));
+  *d_bases = (const uint8_t *)ms->bases[b].p; *d_offs = (const uint64_t *)ms->offs[b].p;
+  *r0 = f->cuts[c]; *r1 = f->cuts[c + 1];
+  return MODGPU_OK;
+}
+
+int mg_feed_release(ModgpuModset *ms, size_t c)
+{
+  MG_CUDA(cudaEventRecord(ms->evFree[c & 1], ms->stream));
+  return MODGPU_OK;
+}
+
+void mg_feed_end(ModgpuModset *ms, MgFeed *f)
+{ // a copy still in flight (early exit) must not outlive the caller's buffers
+  cudaStreamSynchronize(ms->copyStream);
+  delete f;
+}
+
 extern "C" uint64_t modgpuModsetAdd(ModgpuModset *ms, const char *bases, const uint64_t *offs, uint64_t nSeq, int isAscii)
 {
   const uint64_t FAIL = 0xFFFFFFFFFFFFFFFFull;

@@ -37,8 +37,15 @@ cudaStream_t mg_modset_stream(ModgpuModset *ms);
 // scratch of the modset object (api.cu)
 void *mg_modset_kmers(ModgpuModset *ms);
 void *mg_modset_gpos(ModgpuModset *ms);
+// double-buffered staging of host batches (api.cu): the copy of chunk c+1 runs behind the kernels of chunk c
+struct MgFeed;
+MgFeed *mg_feed_begin(ModgpuModset *ms, const char *bases, const uint64_t *offs, uint64_t nSeq, uint64_t limit, size_t *nChunks);
+int mg_feed_chunk(ModgpuModset *ms, MgFeed *f, size_t c, const uint8_t **d_bases, const uint64_t **d_offs, uint64_t *r0, uint64_t *r1);
+int mg_feed_release(ModgpuModset *ms, size_t c);
+void mg_feed_end(ModgpuModset *ms, MgFeed *f);
 
-static const uint64_t MG_REF_CHUNK = 1ull << 31;
+static const uint64_t MG_REF_CHUNK = 1ull << 28;       // bases per staged chunk (whole sequences; a longer sequence is its own chunk)
+static const uint64_t MG_QUERY_CHUNK = 1ull << 27;
 static const uint32_t MG_REF_CAP = 1u << 26;      // modmap.c:363: referenceCreate(ms, 1 << 26)
 
 struct RBuf {
@@ -63,7 +70,7 @@ struct ModgpuReference {
   RBuf index, offset, id;                // per hit                      modmap.c:38-41
   RBuf depth, loc;                       // per modset index, max+1      modmap.c:42,44
   RBuf rev;                              // per hit, grouped by index    modmap.c:43
-  RBuf tmp, tmp2, sortTmp, slot, bases, offs, misc;
+  RBuf tmp, tmp2, sortTmp, slot, misc;
   void *hPinned = nullptr;
 };
 
@@ -140,35 +147,11 @@ static unsigned rgrid(uint64_t n)
 }
 
 // ------------------------------------------------------------------- build
-static void plan(const uint64_t *offs, uint64_t nSeq, uint64_t limit, std::vector<uint64_t> &cuts)
-{
-  cuts.clear(); cuts.push_back(0);
-  uint64_t r = 0;
-  while (r < nSeq)
-    { uint64_t r1 = r + 1;
-      while (r1 < nSeq && offs[r1 + 1] - offs[r] <= limit) ++r1;
-      cuts.push_back(r1); r = r1;
-    }
-}
-
-static int stage(ModgpuReference *R, const char *bases, const uint64_t *offs, uint64_t r0, uint64_t r1, cudaStream_t st)
-{
-  const uint64_t nb = offs[r1] - offs[r0], ns = r1 - r0;
-  int rc;
-  if ((rc = R->bases.ensure(nb + 64, st)) || (rc = R->offs.ensure((ns + 1) * 8, st))) return rc;
-  std::vector<uint64_t> local(ns + 1);
-  for (uint64_t r = 0; r <= ns; ++r) local[r] = offs[r0 + r] - offs[r0];
-  if (nb) MG_CUDA(cudaMemcpyAsync(R->bases.p, bases + offs[r0], nb, cudaMemcpyHostToDevice, st));
-  MG_CUDA(cudaMemcpyAsync(R->offs.p, local.data(), (ns + 1) * 8, cudaMemcpyHostToDevice, st));
-  MG_CUDA(cudaStreamSynchronize(st));              // `local` dies with this scope
-  return MODGPU_OK;
-}
-
 extern "C" void modgpuReferenceDestroy(ModgpuReference *R)
 {
   if (!R) return;
   RBuf *all[] = { &R->index, &R->offset, &R->id, &R->depth, &R->loc, &R->rev, &R->tmp, &R->tmp2, &R->sortTmp,
-                  &R->slot, &R->bases, &R->offs, &R->misc };
+                  &R->slot, &R->misc };
   for (RBuf *b : all) b->release();
   if (R->hPinned) cudaFreeHost(R->hPinned);
   if (R->ms) modgpuModsetDestroy(R->ms);
@@ -192,34 +175,44 @@ extern "C" ModgpuReference *modgpuReferenceBuild(int bits, int k, int w, int see
     if (offs[r + 1] < offs[r] || offs[r + 1] - offs[r] > 0x7FFFFFFFull)
       { mg_set_error("bad length of reference sequence %llu", (unsigned long long)r); RB_FAIL(); }
 
-  std::vector<uint64_t> cuts;
-  plan(offs, nSeq, MG_REF_CHUNK, cuts);
+  // the hit arrays are sized once from the expected density (they still grow if the genome is denser)
+  { const uint64_t guess = offs[nSeq] / (uint64_t)(w > 0 ? w : 1), want = guess + guess / 8 + 4096;
+    const uint64_t n0 = want < MG_REF_CAP ? want : MG_REF_CAP;
+    if (R->index.ensure(n0 * 4, st) || R->offset.ensure(n0 * 4, st) || R->id.ensure(n0 * 4, st)) RB_FAIL();
+  }
+  size_t nChunks = 0;
+  MgFeed *feed = mg_feed_begin(ms, bases, offs, nSeq, MG_REF_CHUNK, &nChunks);
+  if (!feed) RB_FAIL();
+#define RB_FAIL2() do { mg_feed_end(ms, feed); RB_FAIL(); } while (0)
   uint64_t nHits = 0;
-  for (size_t c = 0; c + 1 < cuts.size(); ++c)
-    { const uint64_t r0 = cuts[c], r1 = cuts[c + 1], nb = offs[r1] - offs[r0], ns = r1 - r0;
-      if (nb >= (1ull << 32)) { mg_set_error("reference sequence group exceeds 2^32-1 bases"); RB_FAIL(); }
-      if (stage(R, bases, offs, r0, r1, st)) RB_FAIL();
+  for (size_t c = 0; c < nChunks; ++c)
+    { const uint8_t *dBases; const uint64_t *dOffs; uint64_t r0, r1;
+      if (mg_feed_chunk(ms, feed, c, &dBases, &dOffs, &r0, &r1)) RB_FAIL2();
+      const uint64_t nb = offs[r1] - offs[r0], ns = r1 - r0;
+      if (nb >= (1ull << 32)) { mg_set_error("reference sequence group exceeds 2^32-1 bases"); RB_FAIL2(); }
       uint64_t n = 0;
-      if (mg_modset_select_chunk(ms, (const uint8_t *)R->bases.p, (const uint64_t *)R->offs.p, ns, nb, isAscii, true,
-                                 MODGPU_SEL_ORDERED, &n))
-        RB_FAIL();
-      if (!n) continue;
-      if (nHits + n + 1 >= MG_REF_CAP)               // modmap.c:111: die ("reference size overflow")
-        { mg_set_error("reference size overflow (%llu hits, capacity 2^26)", (unsigned long long)(nHits + n)); RB_FAIL(); }
-      if (R->slot.ensure(n * 4, st) || R->index.ensure((nHits + n) * 4, st, true) ||
-          R->offset.ensure((nHits + n) * 4, st, true) || R->id.ensure((nHits + n) * 4, st, true))
-        RB_FAIL();
-      uint32_t *dIndex = (uint32_t *)R->index.p + nHits, *dOffset = (uint32_t *)R->offset.p + nHits, *dId = (uint32_t *)R->id.p + nHits;
-      // find-or-insert with the multiplicity in the slot count (++ref->depth[index], modmap.c:113)
-      if (mg_table_insert_dev(t, (const uint64_t *)mg_modset_kmers(ms), nullptr, n, (uint32_t *)R->slot.p, 1, st)) RB_FAIL();
-      if (modgpuTableNumber(t, (const uint32_t *)R->slot.p, n, dIndex, st)) RB_FAIL();
-      if (modgpuLocate((const uint32_t *)mg_modset_gpos(ms), n, (const uint64_t *)R->offs.p, ns, dId, dOffset, st)) RB_FAIL();
-      if (r0)
-        { add_const_kernel<<<rgrid(n), 256, 0, st>>>(dId, n, (uint32_t)r0);
-          if (mg_check_cuda(cudaGetLastError(), "add_const", __FILE__, __LINE__)) RB_FAIL();
+      if (mg_modset_select_chunk(ms, dBases, dOffs, ns, nb, isAscii, true, MODGPU_SEL_ORDERED, &n)) RB_FAIL2();
+      if (n)
+        { if (nHits + n + 1 >= MG_REF_CAP)               // modmap.c:111: die ("reference size overflow")
+            { mg_set_error("reference size overflow (%llu hits, capacity 2^26)", (unsigned long long)(nHits + n)); RB_FAIL2(); }
+          if (R->slot.ensure(n * 4, st) || R->index.ensure((nHits + n) * 4, st, true) ||
+              R->offset.ensure((nHits + n) * 4, st, true) || R->id.ensure((nHits + n) * 4, st, true))
+            RB_FAIL2();
+          uint32_t *dIndex = (uint32_t *)R->index.p + nHits, *dOffset = (uint32_t *)R->offset.p + nHits, *dId = (uint32_t *)R->id.p + nHits;
+          // find-or-insert with the multiplicity in the slot count (++ref->depth[index], modmap.c:113)
+          if (mg_table_insert_dev(t, (const uint64_t *)mg_modset_kmers(ms), nullptr, n, (uint32_t *)R->slot.p, 1, st)) RB_FAIL2();
+          if (modgpuTableNumber(t, (const uint32_t *)R->slot.p, n, dIndex, st)) RB_FAIL2();
+          if (modgpuLocate((const uint32_t *)mg_modset_gpos(ms), n, dOffs, ns, dId, dOffset, st)) RB_FAIL2();
+          if (r0)
+            { add_const_kernel<<<rgrid(n), 256, 0, st>>>(dId, n, (uint32_t)r0);
+              if (mg_check_cuda(cudaGetLastError(), "add_const", __FILE__, __LINE__)) RB_FAIL2();
+            }
+          nHits += n;
         }
-      nHits += n;
+      if (mg_feed_release(ms, c)) RB_FAIL2();
     }
+  mg_feed_end(ms, feed);
+#undef RB_FAIL2
   if (modgpuTableEntries(t, st) == 0xFFFFFFFFFFFFFFFFull) RB_FAIL();
   R->max = (uint32_t)nHits;
   mg_modset_mark(ms, false, true);                   // numbered; ms->depth stays 0 in modmap
@@ -259,7 +252,7 @@ extern "C" ModgpuReference *modgpuReferenceBuild(int bits, int k, int w, int see
         RB_FAIL();
     }
   if (mg_check_cuda(cudaStreamSynchronize(st), "sync", __FILE__, __LINE__)) RB_FAIL();
-  R->bases.release(); R->tmp.release(); R->tmp2.release(); R->sortTmp.release(); R->slot.release();
+  R->tmp.release(); R->tmp2.release(); R->sortTmp.release(); R->slot.release();
 #undef RB_FAIL
   return R;
 }
@@ -299,35 +292,38 @@ extern "C" uint64_t modgpuReferenceQuery(ModgpuReference *R, const char *bases, 
   for (uint64_t r = 0; r < nSeq; ++r)
     if (offs[r + 1] < offs[r] || offs[r + 1] - offs[r] > 0x7FFFFFFFull)
       { mg_set_error("bad length of query sequence %llu", (unsigned long long)r); return FAIL; }
-  std::vector<uint64_t> cuts;
-  plan(offs, nSeq, 1ull << 30, cuts);
+  size_t nChunks = 0;
+  MgFeed *feed = mg_feed_begin(ms, bases, offs, nSeq, MG_QUERY_CHUNK, &nChunks);
+  if (!feed) return FAIL;
+#define RQ_FAIL() do { mg_feed_end(ms, feed); return FAIL; } while (0)
   uint64_t total = 0;
   seedOff[0] = 0;
-  for (size_t c = 0; c + 1 < cuts.size(); ++c)
-    { const uint64_t r0 = cuts[c], r1 = cuts[c + 1], nb = offs[r1] - offs[r0], ns = r1 - r0;
-      if (nb >= (1ull << 32)) { mg_set_error("query sequence group exceeds 2^32-1 bases"); return FAIL; }
-      if (stage(R, bases, offs, r0, r1, st)) return FAIL;
+  for (size_t c = 0; c < nChunks; ++c)
+    { // the reads of chunk c+1 cross PCIe while chunk c is looked up and its seeds travel back
+      const uint8_t *dBases; const uint64_t *dOffs; uint64_t r0, r1;
+      if (mg_feed_chunk(ms, feed, c, &dBases, &dOffs, &r0, &r1)) RQ_FAIL();
+      const uint64_t nb = offs[r1] - offs[r0], ns = r1 - r0;
+      if (nb >= (1ull << 32)) { mg_set_error("query sequence group exceeds 2^32-1 bases"); RQ_FAIL(); }
       uint64_t n = 0;
-      if (mg_modset_select_chunk(ms, (const uint8_t *)R->bases.p, (const uint64_t *)R->offs.p, ns, nb, isAscii, true,
-                                 MODGPU_SEL_ORDERED, &n))
-        return FAIL;
+      if (mg_modset_select_chunk(ms, dBases, dOffs, ns, nb, isAscii, true, MODGPU_SEL_ORDERED, &n)) RQ_FAIL();
       // device scratch: aux, readId, pos, seedIndex, hitId[2], hitOffset[2] per seed; counters, seedOff per read
       const size_t perSeed = 4 * 8, need = n * perSeed + (ns + 1) * (16 + 8) + 256;
-      if (R->tmp.ensure(need, st)) return FAIL;
+      if (R->tmp.ensure(need, st)) RQ_FAIL();
       uint32_t *dAux = (uint32_t *)R->tmp.p, *dRead = dAux + n, *dPos = dRead + n, *dIdx = dPos + n;
       uint32_t *dHitId = dIdx + n, *dHitOff = dHitId + 2 * n;
       uint64_t *dSeedOff = (uint64_t *)(((uintptr_t)(dHitOff + 2 * n) + 15) & ~(uintptr_t)15);
       int32_t *dCtr = (int32_t *)(dSeedOff + ns + 1);
-      if (mg_check_cuda(cudaMemsetAsync(dCtr, 0, ns * 16, st), "memset", __FILE__, __LINE__)) return FAIL;
+      if (mg_check_cuda(cudaMemsetAsync(dCtr, 0, ns * 16, st), "memset", __FILE__, __LINE__)) RQ_FAIL();
       if (n)
-        { if (mg_table_lookup_dev(t, (const uint64_t *)mg_modset_kmers(ms), nullptr, n, dAux, st)) return FAIL;
-          if (modgpuLocate((const uint32_t *)mg_modset_gpos(ms), n, (const uint64_t *)R->offs.p, ns, dRead, dPos, st)) return FAIL;
+        { if (mg_table_lookup_dev(t, (const uint64_t *)mg_modset_kmers(ms), nullptr, n, dAux, st)) RQ_FAIL();
+          if (modgpuLocate((const uint32_t *)mg_modset_gpos(ms), n, dOffs, ns, dRead, dPos, st)) RQ_FAIL();
           query_resolve_kernel<<<rgrid(n), 256, 0, st>>>(dAux, n, dRead, (const uint32_t *)R->loc.p, (const uint32_t *)R->rev.p,
                                                          (const uint32_t *)R->id.p, (const uint32_t *)R->offset.p, dIdx, dHitId, dHitOff, dCtr);
-          if (mg_check_cuda(cudaGetLastError(), "query_resolve", __FILE__, __LINE__)) return FAIL;
+          if (mg_check_cuda(cudaGetLastError(), "query_resolve", __FILE__, __LINE__)) RQ_FAIL();
         }
       seed_offsets_kernel<<<rgrid(ns + 1), 256, 0, st>>>(dRead, n, ns, total, dSeedOff);
-      if (mg_check_cuda(cudaGetLastError(), "seed_offsets", __FILE__, __LINE__)) return FAIL;
+      if (mg_check_cuda(cudaGetLastError(), "seed_offsets", __FILE__, __LINE__)) RQ_FAIL();
+      if (mg_feed_release(ms, c)) RQ_FAIL();             // the chunk's bases are no longer needed
       // results back to the caller (clipped to cap)
       uint64_t room = total < cap ? cap - total : 0, take = n < room ? n : room;
       if (take)
@@ -335,13 +331,15 @@ extern "C" uint64_t modgpuReferenceQuery(ModgpuReference *R, const char *bases, 
               mg_check_cuda(cudaMemcpyAsync(seedPos + total, dPos, take * 4, cudaMemcpyDeviceToHost, st), "d2h", __FILE__, __LINE__) ||
               mg_check_cuda(cudaMemcpyAsync(hitId + 2 * total, dHitId, take * 8, cudaMemcpyDeviceToHost, st), "d2h", __FILE__, __LINE__) ||
               mg_check_cuda(cudaMemcpyAsync(hitOffset + 2 * total, dHitOff, take * 8, cudaMemcpyDeviceToHost, st), "d2h", __FILE__, __LINE__))
-            return FAIL;
+            RQ_FAIL();
         }
       if (mg_check_cuda(cudaMemcpyAsync(seedOff + r0, dSeedOff, (ns + 1) * 8, cudaMemcpyDeviceToHost, st), "d2h", __FILE__, __LINE__) ||
           mg_check_cuda(cudaMemcpyAsync(counters + 4 * r0, dCtr, ns * 16, cudaMemcpyDeviceToHost, st), "d2h", __FILE__, __LINE__) ||
           mg_check_cuda(cudaStreamSynchronize(st), "sync", __FILE__, __LINE__))
-        return FAIL;
+        RQ_FAIL();
       total += n;
     }
+  mg_feed_end(ms, feed);
+#undef RQ_FAIL
   return total;
 }

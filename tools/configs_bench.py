@@ -119,8 +119,11 @@ def main():
         from modimizer_b200 import _lib
         lib = _lib.load()
         cap = chunk * 400
-        so = np.zeros(chunk + 1, np.uint64); si = np.zeros(cap, np.uint32); spos = np.zeros(cap, np.uint32)
-        hid = np.zeros(2 * cap, np.uint32); hoff = np.zeros(2 * cap, np.uint32); ctr = np.zeros(4 * chunk, np.int32)
+        # in pinned memory (modgpuHostAlloc / cudaMallocHost in a C caller): the seeds come back by DMA
+        def pinned(n, dt):
+            return torch.zeros(n, dtype=dt, pin_memory=True).numpy()
+        so = pinned(chunk + 1, torch.int64).view(np.uint64); si = pinned(cap, torch.int32).view(np.uint32); spos = pinned(cap, torch.int32).view(np.uint32)
+        hid = pinned(2 * cap, torch.int32).view(np.uint32); hoff = pinned(2 * cap, torch.int32).view(np.uint32); ctr = pinned(4 * chunk, torch.int32)
         for first in range(0, n_reads, chunk):
             n = min(chunk, n_reads - first)
             synth.reads_device(sp, first, n, True, buf.data_ptr())
