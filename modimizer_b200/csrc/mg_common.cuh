@@ -165,14 +165,20 @@ MGHD uint32_t mg_blocked_mask(uint64_t ends, uint32_t k)
 // followed by the `% w` of modRCiterator/modRCnext (seqhash.c:171,190)
 MGHD bool mg_eval_window(const MgKHasher &H, const MgRun &R, uint32_t i, uint64_t *kmer, bool *isF)
 {
-  uint64_t f = mg_run_fwd(R, i, H.mask), r = mg_run_rc(R, i, H.mask);
-  uint64_t hf = mg_hash(H, f), hr = mg_hash(H, r);
-  bool fw = hf < hr;
-  uint64_t hv = fw ? hf : hr;
+  // The hashes are never shifted into place: h = P >> shift is monotone in the masked product P & ~(2^shift - 1)
+  // = h << shift, so the canonical choice compares masked products; "the tz low bits of h are zero" is one AND
+  // with a constant; and the odd part of d divides h exactly when it divides h << shift (it is coprime to 2), which
+  // the exact-division test answers on the masked product itself.  9 instructions fewer per window than
+  // shift - compare - shift - multiply (the full scan of a generic d evaluates every window).
+  const uint64_t f = mg_run_fwd(R, i, H.mask), r = mg_run_rc(R, i, H.mask);
+  const uint64_t keep = ~((((uint64_t)1) << H.shift) - 1);
+  const uint64_t pf = (f * H.factor) & keep, pr = (r * H.factor) & keep;
+  const bool fw = pf < pr;                                     // hashF < hashR (ties go reverse, seqhash.c:66-67)
+  const uint64_t pm = fw ? pf : pr;
   *kmer = fw ? f : r;
   *isF = fw;
-  bool lowOk = (hv & ((1ull << H.tz) - 1)) == 0;
-  bool oddOk = (hv >> H.tz) * H.oddInv <= H.oddLim;
+  const bool lowOk = (pm & (((((uint64_t)1) << H.tz) - 1) << H.shift)) == 0;
+  const bool oddOk = pm * H.oddInv <= H.oddLim;
   return lowOk && oddOk;
 }
 
@@ -187,13 +193,15 @@ MGHD bool mg_eval_single(const MgKHasher &H, uint64_t w0, uint64_t w1, uint32_t 
   uint64_t f = (sh >= 64) ? (w0 >> (sh - 64)) : ((w0 << (64 - sh)) | (w1 >> sh));
   f &= H.mask;
   const uint64_t r = (~mg_pairrev64(f)) >> H.shift;
-  uint64_t hf = mg_hash(H, f), hr = mg_hash(H, r);
-  bool fw = hf < hr;
-  uint64_t hv = fw ? hf : hr;
+  // masked products instead of shifted hashes, as in mg_eval_window
+  const uint64_t keep = ~((((uint64_t)1) << H.shift) - 1);
+  const uint64_t pf = (f * H.factor) & keep, pr = (r * H.factor) & keep;
+  const bool fw = pf < pr;
+  const uint64_t pm = fw ? pf : pr;
   *kmer = fw ? f : r;
   *isF = fw;
-  bool lowOk = (hv & ((1ull << H.tz) - 1)) == 0;
-  bool oddOk = (H.oddInv == 1) || ((hv >> H.tz) * H.oddInv <= H.oddLim);    // odd part 1: d is a power of two
+  const bool lowOk = (pm & (((((uint64_t)1) << H.tz) - 1) << H.shift)) == 0;
+  const bool oddOk = (H.oddInv == 1) || (pm * H.oddInv <= H.oddLim);    // odd part 1: d is a power of two
   return lowOk && oddOk;
 }
 

@@ -31,7 +31,8 @@ def count_reads(name, spec, n_reads, k, d, bits, chunk_reads, ont=False):
     """modset build + count of a synthetic readset, chunk by chunk from device memory"""
     L = spec.readLen
     ms = mg.Modset(bits, k, d, 17)
-    ms.set_accumulate(ACCUMULATE)          # > 1: deferred build, several chunks share one pass over the table
+    if n_reads > chunk_reads:
+        ms.set_accumulate(ACCUMULATE)      # > 1: deferred build, several chunks share one pass over the table
     buf = torch.empty(chunk_reads * L + 64, dtype=torch.uint8, device=dev)
     offs = (torch.arange(chunk_reads + 1, dtype=torch.int64, device=dev) * L)
     tot, gpu_ms, bases = 0, 0.0, 0
@@ -54,7 +55,7 @@ def count_reads(name, spec, n_reads, k, d, bits, chunk_reads, ont=False):
     hist_ms = 1e3 * (time.perf_counter() - t0)
     out = {"config": name, "k": k, "d": d, "tableBits": bits, "bases": bases, "reads": n_reads, "hashes": int(tot),
            "distinct": int(ms.max), "ms": gpu_ms, "gbases_per_s": bases / gpu_ms / 1e6, "histogram_ms": hist_ms,
-           "accumulate": ACCUMULATE, "modal_depth": int(np.argmax(h[2:]) + 2)}
+           "accumulate": ACCUMULATE if n_reads > chunk_reads else 1, "modal_depth": int(np.argmax(h[2:]) + 2)}
     ms.close()
     return out
 
