@@ -276,8 +276,11 @@ static int add_chunk_device(ModgpuModset *ms, const uint8_t *d_bases, const uint
   uint64_t n = 0;
   int rc;
   const uint64_t expected = nBases / (uint64_t)ms->hasher.w;
+  // the bucket path pays one pass over the table per build: worth it when the k-mers sharing that pass (this chunk,
+  // or up to `accumulate` chunks in deferred mode) are at least 1/8 of the slots
   const bool fuse = !ms->exactOrder && ms->hasher.w >= 4 && !(ms->selFlags & 0x10) &&
-                    (ms->regionBits == 254 || (ms->regionBits < 0 && expected >= mg_table_bulk_threshold(ms->table)));
+                    (ms->regionBits == 254 ||
+                     (ms->regionBits < 0 && expected * (uint64_t)ms->accumulate >= mg_table_bulk_threshold(ms->table)));
   if (fuse)
     { rc = add_chunk_fused(ms, d_bases, d_offs, nSeq, nBases, isAscii, expected, nHashes);
       if (rc <= 0) return rc;

@@ -40,16 +40,16 @@ def count_reads(name, spec, n_reads, k, d, bits, chunk_reads, ont=False):
         n = min(chunk_reads, n_reads - first)
         synth.reads_device(spec, first, n, ont, buf.data_ptr())
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        # the library works on its own stream: wall clock between two device-wide synchronisations, so that work a
+        # call leaves in flight (deferred mode returns before a direct insert has finished) is inside the timed region
+        t0 = time.perf_counter()
         tot += ms.add_device(buf.data_ptr(), offs.data_ptr(), n, n * L)
-        e1.record(); torch.cuda.synchronize()
-        gpu_ms += e0.elapsed_time(e1); bases += n * L
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+        torch.cuda.synchronize()
+        gpu_ms += 1e3 * (time.perf_counter() - t0); bases += n * L
+    t0 = time.perf_counter()
     ms.flush()                             # what is still waiting in the buckets: part of the timed work
-    e1.record(); torch.cuda.synchronize()
-    gpu_ms += e0.elapsed_time(e1)
+    torch.cuda.synchronize()
+    gpu_ms += 1e3 * (time.perf_counter() - t0)
     t0 = time.perf_counter()
     h = ms.histogram()
     hist_ms = 1e3 * (time.perf_counter() - t0)
