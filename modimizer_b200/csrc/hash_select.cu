@@ -130,6 +130,26 @@ __device__ __forceinline__ uint32_t scan_run(const MgKHasher &H, const MgRun &R)
               : "+r"(m) : "r"(mn), "r"(H.pfLim), "r"(1u << i));
         }
     }
+  else if (H.shift <= 32)                              // k >= 16 (kernel-uniform): the 32-bit evaluation of mg_common.cuh
+    { const MgEval32 E = mg_eval32_prepare(H);
+      const MgRun32 Q = mg_run32(R);
+      if (H.tz == 0)
+        {
+#pragma unroll
+          for (int i = 0; i < MG_RUN; ++i)
+            { const bool ok = mg_selected32<true>(E, Q, i);
+              asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p or.b32 %0, %0, %2;\n\t}" : "+r"(m) : "r"((uint32_t)ok), "r"(1u << i));
+            }
+        }
+      else
+        {
+#pragma unroll
+          for (int i = 0; i < MG_RUN; ++i)
+            { const bool ok = mg_selected32<false>(E, Q, i);
+              asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p or.b32 %0, %0, %2;\n\t}" : "+r"(m) : "r"((uint32_t)ok), "r"(1u << i));
+            }
+        }
+    }
   else
     {
 #pragma unroll

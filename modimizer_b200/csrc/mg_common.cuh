@@ -182,6 +182,83 @@ MGHD bool mg_eval_window(const MgKHasher &H, const MgRun &R, uint32_t i, uint64_
   return lowOk && oddOk;
 }
 
+// ---- the full scan of a generic d (tz < 3: odd d such as the reference's default 31, 2*odd, 4*odd) evaluates EVERY
+// window, so its instruction count is the kernel's.  For k >= 16 (shift <= 32) the same test in explicit 32-bit
+// pieces: the k-mer's low word needs no mask (2k >= 32), the masked product keeps its whole high word, one funnel
+// shift per k-mer word, three multiply-adds per 64-bit product, and for an odd d no low-bit test at all.
+// 24-26 instructions per window instead of 38 (ncu prof_r01_generic).  Same result as mg_eval_window (checked
+// position by position on the host, tests/test_math_host.py).
+struct MgRun32 { uint32_t y[4], r[4]; };   // y[3]:y[2] = R.yhi, y[1]:y[0] = R.ylo; r[1]:r[0] = R.rlo, r[3]:r[2] = R.rhi
+
+MGHD MgRun32 mg_run32(const MgRun &R)
+{
+  MgRun32 Q;
+  Q.y[3] = (uint32_t)(R.yhi >> 32); Q.y[2] = (uint32_t)R.yhi; Q.y[1] = (uint32_t)(R.ylo >> 32); Q.y[0] = (uint32_t)R.ylo;
+  Q.r[0] = (uint32_t)R.rlo; Q.r[1] = (uint32_t)(R.rlo >> 32); Q.r[2] = (uint32_t)R.rhi; Q.r[3] = (uint32_t)(R.rhi >> 32);
+  return Q;
+}
+
+MGHD uint32_t mg_fl32(uint32_t lo, uint32_t hi, uint32_t s)   // high word of (hi:lo) << s, 0 <= s < 32
+{
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_l(lo, hi, s);
+#else
+  return s ? ((hi << s) | (lo >> (32 - s))) : hi;
+#endif
+}
+
+MGHD uint32_t mg_fr32(uint32_t lo, uint32_t hi, uint32_t s)   // low word of (hi:lo) >> s, 0 <= s < 32
+{
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(lo, hi, s);
+#else
+  return s ? ((lo >> s) | (hi << (32 - s))) : lo;
+#endif
+}
+
+// constants of the 32-bit evaluation (kernel-uniform; the compiler keeps them in registers across the unrolled scan)
+struct MgEval32 { uint32_t fLo, fHi, maskHi, keepLo, lowLo, lowHi, invLo, invHi, limLo, limHi; };
+
+MGHD MgEval32 mg_eval32_prepare(const MgKHasher &H)             // requires H.shift <= 32
+{
+  MgEval32 E;
+  E.fLo = (uint32_t)H.factor; E.fHi = (uint32_t)(H.factor >> 32);
+  E.maskHi = (uint32_t)(H.mask >> 32);
+  const uint64_t keep = ~((((uint64_t)1) << H.shift) - 1);
+  E.keepLo = (uint32_t)keep;
+  const uint64_t low = ((((uint64_t)1) << H.tz) - 1) << H.shift;
+  E.lowLo = (uint32_t)low; E.lowHi = (uint32_t)(low >> 32);
+  E.invLo = (uint32_t)H.oddInv; E.invHi = (uint32_t)(H.oddInv >> 32);
+  E.limLo = (uint32_t)H.oddLim; E.limHi = (uint32_t)(H.oddLim >> 32);
+  return E;
+}
+
+template <bool ODD>
+MGHD bool mg_selected32(const MgEval32 &E, const MgRun32 &Q, uint32_t i)
+{
+  const uint32_t s = (2 * i) & 31u;
+  const uint32_t o = (i < 16) ? 1u : 0u, p = 1u - o;
+  const uint32_t fl = mg_fl32(Q.y[o], Q.y[o + 1], s), fh = mg_fl32(Q.y[o + 1], Q.y[o + 2], s) & E.maskHi;
+  const uint32_t rl = mg_fr32(Q.r[p], Q.r[p + 1], s), rh = mg_fr32(Q.r[p + 1], Q.r[p + 2], s) & E.maskHi;
+  // (branch-free on purpose: 64-bit compares are two ISETP, the short-circuit forms compiled to branches)
+  const uint64_t wf = (uint64_t)fl * E.fLo, wr = (uint64_t)rl * E.fLo;
+  const uint32_t pfh = (uint32_t)(wf >> 32) + fl * E.fHi + fh * E.fLo, pfl = (uint32_t)wf;
+  const uint32_t prh = (uint32_t)(wr >> 32) + rl * E.fHi + rh * E.fLo, prl = (uint32_t)wr;
+  // only the DECISION is wanted here, and it depends on min(hashF, hashR) alone: the smaller whole product has the
+  // smaller-or-equal hash, and on a tie of the hashes either product carries that hash - so the products are compared
+  // unmasked and the bits below the hash are dropped once, after the choice (the strand, where ties matter -
+  // seqhash.c:66-67 - is decided exactly by mg_eval_single when the window is extracted)
+  const uint64_t pf = ((uint64_t)pfh << 32) | pfl, pr = ((uint64_t)prh << 32) | prl;
+  const uint64_t pm = (pf < pr) ? pf : pr;
+  const uint32_t ml = (uint32_t)pm & E.keepLo, mh = (uint32_t)(pm >> 32);
+  const uint64_t wq = (uint64_t)ml * E.invLo;
+  const uint32_t qh = (uint32_t)(wq >> 32) + ml * E.invHi + mh * E.invLo;
+  const uint64_t q = ((uint64_t)qh << 32) | (uint32_t)wq, lim = ((uint64_t)E.limHi << 32) | E.limLo;
+  bool ok = q <= lim;
+  if (!ODD) ok = ok & (((ml & E.lowLo) | (mh & E.lowHi)) == 0u);
+  return ok;
+}
+
 // The same for ONE window given the run's two packed words (phase 3 of the
 // kernel, where only the few queued windows are evaluated): the forward k-mer
 // is a bit field of w0:w1 and the reverse complement is computed from the k-mer

@@ -73,6 +73,16 @@ int64_t hm_select(int k, int d, uint64_t factor1, const uint8_t *bytes, uint64_t
         }
       else
         { for (uint32_t i = 0; i < 32; ++i) { uint64_t km; bool f; if (mg_eval_window(H, R, i, &km, &f)) sel |= 1u << i; }
+          if (H.shift <= 32)                 // the kernel's 32-bit evaluation of the full scan (k >= 16) must agree everywhere
+            { const MgEval32 E = mg_eval32_prepare(H);
+              const MgRun32 Q = mg_run32(R);
+              uint32_t s32 = 0, s32b = 0;
+              for (uint32_t i = 0; i < 32; ++i)
+                { if (mg_selected32<false>(E, Q, i)) s32 |= 1u << i;
+                  if (H.tz == 0 && mg_selected32<true>(E, Q, i)) s32b |= 1u << i;
+                }
+              if (s32 != sel || (H.tz == 0 && s32b != sel)) return -3000000 - (int64_t)p0;
+            }
           sel &= usable;
         }
       for (uint32_t i = 0; i < 32; ++i)

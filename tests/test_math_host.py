@@ -75,6 +75,24 @@ def test_select_matches_oracle(orc, prefilter):
         assert np.array_equal(km, ek) and np.array_equal(gp.astype(np.int64), ep) and np.array_equal(isf, ef), (k, d, seed, trial)
 
 
+@pytest.mark.parametrize("k", [16, 17, 19, 24, 31])
+def test_full_scan_32bit_evaluation(orc, k):
+    """the kernel's 32-bit evaluation of the generic-d full scan (mg_selected32, k >= 16) against the oracle and, inside
+    the host build, against the 64-bit evaluation at every window: odd d, 2*odd, 4*odd, poly-A, AT repeats"""
+    rng = np.random.default_rng(100 + k)
+    for d in (31, 1, 3, 5, 62, 124, 2, 4, 999, 65537):
+        f1 = orc.hasher(k, d, 17)["factor1"]
+        lens = rng.integers(0, 4000, 6)
+        offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+        n = int(offs[-1])
+        codes = rng.integers(0, 4, max(n, 1)).astype(np.uint8)
+        codes[int(offs[1]):int(offs[2])] = 0
+        codes[int(offs[2]):int(offs[3])] = np.tile(np.array([0, 3], np.uint8), n)[:int(offs[3] - offs[2])]
+        ek, ep, ef = oracle_select(orc, k, d, 17, codes, offs)
+        km, gp, isf = he.select(k, d, f1, codes[:n], offs, prefilter=0)
+        assert np.array_equal(km, ek) and np.array_equal(gp.astype(np.int64), ep) and np.array_equal(isf, ef), (k, d)
+
+
 @pytest.mark.parametrize("k,d", [(31, 64), (31, 32), (31, 8), (31, 192), (30, 16), (30, 8), (31, 128), (19, 32)])
 def test_table_prefilter_equals_arithmetic_prefilter(k, d):
     """mg_lut_scan (one shared-memory lookup per 4 positions) marks exactly the windows the
