@@ -233,6 +233,24 @@ MGHD MgEval32 mg_eval32_prepare(const MgKHasher &H)             // requires H.sh
   return E;
 }
 
+// low 64 bits of (ah:al) * (bh:bl) as two words: one wide multiply and two multiply-adds into its high word.
+// Spelled out in PTX on the device: from the C expression the compiler built 64-bit additions of zero-extended
+// halves, four extra ALU-pipe instructions per product in a loop that is ALU-pipe bound.
+MGHD void mg_mul64lo(uint32_t al, uint32_t ah, uint32_t bl, uint32_t bh, uint32_t *lo, uint32_t *hi)
+{
+#if defined(__CUDA_ARCH__)
+  uint32_t l, h;
+  asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %4;\n\tmov.b64 {%0, %1}, t;\n\t"
+      "mad.lo.u32 %1, %2, %5, %1;\n\tmad.lo.u32 %1, %3, %4, %1;\n\t}"
+      : "=&r"(l), "=&r"(h) : "r"(al), "r"(ah), "r"(bl), "r"(bh));
+  *lo = l; *hi = h;
+#else
+  const uint64_t w = (uint64_t)al * bl;
+  *lo = (uint32_t)w;
+  *hi = (uint32_t)(w >> 32) + al * bh + ah * bl;
+#endif
+}
+
 template <bool ODD>
 MGHD bool mg_selected32(const MgEval32 &E, const MgRun32 &Q, uint32_t i)
 {
@@ -241,9 +259,9 @@ MGHD bool mg_selected32(const MgEval32 &E, const MgRun32 &Q, uint32_t i)
   const uint32_t fl = mg_fl32(Q.y[o], Q.y[o + 1], s), fh = mg_fl32(Q.y[o + 1], Q.y[o + 2], s) & E.maskHi;
   const uint32_t rl = mg_fr32(Q.r[p], Q.r[p + 1], s), rh = mg_fr32(Q.r[p + 1], Q.r[p + 2], s) & E.maskHi;
   // (branch-free on purpose: 64-bit compares are two ISETP, the short-circuit forms compiled to branches)
-  const uint64_t wf = (uint64_t)fl * E.fLo, wr = (uint64_t)rl * E.fLo;
-  const uint32_t pfh = (uint32_t)(wf >> 32) + fl * E.fHi + fh * E.fLo, pfl = (uint32_t)wf;
-  const uint32_t prh = (uint32_t)(wr >> 32) + rl * E.fHi + rh * E.fLo, prl = (uint32_t)wr;
+  uint32_t pfl, pfh, prl, prh;
+  mg_mul64lo(fl, fh, E.fLo, E.fHi, &pfl, &pfh);
+  mg_mul64lo(rl, rh, E.fLo, E.fHi, &prl, &prh);
   // only the DECISION is wanted here, and it depends on min(hashF, hashR) alone: the smaller whole product has the
   // smaller-or-equal hash, and on a tie of the hashes either product carries that hash - so the products are compared
   // unmasked and the bits below the hash are dropped once, after the choice (the strand, where ties matter -
@@ -251,9 +269,9 @@ MGHD bool mg_selected32(const MgEval32 &E, const MgRun32 &Q, uint32_t i)
   const uint64_t pf = ((uint64_t)pfh << 32) | pfl, pr = ((uint64_t)prh << 32) | prl;
   const uint64_t pm = (pf < pr) ? pf : pr;
   const uint32_t ml = (uint32_t)pm & E.keepLo, mh = (uint32_t)(pm >> 32);
-  const uint64_t wq = (uint64_t)ml * E.invLo;
-  const uint32_t qh = (uint32_t)(wq >> 32) + ml * E.invHi + mh * E.invLo;
-  const uint64_t q = ((uint64_t)qh << 32) | (uint32_t)wq, lim = ((uint64_t)E.limHi << 32) | E.limLo;
+  uint32_t ql, qh;
+  mg_mul64lo(ml, mh, E.invLo, E.invHi, &ql, &qh);
+  const uint64_t q = ((uint64_t)qh << 32) | ql, lim = ((uint64_t)E.limHi << 32) | E.limLo;
   bool ok = q <= lim;
   if (!ODD) ok = ok & (((ml & E.lowLo) | (mh & E.lowHi)) == 0u);
   return ok;
