@@ -510,11 +510,24 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, LUTK ? 3 : 2) hash_count_kerne
       { const uint64_t p0 = tileBase + (uint64_t)run0 * MG_RUN;
         if (LUTK)
           mg_lut_scan<LUTK ? LUTK : 31>(sLut, w0, w1, w2, &m0, &m1);
-        else
+        else if (PREFILTER)
           { const MgRun RA = mg_run_prepare(w0, w1, H.k);
             m0 = scan_run<PREFILTER>(H, RA);
             const MgRun RB = mg_run_prepare(w1, w2, H.k);
             m1 = scan_run<PREFILTER>(H, RB);
+          }
+        else
+          { // the full scan is ~700 unrolled instructions per run: ONE copy, executed twice, keeps the tile loop
+            // inside the 32 KB instruction cache (two copies: 21 % of the stall samples were instruction fetches)
+            uint64_t wa = w0, wb = w1;
+            m0 = 0; m1 = 0;
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h)
+              { const MgRun RR = mg_run_prepare(wa, wb, H.k);
+                const uint32_t mh = scan_run<PREFILTER>(H, RR);
+                if (h == 0) m0 = mh; else m1 = mh;
+                wa = w1; wb = w2;
+              }
           }
         // windows that would span two sequences or run off the batch are not usable; a tile with no sequence end
         // in sight that lies inside the batch (nearly all of them on long sequences) skips the whole computation
