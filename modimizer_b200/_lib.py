@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmodgpu.so")
+# MODGPU_LIB: another build of the same library (A/B runs of kernel variants); the default is the in-tree build
+LIB_PATH = os.environ.get("MODGPU_LIB") or os.path.join(_HERE, "libmodgpu.so")
 
 u64 = C.c_uint64
 u32 = C.c_uint32
