@@ -88,6 +88,8 @@ int modgpuMarkEnds(const uint64_t *d_offs, uint64_t nSeq, uint64_t nBases,
 #define MODGPU_SEL_NOFUSE 16     /* modset add: keep K2 and the bucket scatter of K3 as separate kernels */
 #define MODGPU_SEL_NOFUSEPACK 32 /* modset add: keep K1 as a separate kernel (packed stream through HBM) */
 #define MODGPU_SEL_NOLUT 64      /* count mode: arithmetic prefilter instead of the shared-memory candidate table */
+#define MODGPU_SEL_APPEND 128    /* modgpuModsetSelectBuckets*: keep the fill counts, append to the buckets of the previous
+                                    batches (multi-GPU deferred build: several batches share one peer build) */
 
 /* workspace bytes modgpuHashSelect needs for nBases (look-back descriptors) */
 uint64_t modgpuHashSelectWorkspace(uint64_t nBases);

@@ -886,9 +886,11 @@ int mg_hash_select_peer(const ModgpuHasher *h, const uint64_t *d_packed, const u
   if (nBases >= (1ull << 32)) { mg_set_error("hash_select: batch of %llu bases exceeds 2^32-1", (unsigned long long)nBases); return MODGPU_EINVAL; }
   if (nOwners < 1 || nOwners > 64) { mg_set_error("hash_select: nOwners %u out of range 1..64", nOwners); return MODGPU_EINVAL; }
   const uint32_t nRegions = 1u << (slotBits - regionBits);
-  MG_CUDA(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
-  MG_CUDA(cudaMemsetAsync(d_cursors, 0, (size_t)nOwners * nRegions * sizeof(uint32_t), st));
-  MG_CUDA(cudaMemsetAsync(d_ovfCounts, 0, nOwners * sizeof(uint32_t), st));
+  if (!(flags & MODGPU_SEL_APPEND))                    // APPEND: the batch joins what earlier batches left in the buckets
+    { MG_CUDA(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
+      MG_CUDA(cudaMemsetAsync(d_cursors, 0, (size_t)nOwners * nRegions * sizeof(uint32_t), st));
+      MG_CUDA(cudaMemsetAsync(d_ovfCounts, 0, nOwners * sizeof(uint32_t), st));
+    }
   if (!nBases) return MODGPU_OK;
   SelectParams P;
   memset(&P, 0, sizeof(P));

@@ -66,6 +66,9 @@ class ShardedModset:
         #                "peer" = the same buckets moved with an equal-split NCCL all-to-all, then a local build
         #                "segments" = per-owner segments + a scatter pass at the receiver
         self.fused_mode = "p2p"
+        # deferred peer build (set_accumulate): the k-mers of up to `accumulate` batches wait in the peer buckets and one
+        # exchange + build applies them all - a populated per-rank table is rewritten once per group, not per batch
+        self.accumulate = 1
         self._p2p = None
         self._peer_cap = 0
         self._seg_cap = 0
@@ -101,7 +104,7 @@ class ShardedModset:
         t = torch.tensor([int(max_bases_per_batch)], dtype=torch.int64, device=self.dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
         nb = int(t.item())
-        expected = nb // max(self.w, 1) + 1
+        expected = (nb // max(self.w, 1) + 1) * self.accumulate     # a group of batches shares the buckets
         mean = expected / float(G * R)
         cap = (int(1.1 * mean + 4.0 * math.sqrt(mean) + 8) + 1) & ~1
         ovf_cap = max(65536, expected // 4)
@@ -151,7 +154,7 @@ class ShardedModset:
             self._p2p_release()
             self.fused_mode = "peer"
             return False
-        self._p2p.update(cap=cap, ovf_cap=ovf_cap, R=R, sb=sb, so=so, bptr=bptr, optr=optr, batch=0,
+        self._p2p.update(cap=cap, ovf_cap=ovf_cap, R=R, sb=sb, so=so, bptr=bptr, optr=optr, batch=0, pending=0,
                          sc=torch.zeros(G * R, dtype=torch.int32, device=self.dev),
                          rc=torch.zeros(G * R, dtype=torch.int32, device=self.dev),
                          soc=torch.zeros(G, dtype=torch.int32, device=self.dev),
@@ -163,10 +166,30 @@ class ShardedModset:
         """select(sb, cap, sc, so, ovf_cap, soc, cnt) launches this rank's hash/select into bucket set `sb`"""
         if self._p2p is None and not self.reserve(nbases):
             return False
+        st = self._p2p
+        b = st["batch"] & 1                      # the bucket set of this group of batches
+        if st["pending"]:                        # joins the batches already waiting: fill counts are kept (MODGPU_SEL_APPEND)
+            flags = getattr(self.local, "_flags", 0)
+            check(self._lib.modgpuModsetSetFlags(self.local._p, flags | 128), "set_flags")
+            try:
+                select(st["sb"][b], st["cap"], st["sc"], st["so"][b], st["ovf_cap"], st["soc"], st["cnt"])
+            finally:
+                check(self._lib.modgpuModsetSetFlags(self.local._p, flags), "set_flags")
+        else:
+            select(st["sb"][b], st["cap"], st["sc"], st["so"][b], st["ovf_cap"], st["soc"], st["cnt"])
+        st["pending"] += 1
+        if st["pending"] >= self.accumulate:
+            self._p2p_flush()
+        return True
+
+    def _p2p_flush(self):
+        """COLLECTIVE: exchange the fill counts of the waiting batches and build them into the owners' tables"""
         st, g, G = self._p2p, self.group, self.world
+        if not st or not st["pending"]:
+            return
         b = st["batch"] & 1
         st["batch"] += 1
-        select(st["sb"][b], st["cap"], st["sc"], st["so"][b], st["ovf_cap"], st["soc"], st["cnt"])
+        st["pending"] = 0
         # fill counts to the owners; completing these two small collectives also means every rank's select is done
         dist.all_to_all_single(st["rc"], st["sc"], group=g)
         dist.all_to_all_single(st["roc"], st["soc"], group=g)
@@ -174,9 +197,18 @@ class ShardedModset:
                                                    st["optr"][b], st["ovf_cap"], C.c_void_p(st["roc"].data_ptr())), "buildFromPeers")
         self._sel_acc += st["cnt"]
         self._ovf_acc = torch.maximum(self._ovf_acc, (st["soc"].max() > st["ovf_cap"]).to(torch.int32).reshape(1))
-        return True
+
+    def set_accumulate(self, n_batches):
+        """COLLECTIVE: up to n_batches batches share one count exchange and one peer build (peer-memory mode).  What
+        is waiting reaches the tables at synchronize() - call it before reading the local sets."""
+        if self.world > 1:
+            self._p2p_flush()
+            self._p2p_release()                  # the buckets are sized for a group: mapped again by the next add
+        self.accumulate = max(1, int(n_batches))
 
     def clear(self):
+        if self._p2p and self._p2p["pending"]:   # batches waiting in the peer buckets are dropped with the rest; the next
+            self._p2p["pending"] = 0             # group reuses the same bucket set (no peer has been told to read it)
         check(self._lib.modgpuModsetClear(self.local._p), "modsetClear")
 
     def _route_and_insert(self, kptr, n):
@@ -271,6 +303,7 @@ class ShardedModset:
         if self.world == 1:
             n, self.total_selected = self.total_selected, 0
             return n
+        self._p2p_flush()
         vals = torch.cat([self._sel_acc, self._ovf_acc.to(torch.int64)]).cpu().tolist()
         self._sel_acc.zero_(); self._ovf_acc.zero_()
         if vals[1]:

@@ -108,6 +108,7 @@ class Modset:
 
     def set_flags(self, flags):
         check(self._lib.modgpuModsetSetFlags(self._p, flags), "set_flags")
+        self._flags = int(flags)
 
     def set_exact_order(self, on=True):
         """number entries by first occurrence like the reference's index = ++max (modset.c:57)"""

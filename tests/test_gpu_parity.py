@@ -789,6 +789,13 @@ def _sharded_worker(rank, world, port, tmpdir):
     sm.fused = False                                          # the list-based exchange, once more
     n3 = sm.add_device(d_b.data_ptr(), d_o.data_ptr(), per, len(data))
     assert n3 == n1
+    # deferred peer build: three batches share one exchange + build, a fourth waits until synchronize()
+    sm.synchronize()                                          # (the list exchange also counts towards synchronize())
+    sm.fused, sm.fused_mode = True, ("p2p" if p2p else "peer")
+    sm.set_accumulate(3)
+    for _ in range(4):
+        sm.add_device(d_b.data_ptr(), d_o.data_ptr(), per, len(data))
+    assert sm.synchronize() == 4 * n1
     v, d, i = sm.gather_sorted_dump()
     h = sm.histogram()
     gmax = sm.global_max()
@@ -813,7 +820,7 @@ def test_sharded_modset_two_gpus(mg, torch_cuda, orc, tmp_path):
     offs = np.arange(601, dtype=np.uint64) * np.uint64(5000)
     oms = orc.modset_new(22, 19, 31, 17)
     assert bool(r["p2p"]), "the peer-memory exchange fell back to NCCL"
-    for _ in range(5):                                        # every rank added its chunk five times
+    for _ in range(9):                                        # every rank added its chunk nine times
         orc.modset_add(oms, data, offs)
     ov, od, _ = orc.modset_sorted(oms)
     assert np.array_equal(r["v"], ov) and np.array_equal(r["d"], od)

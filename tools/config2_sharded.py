@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--bits", type=int, default=27, help="per-GPU table bits")
     ap.add_argument("--check", action="store_true", help="rank 0 repeats the whole set on one GPU and compares")
+    ap.add_argument("--accumulate", type=int, default=1, help="batches per count exchange + peer build (deferred build)")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -49,6 +50,8 @@ def main():
     buf = torch.empty(chunk * L + 64, dtype=torch.uint8, device=dev)
     offs = torch.arange(chunk + 1, dtype=torch.int64, device=dev) * L
     sm = ShardedModset(a.bits, 31, 64, 17)
+    if a.accumulate > 1:
+        sm.set_accumulate(a.accumulate)
 
     def one_pass():
         t_add = 0.0
@@ -86,7 +89,7 @@ def main():
     if rank == 0:
         bases = per_rank * world * L
         out = {"config": "configs[2] HiFi-like 30x of 3.1 Gb, 15 kb reads, 0.1 %% errors, table hash-sharded over %d GPUs" % world,
-               "k": 31, "d": 64, "tableBits_per_gpu": a.bits, "n_gpus": world, "bases": bases, "reads": per_rank * world,
+               "k": 31, "d": 64, "tableBits_per_gpu": a.bits, "n_gpus": world, "accumulate": a.accumulate, "bases": bases, "reads": per_rank * world,
                "hashes": tot[0], "distinct": tot[1], "ms": 1e3 * tmax[1], "gbases_per_s": bases / tmax[1] / 1e9,
                "ms_first_pass_with_allocations": 1e3 * tmax[0], "modal_depth": int(np.argmax(hist[2:]) + 2),
                "timing": "wall clock between device-wide synchronisations around every add (+ the final count readback), max over ranks"}
