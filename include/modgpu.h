@@ -37,6 +37,7 @@ extern "C" {
 #define MODGPU_EINVAL       -3   /* bad argument (k, w, bits, sizes ...) */
 #define MODGPU_EFULL        -4   /* table or output list overflow (reference: die(), modset.c:58) */
 #define MODGPU_ENOMEM       -5
+#define MODGPU_ESKEW        -6   /* sharded add: a group of batches was too skewed for its buckets and was skipped on every rank */
 
 const char *modgpuLastError(void);
 int modgpuDeviceCount(void);
@@ -186,6 +187,12 @@ uint64_t modgpuModsetAdd(ModgpuModset *ms, const char *bases, const uint64_t *of
 /* same with the batch already resident in device memory */
 uint64_t modgpuModsetAddDevice(ModgpuModset *ms, const uint8_t *d_bases, const uint64_t *d_offs,
                                uint64_t nSeq, uint64_t nBases, int isAscii);
+/* same with the sequences in the reference's own 2-bit packing (sqioSeqPack, seqio.c:557-570, the payload of its
+ * "binary" seqio files): four bases per byte, first base in the top two bits, a last byte with fewer than four bases
+ * holding them in its low bits.  Sequence r has offs[r+1] - offs[r] bases and its (len+3)/4 bytes start at
+ * packed + byteOffs[r] (byteOffs has nSeq+1 entries, non-decreasing).  0.25 bytes per base cross PCIe. */
+uint64_t modgpuModsetAddPacked(ModgpuModset *ms, const uint8_t *packed, const uint64_t *byteOffs,
+                               const uint64_t *offs, uint64_t nSeq);
 uint32_t modgpuModsetMax(ModgpuModset *ms);                            /* ms->max */
 /* host arrays of length max, index order (sync-to-host of value/depth/info) */
 int modgpuModsetExport(ModgpuModset *ms, uint64_t *value, uint16_t *depth, uint8_t *info);
@@ -280,6 +287,22 @@ ModgpuModset *modgpuModsetReadMod(const char *path);
 uint64_t modgpuModsetReadset(ModgpuModset *ms, const char *bases, const uint64_t *offs, uint64_t nSeq, int isAscii,
                              int resetDepth, uint64_t *hitOff, uint32_t *hit, uint16_t *dx, int32_t *nMiss, uint64_t cap);
 
+/* ------------------------------------------- host Modset <-> device twin --
+ * The reference's callers use the public fields of Modset directly (ms->depth[index] modutils.c:26, ms->value[i] /
+ * ms->max modutils.c:57-69, ms->info through modset.h:53-69), so a drop-in (libmodshim.so, include/modshim.h) has to
+ * keep host arrays and device table in step.  These three calls are what it needs beside Export / Import:
+ *
+ * batched modsetIndexFind (modset.c:45-62) on host arrays: index[i] = the index of kmers[i], 0 when absent; with
+ * isAdd != 0 absent k-mers are inserted and numbered ++max in input order (the reference's numbering); depths are
+ * not touched (the reference's caller increments them itself) */
+int modgpuModsetIndexFindBatch(ModgpuModset *ms, const uint64_t *kmers, uint64_t n, int isAdd, uint32_t *index);
+/* the caller changed depth[] / info[] of entries 1..n on the host (++depth, msSetCopy*, msSetMinor ...): upload them.
+ * Either pointer may be NULL.  info is the whole byte (modset.h:44-52). */
+int modgpuModsetSetDepthInfo(ModgpuModset *ms, const uint16_t *depth, const uint8_t *info, uint64_t n);
+/* the reference's own index[] table (2^bits U32; home slot hash & mask, odd double-hashing stride, entries
+ * inserted in index order: modset.c:48-57), built on the device and copied to `index` (host) */
+int modgpuModsetReferenceIndex(ModgpuModset *ms, uint32_t *index);
+
 /* per-kernel accumulated device time (ms) since the last reset, measured with
  * CUDA events on the object's stream when profiling is enabled */
 #define MODGPU_T_PACK 0
@@ -353,6 +376,48 @@ int modgpuPeerClose(void *d_ptr);
 int modgpuModsetBuildFromPeers(ModgpuModset *ms, const uint64_t *const *d_buckets, const uint32_t *d_cursors,
                                uint32_t bucketCap, uint32_t nSrc, const uint64_t *const *d_overflow,
                                uint64_t overflowCap, const uint32_t *d_ovfCounts);
+
+/* -------------------------------------------- the sharded modset, in C --
+ * One process (or thread) per GPU; the table is sharded by modgpuOwnerOf, every rank feeds ITS OWN chunk of the input.
+ * The reference has no distributed mode (its recipe is modsetMerge, modset.c:106-128, modutils.c:101-103); counts are
+ * commutative sums, so the union of the shards equals the single-GPU modset for any number of GPUs.
+ * Per group of batches: select into per-(owner, region) buckets in the selecting rank's memory, ONE equal-split
+ * all-to-all of the fill-count rows (it doubles as the cross-GPU barrier), region build on the owner reading the
+ * peers' buckets over NVLink.  A group is applied on every rank or on none (MODGPU_ESKEW from Synchronize).
+ * The communicator is three callbacks; modgpuCommFromNccl binds them to an ncclComm_t (libnccl loaded at run time). */
+typedef struct ModgpuComm {
+  void *ctx;
+  int rank, world;
+  /* equal-split all-to-all of DEVICE memory, ordered on `stream`: bytesPerPeer bytes to and from every rank (self included) */
+  int (*alltoall)(void *ctx, const void *d_send, void *d_recv, size_t bytesPerPeer, void *stream);
+  /* HOST all-gather of `bytes` per rank, blocking (set-up only: sizes and the 64-byte IPC handles) */
+  int (*allgather)(void *ctx, const void *in, void *out, size_t bytes);
+  /* HOST barrier, blocking (before peer buffers are unmapped) */
+  int (*barrier)(void *ctx);
+} ModgpuComm;
+int modgpuCommFromNccl(ModgpuComm *out, void *ncclComm /* ncclComm_t */, int rank, int world);
+void modgpuCommNcclRelease(ModgpuComm *c);
+
+typedef struct ModgpuSharded ModgpuSharded;
+/* bits = the PER-GPU table bits (capacity 2^(bits-2) entries per GPU).  Calls marked COLLECTIVE must be made by every rank. */
+ModgpuSharded *modgpuShardedCreate(int bits, int k, int w, int seed, const ModgpuComm *comm);
+void modgpuShardedDestroy(ModgpuSharded *s);                                   /* COLLECTIVE */
+ModgpuModset *modgpuShardedLocal(ModgpuSharded *s);                            /* this rank's shard: Export, Histogram, Max ... */
+int modgpuShardedSetStream(ModgpuSharded *s, void *stream);
+/* COLLECTIVE: size and map the peer buckets for batches of up to maxBasesPerBatch bases per rank (implied by the first add) */
+int modgpuShardedReserve(ModgpuSharded *s, uint64_t maxBasesPerBatch);
+/* COLLECTIVE: up to nBatches batches share one count exchange and one peer build (streaming many batches into one set) */
+int modgpuShardedSetAccumulate(ModgpuSharded *s, int nBatches);
+/* COLLECTIVE: size the overflow segments for the worst case (every k-mer of a group to one owner): no group is skipped */
+int modgpuShardedSetRobust(ModgpuSharded *s, int on);
+/* this rank's batch (host / device memory, < 2^32 bases); COLLECTIVE once per group (every rank adds the same number of batches) */
+int modgpuShardedAdd(ModgpuSharded *s, const char *bases, const uint64_t *offs, uint64_t nSeq, int isAscii);
+int modgpuShardedAddDevice(ModgpuSharded *s, const uint8_t *d_bases, const uint64_t *d_offs, uint64_t nSeq,
+                           uint64_t nBases, int isAscii);
+int modgpuShardedFlush(ModgpuSharded *s);                                      /* COLLECTIVE: apply the batches that are waiting */
+/* COLLECTIVE: flush and wait; *nSelected = k-mers this rank selected since the last call */
+int modgpuShardedSynchronize(ModgpuSharded *s, uint64_t *nSelected);
+int modgpuShardedClear(ModgpuSharded *s);
 
 /* ---------------------------------------------------- pinned host memory --
  * "seqio parsing stays on the host, feeding pinned buffers" */

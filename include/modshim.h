@@ -1,4 +1,4 @@
-/* modshim.h - libmodshim.so: the reference's OWN seqhash symbols, served by libmodgpu (B200).
+/* modshim.h - libmodshim.so: the reference's OWN seqhash AND modset symbols, served by libmodgpu (B200).
  *
  * The shim is compiled against the reference's headers where they lie (modimizer_b200/csrc/shim/Makefile,
  * -I/root/reference), so the structs are the reference's by construction.  An unmodified caller that links
@@ -16,12 +16,15 @@
  * keep working on the shim's objects (the iterator's result arrays live in its hashBuf / fBuf members).
  * Errors follow the reference: die() (utils.c:19-30).
  *
- * The modset half of the reference API (modsetIndexFind + ++ms->depth[index], one k-mer per call on host arrays)
- * cannot be accelerated call by call; its callers switch to the batched entry points of modgpu.h instead
- * (INTEGRATION.md).  modimizer_b200/csrc/shim/modutils_gpu.c is a complete C host doing exactly that with the
- * reference's seqio, and tests/test_gpu_cli.py holds it byte-identical to the stock modutils.
+ * The modset half (modset.h:30-42) is exported under its own names too (modshim_modset.c): a host Modset with the
+ * reference's layout whose arrays are valid whenever control is in caller code, backed by a device twin.  The
+ * UNMODIFIED modutils.c / modmap.c link against libmodshim.so and produce the stock tools' bytes
+ * (tests/test_gpu_cli.py: modutils_shim, modmap_shim); modsetIndexFind is then one device lookup per call - exact,
+ * not fast.  The throughput path is the batched one: the two caller loops patched as INTEGRATION.md shows
+ * (csrc/shim/modutils_hot.c, modmap_hot.c, applied to the reference's sources at build time: modutils_dropin,
+ * modmap_dropin).
  *
- * This header only adds the one extra symbol the shim exports; include the reference's seqhash.h for the rest.
+ * This header declares what the shim adds; include the reference's seqhash.h / modset.h for the rest.
  */
 #ifndef MODSHIM_H
 #define MODSHIM_H
@@ -34,6 +37,18 @@ extern "C" {
 /* the scanner (modgpu.h) the iterator uses for this hasher: callers that want whole batches instead of one
  * sequence per modRCiterator call share it.  `seqhash` is a reference Seqhash*. */
 ModgpuScanner *modshimScanner(void *seqhash);
+
+/* ---- modset.h under its own names (modshim_modset.c): modsetCreate, modsetDestroy, modsetWrite, modsetRead,
+ * modsetIndexFind, modsetSummary, modsetPack, modsetDepthPrune, modsetMerge (modset.h:30-42) operate on the
+ * reference's host Modset, every one of which has a device twin; include the reference's modset.h for them.
+ * The additions below are the batched path a caller switches its per-read loop to (`ms` is a reference Modset*): */
+ModgpuModset *modshimTwin(void *ms);                                  /* the device twin, for modgpu.h calls */
+void modshimSync(void *ms);                                           /* device -> ms->value/depth/info[1..max], ms->max */
+/* == the addSequence loop (modutils.c:19-31): copy one sequence (codes 0..3) into the pinned batch of `ms`; full
+ * batches are added on the GPU as they fill */
+void modshimBatchPut(void *ms, const char *s, long long len);
+/* add what is waiting, sync the host arrays, return the hashes added since the last flush (modutils.c: totHash) */
+unsigned long long modshimBatchFlush(void *ms);
 
 #ifdef __cplusplus
 }

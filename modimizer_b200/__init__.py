@@ -8,7 +8,7 @@ box without the built library or without a GPU works, but every operation then
 raises ModgpuError - nothing falls back to the CPU.
 """
 from ._lib import ModgpuError, LIB_PATH, SYMBOLS, load, require_device  # noqa: F401
-from .modset import Seqhash, Modset, Reference, kmer_string  # noqa: F401
+from .modset import Seqhash, Modset, Reference, kmer_string, seqio_pack  # noqa: F401
 from . import synth  # noqa: F401
 
-__all__ = ["ModgpuError", "Seqhash", "Modset", "Reference", "kmer_string", "synth", "load", "require_device"]
+__all__ = ["ModgpuError", "Seqhash", "Modset", "Reference", "kmer_string", "seqio_pack", "synth", "load", "require_device"]

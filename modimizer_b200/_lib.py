@@ -70,6 +70,7 @@ _SIGS = {
     "modgpuModsetSetExactOrder": (C.c_int, [vp, C.c_int]),
     "modgpuModsetAdd": (u64, [vp, vp, vp, u64, C.c_int]),
     "modgpuModsetAddDevice": (u64, [vp, vp, vp, u64, u64, C.c_int]),
+    "modgpuModsetAddPacked": (u64, [vp, vp, vp, vp, u64]),
     "modgpuModsetMax": (u32, [vp]),
     "modgpuModsetExport": (C.c_int, [vp, vp, vp, vp]),
     "modgpuModsetHistogram": (C.c_int, [vp, vp]),
@@ -92,6 +93,20 @@ _SIGS = {
     "modgpuPeerExport": (C.c_int, [vp, vp]),
     "modgpuPeerOpen": (vp, [C.c_char_p]),
     "modgpuPeerClose": (C.c_int, [vp]),
+    "modgpuCommFromNccl": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+    "modgpuCommNcclRelease": (None, [vp]),
+    "modgpuShardedCreate": (vp, [C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "modgpuShardedDestroy": (None, [vp]),
+    "modgpuShardedLocal": (vp, [vp]),
+    "modgpuShardedSetStream": (C.c_int, [vp, vp]),
+    "modgpuShardedReserve": (C.c_int, [vp, u64]),
+    "modgpuShardedSetAccumulate": (C.c_int, [vp, C.c_int]),
+    "modgpuShardedSetRobust": (C.c_int, [vp, C.c_int]),
+    "modgpuShardedAdd": (C.c_int, [vp, vp, vp, u64, C.c_int]),
+    "modgpuShardedAddDevice": (C.c_int, [vp, vp, vp, u64, u64, C.c_int]),
+    "modgpuShardedFlush": (C.c_int, [vp]),
+    "modgpuShardedSynchronize": (C.c_int, [vp, C.POINTER(u64)]),
+    "modgpuShardedClear": (C.c_int, [vp]),
     "modgpuModsetInsertSegments": (C.c_int, [vp, vp, u32, u64, vp, u64]),
     "modgpuModsetInsertDevice": (C.c_int, [vp, vp, u64]),
     "modgpuModsetClear": (C.c_int, [vp]),
@@ -106,6 +121,9 @@ _SIGS = {
     "modgpuModsetWriteMod": (C.c_int, [vp, C.c_char_p, C.c_int]),
     "modgpuModsetReadMod": (vp, [C.c_char_p]),
     "modgpuModsetReadset": (u64, [vp, vp, vp, u64, C.c_int, C.c_int, vp, vp, vp, vp, u64]),
+    "modgpuModsetIndexFindBatch": (C.c_int, [vp, vp, u64, C.c_int, vp]),
+    "modgpuModsetSetDepthInfo": (C.c_int, [vp, vp, vp, u64]),
+    "modgpuModsetReferenceIndex": (C.c_int, [vp, vp]),
     "modgpuModsetProfile": (C.c_int, [vp, C.c_int]),
     "modgpuModsetTimes": (C.c_int, [vp, vp, vp]),
     "modgpuReferenceBuild": (vp, [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, u64, C.c_int, vp]),

@@ -61,7 +61,7 @@ extern "C" void modgpuModsetDestroy(ModgpuModset *ms)
   prof_collect(ms);
   for (cudaEvent_t e : ms->evPool) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i)
-    { ms->bases[i].release(); ms->offs[i].release(); ms->hOffs[i].release();
+    { ms->bases[i].release(); ms->offs[i].release(); ms->hOffs[i].release(); ms->pk[i].release();
       if (ms->evCopied[i]) cudaEventDestroy(ms->evCopied[i]);
       if (ms->evFree[i]) cudaEventDestroy(ms->evFree[i]);
     }
@@ -285,6 +285,9 @@ static int add_chunk_device(ModgpuModset *ms, const uint8_t *d_bases, const uint
     { rc = add_chunk_fused(ms, d_bases, d_offs, nSeq, nBases, isAscii, expected, nHashes);
       if (rc <= 0) return rc;
     }
+  // exact order: entries an earlier count-mode / bulk / merge insert left un-numbered get their (slot-order) indices
+  // first, otherwise a reappearance in this batch would number them as first occurrences of THIS batch (modset.c:57)
+  if (ms->exactOrder && ms->dirty && (rc = mg_modset_ensure_numbered(ms))) return rc;
   rc = mg_modset_select_chunk(ms, d_bases, d_offs, nSeq, nBases, isAscii, false, 0, &n);
   if (rc) return rc;
   *nHashes = n;
@@ -456,6 +459,112 @@ extern "C" uint64_t modgpuModsetAddDevice(ModgpuModset *ms, const uint8_t *d_bas
   return total;
 }
 
+// ------------------------------------------------------------ packed input --
+// The reference's own 2-bit sequence packing (sqioSeqPack, seqio.c:557-570: what its "binary" seqio files hold):
+// four bases per byte, first base in the top two bits, every sequence starting on a byte, and a last byte with fewer
+// than four bases holding them in its LOW bits.  A caller that has such records ships 0.25 bytes per base over PCIe
+// instead of 1; the device expands them to codes (one streaming pass, 1.25 B/base) and the batch then takes the
+// normal path.  One thread expands 16 bases: five packed bytes, a funnel shift, and per output word one multiply
+// that spreads a byte's four codes (b * 0x40100401 >> 6 & 0x03030303) - unless the group touches a sequence boundary.
+__global__ void __launch_bounds__(256) unpack_seqio_kernel(const uint8_t *__restrict__ packed, const uint64_t *__restrict__ byteOffs,
+                                                           const uint64_t *__restrict__ baseOffs, uint64_t nSeq, uint64_t nBases,
+                                                           uint8_t *__restrict__ out)
+{
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t nGroups = (nBases + 15) / 16;
+  for (uint64_t grp = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; grp < nGroups; grp += stride)
+    { const uint64_t g0 = grp * 16;
+      uint64_t lo = 0, hi = nSeq;                          // last sequence starting at or before g0 (it holds base g0)
+      while (hi - lo > 1) { const uint64_t mid = (lo + hi) >> 1; if (__ldg(baseOffs + mid) <= g0) lo = mid; else hi = mid; }
+      uint64_t r = lo;
+      const uint64_t s0 = __ldg(baseOffs + r), s1 = __ldg(baseOffs + r + 1);
+      const uint64_t j0 = g0 - s0, len = s1 - s0, whole = len & ~(uint64_t)3;   // bases in fully packed bytes
+      uint4 w;
+      if (j0 + 16 <= whole)
+        { const uint8_t *p = packed + __ldg(byteOffs + r) + (j0 >> 2);
+          const uint64_t v = ((uint64_t)p[0] << 32) | ((uint64_t)p[1] << 24) | ((uint64_t)p[2] << 16) | ((uint64_t)p[3] << 8) | (uint64_t)p[4];
+          const uint32_t x = (uint32_t)(v >> (8 - 2 * (uint32_t)(j0 & 3)));      // 16 bases, the first in the top two bits
+          w.x = (((x >> 24) * 0x40100401u) >> 6) & 0x03030303u;
+          w.y = ((((x >> 16) & 0xFFu) * 0x40100401u) >> 6) & 0x03030303u;
+          w.z = ((((x >> 8) & 0xFFu) * 0x40100401u) >> 6) & 0x03030303u;
+          w.w = (((x & 0xFFu) * 0x40100401u) >> 6) & 0x03030303u;
+        }
+      else
+        { uint32_t c[4] = { 0, 0, 0, 0 };
+          for (uint32_t t = 0; t < 16; ++t)
+            { const uint64_t g = g0 + t;
+              if (g >= nBases) break;
+              while (g >= __ldg(baseOffs + r + 1)) ++r;
+              const uint64_t a = __ldg(baseOffs + r), j = g - a, L = __ldg(baseOffs + r + 1) - a;
+              const uint32_t b = packed[__ldg(byteOffs + r) + (j >> 2)], rem = (uint32_t)(L & 3);
+              const bool tail = rem && (j >> 2) == ((L - 1) >> 2);               // the short last byte is right-aligned
+              const uint32_t shift = tail ? 2 * (rem - 1 - (uint32_t)(j & 3)) : 6 - 2 * (uint32_t)(j & 3);
+              c[t >> 2] |= ((b >> shift) & 3u) << (8 * (t & 3));
+            }
+          w.x = c[0]; w.y = c[1]; w.z = c[2]; w.w = c[3];
+        }
+      reinterpret_cast<uint4 *>(out)[grp] = w;
+    }
+}
+
+extern "C" uint64_t modgpuModsetAddPacked(ModgpuModset *ms, const uint8_t *packed, const uint64_t *byteOffs,
+                                          const uint64_t *offs, uint64_t nSeq)
+{
+  const uint64_t FAIL = 0xFFFFFFFFFFFFFFFFull;
+  if (!ms || !offs || !byteOffs) { mg_set_error("modgpuModsetAddPacked: null argument"); return FAIL; }
+  if (!nSeq) return 0;
+  if (check_offsets(offs, nSeq)) return FAIL;
+  if (!packed && offs[nSeq]) { mg_set_error("modgpuModsetAddPacked: null bases"); return FAIL; }
+  for (uint64_t r = 0; r < nSeq; ++r)
+    if (byteOffs[r + 1] < byteOffs[r] + (offs[r + 1] - offs[r] + 3) / 4)
+      { mg_set_error("modgpuModsetAddPacked: sequence %llu has fewer packed bytes than (len+3)/4", (unsigned long long)r); return FAIL; }
+  std::vector<uint64_t> cuts;
+  plan_chunks(offs, nSeq, MG_HOST_CHUNK, cuts);
+  const size_t nChunks = cuts.size() - 1;
+  cudaStream_t st = ms->stream;
+  uint64_t total = 0;
+  // per chunk: the packed bytes and the two rebased offset arrays cross PCIe on the copy stream into buffer c & 1 while the
+  // kernels of chunk c - 1 run (the same events as the byte path); pkOffs[b] holds byteOffs then baseOffs
+  auto stage = [&](size_t c) -> int {
+    const int b = (int)(c & 1);
+    const uint64_t r0 = cuts[c], r1 = cuts[c + 1], ns = r1 - r0, nbytes = byteOffs[r1] - byteOffs[r0];
+    int rc;
+    MG_CUDA(cudaStreamWaitEvent(ms->copyStream, ms->evFree[b], 0));
+    MG_CUDA(cudaEventSynchronize(ms->evCopied[b]));
+    if ((rc = ms->pk[b].ensure(nbytes + 64)) || (rc = ms->offs[b].ensure(2 * (ns + 1) * 8)) || (rc = ms->hOffs[b].ensure(2 * (ns + 1) * 8))) return rc;
+    uint64_t *ho = (uint64_t *)ms->hOffs[b].p;
+    for (uint64_t r = 0; r <= ns; ++r) { ho[r] = byteOffs[r0 + r] - byteOffs[r0]; ho[ns + 1 + r] = offs[r0 + r] - offs[r0]; }
+    if (nbytes) MG_CUDA(cudaMemcpyAsync(ms->pk[b].p, packed + byteOffs[r0], nbytes, cudaMemcpyHostToDevice, ms->copyStream));
+    MG_CUDA(cudaMemcpyAsync(ms->offs[b].p, ho, 2 * (ns + 1) * 8, cudaMemcpyHostToDevice, ms->copyStream));
+    MG_CUDA(cudaEventRecord(ms->evCopied[b], ms->copyStream));
+    return MODGPU_OK;
+  };
+  if (stage(0)) return FAIL;
+  for (size_t c = 0; c < nChunks; ++c)
+    { const int b = (int)(c & 1);
+      if (c + 1 < nChunks && stage(c + 1)) return FAIL;
+      if (mg_check_cuda(cudaStreamWaitEvent(st, ms->evCopied[b], 0), "cudaStreamWaitEvent", __FILE__, __LINE__)) return FAIL;
+      const uint64_t r0 = cuts[c], r1 = cuts[c + 1], ns = r1 - r0, nb = offs[r1] - offs[r0];
+      uint64_t n = 0;
+      if (nb)
+        { if (ms->bases[0].ensure(nb + 64)) return FAIL;
+          const uint64_t *dByte = (const uint64_t *)ms->offs[b].p, *dBase = dByte + ns + 1;
+          { ProfScope p(ms, MODGPU_T_PACK, 1);
+            uint64_t blocks = ((nb + 15) / 16 + 255) / 256, maxBlocks = (uint64_t)mg_num_sms() * 16;
+            if (blocks > maxBlocks) blocks = maxBlocks;
+            unpack_seqio_kernel<<<(unsigned)blocks, 256, 0, st>>>((const uint8_t *)ms->pk[b].p, dByte, dBase, ns, nb, (uint8_t *)ms->bases[0].p);
+            if (mg_check_cuda(cudaGetLastError(), "unpack_seqio", __FILE__, __LINE__)) return FAIL;
+          }
+          if (add_chunk_device(ms, (const uint8_t *)ms->bases[0].p, dBase, ns, nb, 0, &n)) return FAIL;
+        }
+      if (mg_check_cuda(cudaEventRecord(ms->evFree[b], st), "cudaEventRecord", __FILE__, __LINE__)) return FAIL;
+      total += n;
+    }
+  ms->totalHashes += total;
+  if (ms->accumulate <= 1 && modgpuTableEntries(ms->table, st) == FAIL) return FAIL;
+  return total;
+}
+
 extern "C" int modgpuModsetSelectDevice(ModgpuModset *ms, const uint8_t *d_bases, const uint64_t *d_offs,
                                         uint64_t nSeq, uint64_t nBases, int isAscii,
                                         const uint64_t **d_kmers, uint64_t *nSelected)
@@ -527,13 +636,13 @@ extern "C" uint64_t modgpuScannerScan(ModgpuScanner *sc, const char *bases, cons
                              MODGPU_SEL_ORDERED | MODGPU_SEL_STRAND, &n))
     return FAIL;
   const uint64_t m = n < cap ? n : cap;
-  if (m)
+  if (m || (seqOff && n))                               // the per-sequence ranges need the ids even when nothing is stored
     { if (sc->id.ensure(n * 4) || sc->pos.ensure(n * 4)) return FAIL;
       // global offset -> (sequence, position in sequence)
       if (modgpuLocate((const uint32_t *)ms->gpos.p, n, (const uint64_t *)ms->offs[0].p, nSeq, (uint32_t *)sc->id.p, (uint32_t *)sc->pos.p, st))
         return FAIL;
-      if (kmers && mg_check_cuda(cudaMemcpyAsync(kmers, ms->kmers.p, m * 8, cudaMemcpyDeviceToHost, st), "D2H kmers", __FILE__, __LINE__)) return FAIL;
-      if (pos && mg_check_cuda(cudaMemcpyAsync(pos, sc->pos.p, m * 4, cudaMemcpyDeviceToHost, st), "D2H pos", __FILE__, __LINE__)) return FAIL;
+      if (m && kmers && mg_check_cuda(cudaMemcpyAsync(kmers, ms->kmers.p, m * 8, cudaMemcpyDeviceToHost, st), "D2H kmers", __FILE__, __LINE__)) return FAIL;
+      if (m && pos && mg_check_cuda(cudaMemcpyAsync(pos, sc->pos.p, m * 4, cudaMemcpyDeviceToHost, st), "D2H pos", __FILE__, __LINE__)) return FAIL;
     }
   std::vector<uint32_t> id;
   if (seqOff && n)

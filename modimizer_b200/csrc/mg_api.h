@@ -100,7 +100,7 @@ struct ModgpuModset {
   int exactOrder = 0;
   bool depthIsZero = false;         // modmap-built sets keep ms->depth at 0
   bool dirty = false;               // entries inserted since the last numbering
-  DevBuf bases[2], offs[2], packed, ends, kmers, kmers2, gpos, slot, work, misc, expo;
+  DevBuf bases[2], offs[2], pk[2], packed, ends, kmers, kmers2, gpos, slot, work, misc, expo;
   size_t endsCleanCap = 0;          // ms->ends is all zero over this capacity (0: unknown / flags of a batch still set)
   int regionBits = -1;              // -1 auto: partition inserts by table region when the table exceeds L2
   PinBuf hOffs[2], hMisc;

@@ -12,12 +12,11 @@
 //
 // Index numbering is the reference's (first occurrence, modset.c:57), so the
 // arrays are identical to the reference's, not merely isomorphic.
-// rev[] needs a stable sort of the occurrence list by index; that one step uses
-// cub::DeviceRadixSort (header-only, ships with the toolkit) - it is outside the
-// north-star hot path; everything else here is hand-written.
+// rev[] is the reference's counting sort of the occurrence list by index (modmap.c:88-90), done here as a
+// stable least-significant-digit radix sort of (index, ordinal) pairs: per pass a per-tile digit histogram,
+// one exclusive scan over (digit, tile), and a scatter that ranks equal digits in input order.
 #include <vector>
 #include <string.h>
-#include <cub/device/device_radix_sort.cuh>
 #include "mg_device.cuh"
 #include "mg_scan.cuh"
 
@@ -81,12 +80,6 @@ __global__ void __launch_bounds__(256) add_const_kernel(uint32_t *a, uint64_t n,
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a[i] += c;
 }
 
-__global__ void __launch_bounds__(256) iota_kernel(uint32_t *a, uint64_t n)
-{
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a[i] = (uint32_t)i;
-}
-
 // loc[i] = sum of depth[0..i-1]  (modmap.c:84-86; depth[0] = 0)
 struct LocScan {
   const uint32_t *depth; uint32_t *loc;
@@ -135,6 +128,108 @@ __global__ void __launch_bounds__(256) seed_offsets_kernel(const uint32_t *__res
         }
       seedOff[r] = base + lo;
     }
+}
+
+// ---- stable LSD radix sort of (key, ordinal) pairs, 8 bits per pass --------------------------------------
+// A tile is 4096 consecutive elements; warp w of the tile's block owns elements [512 w, 512 w + 512) and walks them
+// 32 at a time, so "input order" inside a tile is (warp, iteration, lane).
+#define MG_RS_TILE 4096
+#define MG_RS_ITERS 16
+
+__global__ void __launch_bounds__(256) rs_hist_kernel(const uint32_t *__restrict__ keys, uint64_t n, int shift,
+                                                      uint32_t *__restrict__ hist, uint32_t nTiles)
+{
+  __shared__ uint32_t sH[256];
+  sH[threadIdx.x] = 0;
+  __syncthreads();
+  const uint64_t base = (uint64_t)blockIdx.x * MG_RS_TILE;
+#pragma unroll 4
+  for (int r = 0; r < MG_RS_ITERS; ++r)
+    { const uint64_t i = base + (uint64_t)r * 256 + threadIdx.x;
+      if (i < n) atomicAdd(&sH[(keys[i] >> shift) & 255u], 1u);
+    }
+  __syncthreads();
+  hist[(uint64_t)threadIdx.x * nTiles + blockIdx.x] = sH[threadIdx.x];        // digit-major: the scan runs over (digit, tile)
+}
+
+struct RsScan {                 // exclusive scan of the (digit, tile) counts in place
+  uint32_t *h;
+  __device__ uint32_t value(uint64_t i) const { return h[i]; }
+  __device__ void emit(uint64_t i, uint32_t prefix, uint32_t) const { h[i] = prefix; }
+};
+
+// valsIn == nullptr: the ordinals themselves (first pass); keysOut == nullptr: the sorted keys are not wanted (last pass)
+__global__ void __launch_bounds__(256) rs_scatter_kernel(const uint32_t *__restrict__ keysIn, const uint32_t *__restrict__ valsIn,
+                                                         uint64_t n, int shift, const uint32_t *__restrict__ offsets, uint32_t nTiles,
+                                                         uint32_t *__restrict__ keysOut, uint32_t *__restrict__ valsOut)
+{
+  __shared__ uint32_t sCnt[8][256];                     // per warp: elements of each digit seen so far, then their base
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (uint32_t i = tid; i < 8 * 256; i += 256) (&sCnt[0][0])[i] = 0;
+  __syncthreads();
+  const uint64_t first = (uint64_t)blockIdx.x * MG_RS_TILE + (uint64_t)warp * (MG_RS_TILE / 8) + lane;
+  uint32_t key[MG_RS_ITERS], rank[MG_RS_ITERS];
+#pragma unroll
+  for (int it = 0; it < MG_RS_ITERS; ++it)
+    { const uint64_t i = first + (uint64_t)it * 32;
+      const bool valid = i < n;
+      const uint32_t k = valid ? keysIn[i] : 0u;
+      const uint32_t d = valid ? ((k >> shift) & 255u) : 256u;          // lanes past the end form their own group
+      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      const uint32_t r = __popc(peers & ((1u << lane) - 1u));
+      uint32_t old = 0;
+      if (valid && r == 0) { old = sCnt[warp][d]; sCnt[warp][d] = old + __popc(peers); }   // one leader per digit: no conflict
+      old = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1);
+      key[it] = k; rank[it] = old + r;
+      __syncwarp();
+    }
+  __syncthreads();
+  { uint32_t run = offsets[(uint64_t)tid * nTiles + blockIdx.x];          // thread d: where digit d of this tile starts
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { const uint32_t c = sCnt[w][tid]; sCnt[w][tid] = run; run += c; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < MG_RS_ITERS; ++it)
+    { const uint64_t i = first + (uint64_t)it * 32;
+      if (i < n)
+        { const uint32_t dst = sCnt[warp][(key[it] >> shift) & 255u] + rank[it];
+          if (keysOut) keysOut[dst] = key[it];
+          valsOut[dst] = valsIn ? valsIn[i] : (uint32_t)i;
+        }
+    }
+}
+
+// out[j] = ordinal of the j-th pair in (key, ordinal) order; keys < 2^keyBits.  kA, kB, vA, vB: n words of scratch each;
+// hist: 256 * tiles + scan scratch (see rs_scratch_words)
+static uint64_t rs_scratch_words(uint64_t n)
+{
+  const uint64_t tiles = (n + MG_RS_TILE - 1) / MG_RS_TILE, h = 256 * tiles;
+  return h + (h + MG_CP_CHUNK - 1) / MG_CP_CHUNK + 64;
+}
+
+static int rs_sort_ordinals(const uint32_t *dKeys, uint64_t n, int keyBits, uint32_t *kA, uint32_t *kB, uint32_t *vA, uint32_t *vB,
+                            uint32_t *hist, uint32_t *out, cudaStream_t st)
+{
+  const uint32_t tiles = (uint32_t)((n + MG_RS_TILE - 1) / MG_RS_TILE);
+  const uint64_t h = 256ull * tiles;
+  uint32_t *scanScratch = hist + h + 16;
+  unsigned long long *dTotal = (unsigned long long *)(hist + h);          // 8-byte aligned: h is a multiple of 256
+  const int passes = keyBits <= 8 ? 1 : (keyBits + 7) / 8;
+  const uint32_t *kin = dKeys, *vin = nullptr;
+  for (int p = 0; p < passes; ++p)
+    { const bool last = p == passes - 1;
+      uint32_t *kout = last ? nullptr : ((p & 1) ? kB : kA), *vout = last ? out : ((p & 1) ? vB : vA);
+      rs_hist_kernel<<<tiles, 256, 0, st>>>(kin, n, 8 * p, hist, tiles);
+      MG_LAUNCH_CHECK("rs_hist");
+      RsScan f; f.h = hist;
+      int rc = mg_ordered_scan(f, h, scanScratch, dTotal, st);
+      if (rc) return rc;
+      rs_scatter_kernel<<<tiles, 256, 0, st>>>(kin, vin, n, 8 * p, hist, tiles, kout, vout);
+      MG_LAUNCH_CHECK("rs_scatter");
+      kin = kout; vin = vout;
+    }
+  return MODGPU_OK;
 }
 
 static unsigned rgrid(uint64_t n)
@@ -235,20 +330,12 @@ extern "C" ModgpuReference *modgpuReferenceBuild(int bits, int k, int w, int see
   }
   if (nHits)
     { // stable sort of hit ordinals by modset index == the counting sort of modmap.c:88-90
-      if (R->tmp.ensure(nHits * 4, st) || R->tmp2.ensure(nHits * 4, st)) RB_FAIL();
-      iota_kernel<<<rgrid(nHits), 256, 0, st>>>((uint32_t *)R->tmp.p, nHits);
-      if (mg_check_cuda(cudaGetLastError(), "iota", __FILE__, __LINE__)) RB_FAIL();
+      if (R->tmp.ensure(nHits * 16, st) || R->sortTmp.ensure(rs_scratch_words(nHits) * 4, st)) RB_FAIL();
       int endBit = 1;
       while (endBit < 32 && (m >> endBit)) ++endBit;
-      size_t tmpBytes = 0;
-      if (mg_check_cuda(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, (const uint32_t *)R->index.p, (uint32_t *)R->tmp2.p,
-                                                        (const uint32_t *)R->tmp.p, (uint32_t *)R->rev.p, (uint64_t)nHits, 0, endBit, st),
-                        "cub sort size", __FILE__, __LINE__))
-        RB_FAIL();
-      if (R->sortTmp.ensure(tmpBytes + 16, st)) RB_FAIL();
-      if (mg_check_cuda(cub::DeviceRadixSort::SortPairs(R->sortTmp.p, tmpBytes, (const uint32_t *)R->index.p, (uint32_t *)R->tmp2.p,
-                                                        (const uint32_t *)R->tmp.p, (uint32_t *)R->rev.p, (uint64_t)nHits, 0, endBit, st),
-                        "cub sort", __FILE__, __LINE__))
+      uint32_t *w = (uint32_t *)R->tmp.p;
+      if (rs_sort_ordinals((const uint32_t *)R->index.p, nHits, endBit, w, w + nHits, w + 2 * nHits, w + 3 * nHits,
+                           (uint32_t *)R->sortTmp.p, (uint32_t *)R->rev.p, st))
         RB_FAIL();
     }
   if (mg_check_cuda(cudaStreamSynchronize(st), "sync", __FILE__, __LINE__)) RB_FAIL();

@@ -7,11 +7,9 @@
 //   modgpuModsetReadset  == the hot loop of readsetFileRead   reference modasm.c:151-191
 //
 // SURVEY 8(f) "next" rows 1, 3, 4.  Set arithmetic runs on the device (ordered
-// compaction, find-or-insert with first-occurrence numbering); the file
-// functions are host I/O: the only host-side work is the byte layout and the
-// reference's own index[] probe order, which is inherently sequential
-// (modset.c:49-57) and only exists so that an unmodified `modutils -r` can load
-// a GPU-built set.
+// compaction, find-or-insert with first-occurrence numbering, the reference's
+// index[] layout: hostsync.cu); the file functions are host I/O: the only
+// host-side work is the byte layout of the files.
 #include <stdio.h>
 #include <string.h>
 #include <stdlib.h>
@@ -22,6 +20,7 @@
 #include "mg_scan.cuh"
 
 void mg_table_counters(ModgpuTable *t, unsigned long long **entries, uint32_t **error);
+uint8_t *mg_table_info_hi(ModgpuTable *t);
 
 static unsigned sgrid(uint64_t n)
 {
@@ -32,7 +31,8 @@ static unsigned sgrid(uint64_t n)
   return (unsigned)blocks;
 }
 
-static MgSlot *table_slots(ModgpuModset *ms) { return (MgSlot *)modgpuTableDevicePtr(ms->table); }
+MgSlot *mg_table_slots_on(ModgpuTable *t, cudaStream_t st);
+static MgSlot *table_slots(ModgpuModset *ms) { return mg_table_slots_on(ms->table, ms->stream); }
 
 // dense export of a numbered set into one device buffer: value[n] | depth[n] | info[n]
 static int export_dense(ModgpuModset *ms, DevBuf &buf, uint64_t n, uint64_t **dV, uint16_t **dD, uint8_t **dI)
@@ -105,9 +105,10 @@ __global__ void __launch_bounds__(256) merge_insert_kernel(MgSlot *slots, uint32
   if (mg_lane() == 0 && fresh) atomicAdd(entries, (unsigned long long)fresh);
 }
 
-// copy numbers: c = min(c1 + c2, 3), info = (info & 3) | c      (modset.c:124-125)
+// copy numbers: c = min(c1 + c2, 3), info = (info & 3) | c      (modset.c:124-125): every entry of ms1 that ms2 touches
+// loses its flags beyond the copy bits (`&= 0x3`), the others keep theirs
 __global__ void __launch_bounds__(256) merge_copy_kernel(MgSlot *slots, const uint32_t *__restrict__ slotOf,
-                                                         const uint8_t *__restrict__ i2, uint64_t n)
+                                                         const uint8_t *__restrict__ i2, uint64_t n, uint8_t *__restrict__ infoHi)
 {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(256) merge_copy_kernel(MgSlot *slots, const ui
       uint32_t c1 = aux & 3u, c = c1 + (i2[i] & 3u);
       if (c > 3u) c = 3u;
       slots[s].aux = (aux & ~3u) | c1 | c;
+      if (infoHi) infoHi[(aux >> 2) - 1] = 0;
     }
 }
 
@@ -137,13 +139,14 @@ extern "C" int modgpuModsetMerge(ModgpuModset *a, ModgpuModset *b)
   unsigned long long *entries; uint32_t *error;
   mg_table_counters(a->table, &entries, &error);
   MgSlot *slots = table_slots(a);
+  if (!slots) return MODGPU_ECUDA;
   { ProfScope p(a, MODGPU_T_INSERT, 1);
     merge_insert_kernel<<<sgrid(n2), 256, 0, st>>>(slots, mg_table_slot_bits(a->table), dV, dD, n2, dSlot, entries, error);
     MG_LAUNCH_CHECK("merge_insert");
   }
   { ProfScope p(a, MODGPU_T_OTHER, 4);
     if ((rc = modgpuTableNumber(a->table, dSlot, n2, nullptr, st))) return rc;
-    merge_copy_kernel<<<sgrid(n2), 256, 0, st>>>(slots, dSlot, dI, n2);
+    merge_copy_kernel<<<sgrid(n2), 256, 0, st>>>(slots, dSlot, dI, n2, mg_table_info_hi(a->table));
     MG_LAUNCH_CHECK("merge_copy");
   }
   if (modgpuTableEntries(a->table, st) == 0xFFFFFFFFFFFFFFFFull) return MODGPU_EFULL;
@@ -189,17 +192,13 @@ extern "C" int modgpuModsetWriteMod(ModgpuModset *ms, const char *path, int gzip
   std::vector<uint16_t> depth(size, 0);
   std::vector<uint8_t> info(size, 0);
   if (n && (rc = modgpuModsetExport(ms, value.data() + 1, depth.data() + 1, info.data() + 1))) return rc;
-  // index[]: the reference's own open-addressing order - entries inserted in index order, home slot
-  // hash & mask, odd stride from the next hash bits (modset.c:48-57)
+  // index[]: the reference's own open-addressing layout (entries inserted in index order, home slot hash & mask, odd
+  // double-hashing stride: modset.c:48-57), built on the device (hostsync.cu) so that an unmodified `modutils -r` /
+  // `modmap -r` can look k-mers up in a GPU-built set
   const int bits = ms->bits;
-  const uint64_t tableSize = 1ull << bits, mask = tableSize - 1;
+  const uint64_t tableSize = 1ull << bits;
   std::vector<uint32_t> index(tableSize, 0);
-  for (uint32_t i = 1; i <= n; ++i)
-    { uint64_t hash = (value[i] * ms->hasher.factor1) >> ms->hasher.shift1;
-      uint64_t offset = hash & mask, diff = ((hash >> bits) & mask) | 1;
-      while (index[offset]) offset = (offset + diff) & mask;
-      index[offset] = i;
-    }
+  if ((rc = modgpuModsetReferenceIndex(ms, index.data()))) return rc;
   OutFile out;
   if (!out.open(path, gzip)) { mg_set_error("failed to open mod file %s", path); return MODGPU_EINVAL; }
   unsigned char sh[80];
@@ -234,9 +233,11 @@ extern "C" ModgpuModset *modgpuModsetReadMod(const char *path)
   ModgpuModset *ms = nullptr;
   std::vector<uint64_t> value; std::vector<uint16_t> depth; std::vector<uint8_t> info;
   ModgpuHasher h;
-  if (!gz_read_all(z, name, 8) || strcmp(name, "MSHSTv2")) { mg_set_error("bad modset header in %s", path); goto fail; }   // modset.c:92-93
+  if (!gz_read_all(z, name, 8) || memcmp(name, "MSHSTv2", 8)) { mg_set_error("bad modset header in %s", path); goto fail; }   // modset.c:92-93
   if (!gz_read_all(z, &bits, 4) || !gz_read_all(z, &size, 4) || size < 1) { mg_set_error("failed to read bits/size"); goto fail; }
-  if (!gz_read_all(z, name, 8) || strcmp(name, "SQHSHv2") || !gz_read_all(z, sh, 80)) { mg_set_error("seqhash read mismatch"); goto fail; }
+  if (bits < 20 || bits > 34) { mg_set_error("table bits %d must be between 20 and 34 (%s)", bits, path); goto fail; }         // modset.c:17
+  if ((uint64_t)size >= (1ull << (bits - 2))) { mg_set_error("Modset size %u is too big for %d bits (%s)", size, bits, path); goto fail; }   // modset.c:24
+  if (!gz_read_all(z, name, 8) || memcmp(name, "SQHSHv2", 8) || !gz_read_all(z, sh, 80)) { mg_set_error("seqhash read mismatch"); goto fail; }
   if (modgpuHasherFromSeqhash(&h, sh)) goto fail;
   { // index[] is the reference's host-side table: skipped, ours is rebuilt from value[]
     std::vector<char> skip(1 << 24);
@@ -321,6 +322,7 @@ extern "C" uint64_t modgpuModsetReadset(ModgpuModset *ms, const char *bases, con
   for (uint64_t r = 0; r < nSeq; ++r)
     if (offs[r + 1] < offs[r] || offs[r + 1] - offs[r] > 0x7FFFFFFFull) { mg_set_error("bad length of read %llu", (unsigned long long)r); return FAIL; }
   MgSlot *slots = table_slots(ms);
+  if (!slots) return FAIL;
   const uint64_t nSlots = modgpuTableSlots(ms->table);
   if (resetDepth)
     { zero_counts_kernel<<<sgrid(nSlots), 256, 0, st>>>(slots, nSlots);      // memset (rs->ms->depth, 0, ..), modasm.c:158

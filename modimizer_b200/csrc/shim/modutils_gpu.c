@@ -70,7 +70,10 @@ static void addFile (char *filename, int is10x)
   U64 nSeq = 0, totLen = 0 ;
   while (seqIOread (si))
     { ++nSeq ; totLen += si->seqLen ;
-      if (is10x && (nSeq & 1)) batchPut (&b, sqioSeq(si) + 23, si->seqLen - 23) ;  /* modutils.c:44 */
+      if (is10x && (nSeq & 1))                                                    /* modutils.c:44: int len = seqLen-23; */
+        { if (si->seqLen > 23) batchPut (&b, sqioSeq(si) + 23, si->seqLen - 23) ;   /* a negative length has no k-mer (seqhash.c:162) */
+          else batchPut (&b, sqioSeq(si), 0) ;
+        }
       else batchPut (&b, sqioSeq(si), si->seqLen) ;
     }
   batchFlush (&b) ;

@@ -50,6 +50,11 @@ struct ModgpuTable {
   uint64_t bulkRoom, bulkUsed;    // expected k-mers the open buckets were sized for / scattered so far
   uint64_t bulkOvfSeen;           // overflow-list entries in use after the last committed chunk (host copy)
   uint32_t *dCursorSnap;          // the fill counts before the chunk in flight (rollback of a skewed chunk)
+  // Modset.info beyond the two copy bits (MS_MINOR, MS_REPEAT, MS_INTERNAL, MS_RDNA: modset.h:49-52, set by modasm):
+  // info >> 2 per dense index, kept beside the table once an import carried an info array; aux holds only the copy bits
+  uint8_t *dInfoHi;
+  uint64_t infoHiCap;
+  bool trackInfo;
 };
 
 // ------------------------------------------------------------------ kernels
@@ -64,7 +69,7 @@ __global__ void __launch_bounds__(256) table_clear_kernel(MgSlot *slots, uint64_
 
 // n is read from device memory (the count hash_select just produced) so that no
 // host round trip sits between select and insert; nHost bounds it (the cap).
-template <bool EXACT, bool STRICT = false>       // STRICT: a device count beyond the capacity means "incomplete list": do nothing
+template <bool EXACT, bool STRICT = false, bool COUNT = true>   // STRICT: a device count beyond the capacity means "incomplete list": do nothing
 __global__ void __launch_bounds__(256) table_insert_kernel(MgSlot *slots, uint32_t slotBits,
                                                            const uint64_t *__restrict__ kmers,
                                                            const unsigned long long *__restrict__ nDev, uint64_t nHost,
@@ -82,7 +87,7 @@ __global__ void __launch_bounds__(256) table_insert_kernel(MgSlot *slots, uint32
       uint64_t s = probe_insert(slots, slotBits, key, &isNew);
       if (s == 0xFFFFFFFFFFFFFFFFull) { atomicExch(error, 1u); if (slotOut) slotOut[i] = 0xFFFFFFFFu; continue; }
       fresh += isNew ? 1u : 0u;
-      atomicAdd(&slots[s].count, 1u);
+      if (COUNT) atomicAdd(&slots[s].count, 1u);        // COUNT false: modsetIndexFind (.., true) alone, the caller owns the depth
       if (EXACT) atomicMin(&slots[s].aux, MG_AUX_ORD + (uint32_t)i);
       if (slotOut) slotOut[i] = (uint32_t)s;
     }
@@ -229,11 +234,15 @@ __global__ void __launch_bounds__(256, 5) region_build_pipe_kernel(MgSlot *slots
                                                                 const uint32_t *__restrict__ cursors, uint32_t cap, uint32_t nSrc,
                                                                 uint64_t srcStride, uint32_t nRegions,
                                                                 unsigned long long *entries, uint32_t *error,
-                                                                const uint32_t *__restrict__ guard = nullptr, uint32_t guardLimit = 0)
+                                                                const uint32_t *__restrict__ guard = nullptr, uint32_t guardLimit = 0,
+                                                                int emptyOnSkip = 0)
 {
   __shared__ uint4 sR[MG_REGION_SLOTS];
-  // the scatter that filled the buckets ran out of overflow space: the batch is incomplete, touch nothing
-  if (guard && __ldg(guard) > guardLimit) return;
+  // the scatter that filled the buckets ran out of overflow space: the batch is incomplete, touch nothing - or, when the
+  // caller cannot undo its bookkeeping (the sharded build: every rank takes the same decision from the same flags), create
+  // the regions of a fresh table empty and add nothing
+  const bool skip = guard && __ldg(guard) > guardLimit;
+  if (skip && !(FRESH && emptyOnSkip)) return;
   __shared__ const uint64_t *sSrc[MODGPU_MAX_PEERS];            // (a dynamically indexed kernel parameter would live in local memory)
   MgSlot *sS = reinterpret_cast<MgSlot *>(sR);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -264,7 +273,7 @@ __global__ void __launch_bounds__(256, 5) region_build_pipe_kernel(MgSlot *slots
 
   auto count_of = [&](int q, uint32_t region) -> uint32_t {
     uint32_t c = 0;
-    if (uOn[q] && region < nRegions) { c = __ldg(uCur[q] + region); if (c > cap) c = cap; }
+    if (uOn[q] && region < nRegions && !skip) { c = __ldg(uCur[q] + region); if (c > cap) c = cap; }
     return c;
   };
   auto load_key = [&](int q, uint32_t region, uint32_t j) -> unsigned long long {
@@ -523,7 +532,8 @@ __global__ void __launch_bounds__(256) table_classify_kernel(MgSlot *slots, uint
 }
 
 __global__ void __launch_bounds__(256) table_export_kernel(const MgSlot *slots, uint64_t nSlots,
-                                                           uint64_t *value, uint16_t *depth, uint8_t *info, uint32_t *count32)
+                                                           uint64_t *value, uint16_t *depth, uint8_t *info, uint32_t *count32,
+                                                           const uint8_t *__restrict__ infoHi)
 {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nSlots; i += stride)
@@ -532,7 +542,7 @@ __global__ void __launch_bounds__(256) table_export_kernel(const MgSlot *slots, 
       uint32_t ix = (v.w >> 2) - 1;                      // reference indices are 1-based
       if (value) value[ix] = ((uint64_t)v.y << 32) | v.x;
       if (depth) depth[ix] = (uint16_t)clamp16(v.z);
-      if (info) info[ix] = (uint8_t)(v.w & 3u);
+      if (info) info[ix] = (uint8_t)((v.w & 3u) | (infoHi ? ((uint32_t)infoHi[ix] << 2) : 0u));   // the whole byte (modset.c:73,87)
       if (count32) count32[ix] = v.z;
     }
 }
@@ -541,12 +551,13 @@ __global__ void __launch_bounds__(256) table_import_kernel(MgSlot *slots, uint32
                                                            const uint64_t *__restrict__ value,
                                                            const uint16_t *__restrict__ depth,
                                                            const uint8_t *__restrict__ info, uint64_t n, uint64_t indexBase,
-                                                           unsigned long long *entries, uint32_t *error)
+                                                           unsigned long long *entries, uint32_t *error, uint8_t *__restrict__ infoHi)
 {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   uint32_t fresh = 0;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     { bool isNew;
+      if (infoHi) infoHi[indexBase + i] = info ? (uint8_t)(info[i] >> 2) : (uint8_t)0;
       uint64_t s = probe_insert(slots, slotBits, value[i], &isNew);
       if (s == 0xFFFFFFFFFFFFFFFFull || !isNew) { atomicExch(error, s == 0xFFFFFFFFFFFFFFFFull ? 1u : 2u); continue; }
       ++fresh;
@@ -571,6 +582,13 @@ extern "C" ModgpuTable *modgpuTableCreate(int bits, void *stream)
 {
   if (bits < 20 || bits > 34)                            // modset.c:17
     { mg_set_error("table bits %d must be between 20 and 34", bits); return nullptr; }
+  // slot ids travel as uint32 (slotOf / slotOut arrays of the exact-order, merge and readset paths; 0xFFFFFFFF = none),
+  // and the dense index has 30 bits beside the two copy bits: one GPU table stops at bits 32 (2^31 slots = 32 GiB,
+  // 805 M entries).  The reference's 33 and 34 are reached by sharding the table over GPUs (modgpuSharded*).
+  if (bits > 32)
+    { mg_set_error("table bits %d: one GPU table supports 20..32 (2^31 slots, 805 M entries); shard larger sets over GPUs", bits);
+      return nullptr;
+    }
   // random 16-byte probes: ask L2 to fetch 32-byte sectors instead of whole lines
   // (MODGPU_L2_FETCH=32|64|128 overrides; measured in profiles/)
   { const char *g = getenv("MODGPU_L2_FETCH");
@@ -587,6 +605,7 @@ extern "C" ModgpuTable *modgpuTableCreate(int bits, void *stream)
   t->slots = nullptr; t->dEntries = nullptr; t->dError = nullptr; t->dScratch = nullptr; t->hPinned = nullptr;
   t->clearPending = false; t->dBuckets = nullptr; t->bucketBytes = 0; t->dCursors = nullptr; t->dOverflow = nullptr; t->overflowCap = 0;
   t->bulkOpen = false; t->bulkRoom = t->bulkUsed = t->bulkOvfSeen = 0; t->dCursorSnap = nullptr;
+  t->dInfoHi = nullptr; t->infoHiCap = 0; t->trackInfo = false;
   t->scratchWords = t->nSlots / MG_CP_CHUNK + 1024;
   if (mg_check_cuda(cudaMalloc(&t->slots, t->nSlots * sizeof(MgSlot)), "cudaMalloc(table)", __FILE__, __LINE__) ||
       mg_check_cuda(cudaMalloc(&t->dEntries, 64), "cudaMalloc", __FILE__, __LINE__) ||
@@ -609,6 +628,7 @@ extern "C" void modgpuTableDestroy(ModgpuTable *t)
   if (t->dCursors) cudaFree(t->dCursors);
   if (t->dOverflow) cudaFree(t->dOverflow);
   if (t->dCursorSnap) cudaFree(t->dCursorSnap);
+  if (t->dInfoHi) cudaFree(t->dInfoHi);
   delete t;
 }
 
@@ -635,8 +655,36 @@ extern "C" int modgpuTableClear(ModgpuTable *t, void *stream)
   t->numbered = 0;
   t->clearPending = true;
   t->bulkOpen = false;                                   // k-mers waiting in open buckets are dropped with the rest
+  t->trackInfo = false;                                  // an empty set has no info bytes
   return MODGPU_OK;
 }
+
+// the info side array covers dense indices 1..n (entry i at [i-1]); new entries start with no flags
+static int ensure_info_hi(ModgpuTable *t, uint64_t n, uint64_t have, cudaStream_t st)
+{
+  if (n > t->infoHiCap)
+    { uint8_t *q = nullptr;
+      const uint64_t want = n + n / 4 + 4096;
+      MG_CUDA(cudaMalloc(&q, want));
+      if (t->dInfoHi && have) MG_CUDA(cudaMemcpyAsync(q, t->dInfoHi, have, cudaMemcpyDeviceToDevice, st));
+      if (t->dInfoHi) { MG_CUDA(cudaStreamSynchronize(st)); cudaFree(t->dInfoHi); }
+      t->dInfoHi = q; t->infoHiCap = want;
+    }
+  if (n > have) MG_CUDA(cudaMemsetAsync(t->dInfoHi + have, 0, n - have, st));
+  return MODGPU_OK;
+}
+
+uint8_t *mg_table_info_hi(ModgpuTable *t) { return t->trackInfo ? t->dInfoHi : nullptr; }
+// start keeping whole info bytes for the entries numbered so far (no flags yet)
+int mg_table_ensure_info(ModgpuTable *t, cudaStream_t st)
+{
+  if (t->trackInfo) return MODGPU_OK;
+  int rc = ensure_info_hi(t, t->numbered, 0, st);
+  if (rc) return rc;
+  t->trackInfo = true;
+  return MODGPU_OK;
+}
+void mg_table_set_track_info(ModgpuTable *t, bool on) { t->trackInfo = on; }
 
 // ---- bulk insert in three steps, so that hash_select can do the scatter itself:
 //   mg_table_bulk_begin   size + zero the per-region buckets for ~expectedN k-mers
@@ -833,13 +881,21 @@ int mg_table_build_from_buckets(ModgpuTable *t, const uint64_t *d_buckets, const
   return MODGPU_OK;
 }
 
-// build every region from the buckets in nSrc ranks' memory (peer-mapped) + their overflow segments
-int mg_table_build_from_peers(ModgpuTable *t, const uint64_t *const *d_buckets, const uint32_t *d_cursors, uint32_t cap, uint32_t nSrc,
-                              const uint64_t *const *d_overflow, uint64_t overflowCap, const uint32_t *d_ovfCounts, cudaStream_t st)
+// build every region from the buckets in nSrc ranks' memory (peer-mapped) + their overflow segments.
+// d_cursors: [nSrc][cursorStride] fill counts (cursorStride >= nRegions; 0 = nRegions); d_ovfCounts[s * ovfStride];
+// d_guard (nullable): a device word > 0 means "some rank lost k-mers of this group": build nothing (a fresh table is
+// created empty) - every rank sees the same flags, so the group is applied everywhere or nowhere.
+__global__ void peer_ovf_count_kernel(unsigned long long *wide, const uint32_t *count, const uint32_t *guard)
+{ *wide = (guard && *guard) ? 0ull : (unsigned long long)*count; }
+
+int mg_table_build_from_peers_ex(ModgpuTable *t, const uint64_t *const *d_buckets, const uint32_t *d_cursors, uint64_t cursorStride,
+                                 uint32_t cap, uint32_t nSrc, const uint64_t *const *d_overflow, uint64_t overflowCap,
+                                 const uint32_t *d_ovfCounts, uint64_t ovfStride, const uint32_t *d_guard, cudaStream_t st)
 {
   if (nSrc < 1 || nSrc > MODGPU_MAX_PEERS) { mg_set_error("build from peers: %u sources out of range 1..%d", nSrc, MODGPU_MAX_PEERS); return MODGPU_EINVAL; }
   if (t->bulkOpen) { int rc = mg_table_bulk_close(t, st); if (rc) return rc; }
   const uint32_t nRegions = (uint32_t)(t->nSlots >> MG_REGION_BITS);
+  if (!cursorStride) cursorStride = nRegions;
   MgPeerSrc src;
   for (uint32_t s = 0; s < MODGPU_MAX_PEERS; ++s) src.p[s] = d_buckets[s < nSrc ? s : 0];
   static int blocksPerSm = 0;
@@ -849,7 +905,7 @@ int mg_table_build_from_peers(ModgpuTable *t, const uint64_t *const *d_buckets, 
     }
   uint32_t grid = (uint32_t)mg_num_sms() * (uint32_t)blocksPerSm;
   if (grid > nRegions) grid = nRegions;
-#define MG_PIPE_LAUNCH(FR, UN) region_build_pipe_kernel<FR, true, UN><<<grid, 256, 0, st>>>(t->slots, t->slotBits, src, d_cursors, cap, nSrc, nRegions, nRegions, t->dEntries, t->dError)
+#define MG_PIPE_LAUNCH(FR, UN) region_build_pipe_kernel<FR, true, UN><<<grid, 256, 0, st>>>(t->slots, t->slotBits, src, d_cursors, cap, nSrc, cursorStride, nRegions, t->dEntries, t->dError, d_guard, 0u, 1)
   if (t->clearPending)
     { if (nSrc <= 8) MG_PIPE_LAUNCH(true, 1); else MG_PIPE_LAUNCH(true, 2);
       t->clearPending = false;
@@ -861,14 +917,17 @@ int mg_table_build_from_peers(ModgpuTable *t, const uint64_t *const *d_buckets, 
   // the (rare) k-mers that did not fit their bucket at the sender: direct inserts reading the peer's segment
   for (uint32_t s = 0; d_overflow && s < nSrc; ++s)
     { unsigned long long *wide = t->dEntries + 4 + (s & 3);
-      MG_CUDA(cudaMemsetAsync(wide, 0, 8, st));
-      MG_CUDA(cudaMemcpyAsync(wide, d_ovfCounts + s, 4, cudaMemcpyDeviceToDevice, st));
+      peer_ovf_count_kernel<<<1, 1, 0, st>>>(wide, d_ovfCounts + s * ovfStride, d_guard);
       table_insert_kernel<false><<<grid_for(65536, 4), 256, 0, st>>>(t->slots, t->slotBits, d_overflow[s], wide,
                                                                      overflowCap, nullptr, t->dEntries, t->dError);
       MG_LAUNCH_CHECK("overflow_insert");
     }
   return MODGPU_OK;
 }
+
+int mg_table_build_from_peers(ModgpuTable *t, const uint64_t *const *d_buckets, const uint32_t *d_cursors, uint32_t cap, uint32_t nSrc,
+                              const uint64_t *const *d_overflow, uint64_t overflowCap, const uint32_t *d_ovfCounts, cudaStream_t st)
+{ return mg_table_build_from_peers_ex(t, d_buckets, d_cursors, 0, cap, nSrc, d_overflow, overflowCap, d_ovfCounts, 1, nullptr, st); }
 
 bool mg_table_clear_pending(const ModgpuTable *t) { return t->clearPending; }
 // the guarded build kernels of mg_table_bulk_finish did nothing (overflow list too small): undo the host bookkeeping
@@ -890,6 +949,14 @@ extern "C" void *modgpuTableDevicePtr(const ModgpuTable *t)
   return t->slots;
 }
 
+// internal: the slot array for kernels launched on `st` (the pending clear / deferred build run on the same stream:
+// ordered before them without a device-wide synchronisation)
+MgSlot *mg_table_slots_on(ModgpuTable *t, cudaStream_t st)
+{
+  if ((t->clearPending || t->bulkOpen) && ensure_cleared(t, st)) return nullptr;
+  return t->slots;
+}
+
 // internal: insert with the element count taken from device memory
 int mg_table_insert_dev(ModgpuTable *t, const uint64_t *d_kmers, const uint64_t *d_n, uint64_t nMax,
                         uint32_t *d_slot, int exactOrder, cudaStream_t st)
@@ -901,7 +968,9 @@ int mg_table_insert_dev(ModgpuTable *t, const uint64_t *d_kmers, const uint64_t 
   // two waves of resident blocks measured faster than one on B200 for this
   // latency-bound probe loop (profiles/README.md, insert sweep)
   unsigned grid = grid_for(nMax, 16);
-  if (exactOrder)
+  if (exactOrder == 2)                                   // find-or-insert without counting
+    table_insert_kernel<true, false, false><<<grid, 256, 0, st>>>(t->slots, t->slotBits, d_kmers, (const unsigned long long *)d_n, nMax, d_slot, t->dEntries, t->dError);
+  else if (exactOrder)
     table_insert_kernel<true><<<grid, 256, 0, st>>>(t->slots, t->slotBits, d_kmers, (const unsigned long long *)d_n, nMax, d_slot, t->dEntries, t->dError);
   else
     table_insert_kernel<false><<<grid, 256, 0, st>>>(t->slots, t->slotBits, d_kmers, (const unsigned long long *)d_n, nMax, d_slot, t->dEntries, t->dError);
@@ -970,6 +1039,7 @@ extern "C" int modgpuTableNumber(ModgpuTable *t, const uint32_t *d_slot, uint64_
       int rc = run_compaction(t, f, t->nSlots, &added, st);
       if (rc) return rc;
     }
+  if (t->trackInfo && added) { int rc = ensure_info_hi(t, t->numbered + added, t->numbered, st); if (rc) return rc; }
   t->numbered += added;
   if (t->numbered > t->maxEntries)
     { mg_set_error("hashTableSize %llu is too small for %llu (table bits %d)",
@@ -1030,7 +1100,8 @@ extern "C" int modgpuTableExport(ModgpuTable *t, uint64_t *d_value, uint16_t *d_
                                  uint32_t *d_count32, void *stream)
 {
   { int rc = ensure_cleared(t, (cudaStream_t)stream); if (rc) return rc; }
-  table_export_kernel<<<grid_for(t->nSlots, 8), 256, 0, (cudaStream_t)stream>>>(t->slots, t->nSlots, d_value, d_depth, d_info, d_count32);
+  table_export_kernel<<<grid_for(t->nSlots, 8), 256, 0, (cudaStream_t)stream>>>(t->slots, t->nSlots, d_value, d_depth, d_info, d_count32,
+                                                                                t->trackInfo ? t->dInfoHi : nullptr);
   MG_LAUNCH_CHECK("table_export");
   return MODGPU_OK;
 }
@@ -1042,7 +1113,14 @@ extern "C" int modgpuTableImport(ModgpuTable *t, const uint64_t *d_value, const 
   if (t->numbered + n > t->maxEntries)
     { mg_set_error("Modset size %llu is too big for %d bits", (unsigned long long)(t->numbered + n), t->bits); return MODGPU_EFULL; }
   { int rc = ensure_cleared(t, (cudaStream_t)stream); if (rc) return rc; }
-  table_import_kernel<<<grid_for(n, 16), 256, 0, (cudaStream_t)stream>>>(t->slots, t->slotBits, d_value, d_depth, d_info, n, t->numbered, t->dEntries, t->dError);
+  // an info array brings the whole byte: the flags beyond the copy bits live in the side array from here on
+  if (d_info && !t->trackInfo)
+    { int rc = ensure_info_hi(t, t->numbered, 0, (cudaStream_t)stream); if (rc) return rc;
+      t->trackInfo = true;
+    }
+  if (t->trackInfo) { int rc = ensure_info_hi(t, t->numbered + n, t->numbered, (cudaStream_t)stream); if (rc) return rc; }
+  table_import_kernel<<<grid_for(n, 16), 256, 0, (cudaStream_t)stream>>>(t->slots, t->slotBits, d_value, d_depth, d_info, n, t->numbered, t->dEntries, t->dError,
+                                                                         t->trackInfo ? t->dInfoHi : nullptr);
   MG_LAUNCH_CHECK("table_import");
   t->numbered += n;
   return MODGPU_OK;

@@ -1,6 +1,11 @@
 """Hash-sharded modset over the GPUs of one node: one process per GPU,
 torch.distributed (NCCL over NVLink/NVSwitch) for the plumbing.
 
+The sharded build itself is C (modimizer_b200/csrc/sharded.cu, modgpuSharded* in include/modgpu.h): this class is its
+ctypes mirror, binding the three communicator callbacks (equal-split all-to-all on a stream, host all-gather,
+barrier) to torch.distributed.  The older exchange flavours (buckets through an NCCL all-to-all, per-owner segments,
+list exchange) stay here in Python as fallbacks and A/B references.
+
 The reference has no distributed mode; its offline recipe is one modset per
 input merged with modsetMerge (reference modset.c:106-128, modutils.c:101-103).
 Here reads are sharded by input chunk, the table by an independent hash of the
@@ -39,6 +44,62 @@ def exchange(send, send_counts, group=None):
     return recv, hr
 
 
+class _Comm(C.Structure):
+    """ModgpuComm (include/modgpu.h)"""
+    A2A = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+    AG = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
+    BAR = C.CFUNCTYPE(C.c_int, C.c_void_p)
+    _fields_ = [("ctx", C.c_void_p), ("rank", C.c_int), ("world", C.c_int), ("alltoall", A2A), ("allgather", AG), ("barrier", BAR)]
+
+
+class _DevBytes:
+    """a raw device pointer as a CUDA-array-interface object (torch.as_tensor wraps it without a copy)"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def torch_comm(group, dev):
+    """the three ModgpuComm callbacks on torch.distributed; returns (struct, keepalive)"""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def a2a(ctx, d_send, d_recv, per_peer, stream):
+        try:
+            n = int(per_peer) * world
+            send = torch.as_tensor(_DevBytes(d_send, n), device=dev)
+            recv = torch.as_tensor(_DevBytes(d_recv, n), device=dev)
+            dist.all_to_all_single(recv, send, group=group)         # ordered on torch's current stream = the modset's stream
+            return 0
+        except Exception:                                            # never let an exception cross the C frame
+            import traceback; traceback.print_exc()
+            return -1
+
+    def ag(ctx, h_in, h_out, nbytes):
+        try:
+            nbytes = int(nbytes)
+            mine = torch.frombuffer(bytearray(C.string_at(h_in, nbytes)), dtype=torch.uint8).to(dev)
+            out = torch.empty(world * nbytes, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(out, mine, group=group)
+            C.memmove(h_out, out.cpu().numpy().tobytes(), world * nbytes)
+            return 0
+        except Exception:
+            import traceback; traceback.print_exc()
+            return -1
+
+    def bar(ctx):
+        try:
+            dist.barrier(group=group)
+            return 0
+        except Exception:
+            import traceback; traceback.print_exc()
+            return -1
+
+    cbs = (_Comm.A2A(a2a), _Comm.AG(ag), _Comm.BAR(bar))
+    comm = _Comm(None, rank, world, *cbs)
+    return comm, cbs
+
+
 class ShardedModset:
     """A modset whose table is sharded over the ranks of `group` by k-mer hash.
 
@@ -50,9 +111,14 @@ class ShardedModset:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.local = Modset(bits, k, w, seed)
         self._lib = _lib.load()
         self.dev = torch.device("cuda", torch.cuda.current_device())
+        # the C sharded modset owns this rank's shard; self.local is the reference-style view of it
+        self._comm, self._comm_keep = torch_comm(group, self.dev)
+        self._sh = self._lib.modgpuShardedCreate(bits, k, w, seed, C.byref(self._comm))
+        if not self._sh:
+            raise ModgpuError("modgpuShardedCreate: " + _lib.last_error())
+        self.local = Modset(bits, k, w, seed, _handle=self._lib.modgpuShardedLocal(self._sh), _owner=self)
         # all kernels and NCCL calls are ordered on torch's current stream
         self.local.set_stream(torch.cuda.current_stream().cuda_stream)
         self.total_selected = 0
@@ -69,7 +135,6 @@ class ShardedModset:
         # deferred peer build (set_accumulate): the k-mers of up to `accumulate` batches wait in the peer buckets and one
         # exchange + build applies them all - a populated per-rank table is rewritten once per group, not per batch
         self.accumulate = 1
-        self._p2p = None
         self._peer_cap = 0
         self._seg_cap = 0
         self._sel_pending = 0
@@ -77,139 +142,36 @@ class ShardedModset:
         self._ovf_acc = torch.zeros(1, dtype=torch.int32, device=self.dev)
 
     def close(self):
-        self._p2p_release()
-        self.local.close()
+        if self._sh:
+            self._lib.modgpuShardedDestroy(self._sh)            # COLLECTIVE (barrier before the peer buffers are unmapped)
+            self._sh = None
+            self.local._p = None
 
-    # ---- peer-memory exchange (fused_mode "p2p") -----------------------------
-    def _p2p_release(self):
-        st = self._p2p
-        self._p2p = None
-        if not st:
-            return
-        torch.cuda.synchronize()
-        if dist.is_initialized() and self.world > 1:
-            dist.barrier(group=self.group)              # nobody still reads my buffers
-        for p in st["opened"]:
-            self._lib.modgpuPeerClose(C.c_void_p(p))
-        for p in st["mine"]:
-            self._lib.modgpuPeerFree(C.c_void_p(p))
-
+    # ---- peer-memory exchange (fused_mode "p2p"): modgpuSharded* (csrc/sharded.cu) ---------------------------
     def reserve(self, max_bases_per_batch):
         """COLLECTIVE: size and map the peer buckets for batches of up to max_bases_per_batch bases per rank.
-        Called implicitly by the first add; call it again (on every rank) before feeding larger batches -
-        a batch larger than reserved still works, its surplus travels in the overflow segments."""
-        import math
-        lib, G = self._lib, self.world
-        R = int(lib.modgpuModsetRegions(self.local._p))
-        t = torch.tensor([int(max_bases_per_batch)], dtype=torch.int64, device=self.dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
-        nb = int(t.item())
-        expected = (nb // max(self.w, 1) + 1) * self.accumulate     # a group of batches shares the buckets
-        mean = expected / float(G * R)
-        cap = (int(1.1 * mean + 4.0 * math.sqrt(mean) + 8) + 1) & ~1
-        ovf_cap = max(65536, expected // 4)
-        self._p2p_release()
-        mine, opened, ok = [], [], 1
-        sb, so = [], []
-        for b in range(2):                               # double buffered: one barrier per batch suffices
-            p1 = lib.modgpuPeerAlloc(G * R * cap * 8)
-            p2 = lib.modgpuPeerAlloc(G * ovf_cap * 8)
-            if not p1 or not p2:
-                ok = 0
-            sb.append(p1 or 0); so.append(p2 or 0)
-            mine += [x for x in (p1, p2) if x]
-        handles = []
-        for ptr in sb + so:
-            h = (C.c_ubyte * 64)()
-            if not ptr or lib.modgpuPeerExport(C.c_void_p(ptr), h) != 0:
-                ok = 0
-            handles.append(bytes(h))
-        allh = [None] * G
-        dist.all_gather_object(allh, (ok, handles), group=self.group)
-        ok = min(x[0] for x in allh)
-        # peer pointers, already offset to THIS owner's part of every source's arrays
-        bptr = [(C.c_void_p * G)() for _ in range(2)]
-        optr = [(C.c_void_p * G)() for _ in range(2)]
-        if ok:
-            for s_rank in range(G):
-                ptrs = []
-                for i, hb in enumerate(allh[s_rank][1]):
-                    if s_rank == self.rank:
-                        ptrs.append((sb + so)[i])
-                    else:
-                        q = lib.modgpuPeerOpen(hb)
-                        if not q:
-                            ok = 0
-                            q = 0
-                        else:
-                            opened.append(q)
-                        ptrs.append(q)
-                for b in range(2):
-                    bptr[b][s_rank] = ptrs[b] + self.rank * R * cap * 8
-                    optr[b][s_rank] = ptrs[2 + b] + self.rank * ovf_cap * 8
-        t = torch.tensor([ok], dtype=torch.int64, device=self.dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
-        self._p2p = {"mine": mine, "opened": opened}
-        if not int(t.item()):                            # some rank could not map a peer: everybody uses NCCL
-            self._p2p_release()
+        Called implicitly by the first add.  False when a rank could not map its peers (everybody then uses NCCL)."""
+        if self._lib.modgpuShardedReserve(self._sh, int(max_bases_per_batch)) != 0:
             self.fused_mode = "peer"
             return False
-        self._p2p.update(cap=cap, ovf_cap=ovf_cap, R=R, sb=sb, so=so, bptr=bptr, optr=optr, batch=0, pending=0,
-                         sc=torch.zeros(G * R, dtype=torch.int32, device=self.dev),
-                         rc=torch.zeros(G * R, dtype=torch.int32, device=self.dev),
-                         soc=torch.zeros(G, dtype=torch.int32, device=self.dev),
-                         roc=torch.zeros(G, dtype=torch.int32, device=self.dev),
-                         cnt=torch.zeros(1, dtype=torch.int64, device=self.dev))
+        self._reserved = True
         return True
-
-    def _p2p_add(self, select, nbases):
-        """select(sb, cap, sc, so, ovf_cap, soc, cnt) launches this rank's hash/select into bucket set `sb`"""
-        if self._p2p is None and not self.reserve(nbases):
-            return False
-        st = self._p2p
-        b = st["batch"] & 1                      # the bucket set of this group of batches
-        if st["pending"]:                        # joins the batches already waiting: fill counts are kept (MODGPU_SEL_APPEND)
-            flags = getattr(self.local, "_flags", 0)
-            check(self._lib.modgpuModsetSetFlags(self.local._p, flags | 128), "set_flags")
-            try:
-                select(st["sb"][b], st["cap"], st["sc"], st["so"][b], st["ovf_cap"], st["soc"], st["cnt"])
-            finally:
-                check(self._lib.modgpuModsetSetFlags(self.local._p, flags), "set_flags")
-        else:
-            select(st["sb"][b], st["cap"], st["sc"], st["so"][b], st["ovf_cap"], st["soc"], st["cnt"])
-        st["pending"] += 1
-        if st["pending"] >= self.accumulate:
-            self._p2p_flush()
-        return True
-
-    def _p2p_flush(self):
-        """COLLECTIVE: exchange the fill counts of the waiting batches and build them into the owners' tables"""
-        st, g, G = self._p2p, self.group, self.world
-        if not st or not st["pending"]:
-            return
-        b = st["batch"] & 1
-        st["batch"] += 1
-        st["pending"] = 0
-        # fill counts to the owners; completing these two small collectives also means every rank's select is done
-        dist.all_to_all_single(st["rc"], st["sc"], group=g)
-        dist.all_to_all_single(st["roc"], st["soc"], group=g)
-        check(self._lib.modgpuModsetBuildFromPeers(self.local._p, st["bptr"][b], C.c_void_p(st["rc"].data_ptr()), st["cap"], G,
-                                                   st["optr"][b], st["ovf_cap"], C.c_void_p(st["roc"].data_ptr())), "buildFromPeers")
-        self._sel_acc += st["cnt"]
-        self._ovf_acc = torch.maximum(self._ovf_acc, (st["soc"].max() > st["ovf_cap"]).to(torch.int32).reshape(1))
 
     def set_accumulate(self, n_batches):
         """COLLECTIVE: up to n_batches batches share one count exchange and one peer build (peer-memory mode).  What
         is waiting reaches the tables at synchronize() - call it before reading the local sets."""
-        if self.world > 1:
-            self._p2p_flush()
-            self._p2p_release()                  # the buckets are sized for a group: mapped again by the next add
         self.accumulate = max(1, int(n_batches))
+        if self.world > 1:
+            check(self._lib.modgpuShardedSetAccumulate(self._sh, self.accumulate), "shardedSetAccumulate")
+            self._reserved = False
+
+    def set_robust(self, on=True):
+        """COLLECTIVE: overflow segments sized for the worst case (after a ModgpuError about a skipped group)"""
+        check(self._lib.modgpuShardedSetRobust(self._sh, 1 if on else 0), "shardedSetRobust")
+        self._reserved = False
 
     def clear(self):
-        if self._p2p and self._p2p["pending"]:   # batches waiting in the peer buckets are dropped with the rest; the next
-            self._p2p["pending"] = 0             # group reuses the same bucket set (no peer has been told to read it)
-        check(self._lib.modgpuModsetClear(self.local._p), "modsetClear")
+        check(self._lib.modgpuShardedClear(self._sh), "shardedClear")
 
     def _route_and_insert(self, kptr, n):
         st = torch.cuda.current_stream().cuda_stream
@@ -298,17 +260,23 @@ class ShardedModset:
         return True
 
     def synchronize(self):
-        """finish the outstanding fused batches; returns the number of k-mers this rank selected since the
-        last call.  Raises when a segment overflowed (heavily skewed batch): repeat it with fused = False."""
+        """COLLECTIVE: finish the outstanding batches; returns the number of k-mers this rank selected since the last
+        call.  Raises when a group of batches was skipped for skew: NOTHING of it was applied on any rank (the C layer
+        decides from flags every rank receives) - set_robust() or fused = False, then add those batches again."""
         if self.world == 1:
             n, self.total_selected = self.total_selected, 0
             return n
-        self._p2p_flush()
+        nsel = C.c_uint64(0)
+        rc = self._lib.modgpuShardedSynchronize(self._sh, C.byref(nsel))
         vals = torch.cat([self._sel_acc, self._ovf_acc.to(torch.int64)]).cpu().tolist()
         self._sel_acc.zero_(); self._ovf_acc.zero_()
+        n, self._sel_pending = int(nsel.value) + int(vals[0]) + self._sel_pending, 0
+        if rc != 0:
+            raise ModgpuError("sharded synchronize (%d): %s" % (rc, _lib.last_error()))
         if vals[1]:
-            raise ModgpuError("owner segment overflow (skewed batch): repeat with ShardedModset.fused = False")
-        n, self._sel_pending = int(vals[0]) + self._sel_pending, 0
+            # the NCCL fallback flavours ("peer" checks before it builds; "segments" does not): state which
+            raise ModgpuError("owner segment overflow in fused_mode '%s' (skewed batch): clear() and rebuild with "
+                              "ShardedModset.fused = False" % self.fused_mode)
         return n
 
     def add_device(self, d_bases, d_offsets, nseq, nbases, is_ascii=0):
@@ -318,12 +286,9 @@ class ShardedModset:
             self.total_selected += n
             return n
         if self.fused and self.fused_mode == "p2p":
-            def sel(sb, cap, sc, so, oc, soc, cnt):
-                check(self._lib.modgpuModsetSelectBucketsDevice(self.local._p, C.c_void_p(d_bases), C.c_void_p(d_offsets), nseq, nbases,
-                                                                is_ascii, self.world, C.c_void_p(sb), cap, C.c_void_p(sc.data_ptr()),
-                                                                C.c_void_p(so), oc, C.c_void_p(soc.data_ptr()),
-                                                                C.c_void_p(cnt.data_ptr())), "selectBuckets")
-            if self._p2p_add(sel, nbases):
+            if getattr(self, "_reserved", False) or self.reserve(nbases):
+                check(self._lib.modgpuShardedAddDevice(self._sh, C.c_void_p(d_bases), C.c_void_p(d_offsets), nseq, nbases, is_ascii),
+                      "shardedAddDevice")
                 return 0                         # the count comes from synchronize()
         if self.fused and self.fused_mode == "peer":
             self._ensure_peer(nbases)
@@ -366,12 +331,8 @@ class ShardedModset:
         if self.fused and nbases is None:
             nbases = int((C.c_uint64 * (nseq + 1)).from_address(offsets_ptr)[nseq])
         if self.fused and self.fused_mode == "p2p":
-            def sel(sb, cap, sc, so, oc, soc, cnt):
-                check(self._lib.modgpuModsetSelectBucketsHost(self.local._p, C.c_void_p(host_ptr), C.c_void_p(offsets_ptr), nseq,
-                                                              is_ascii, self.world, C.c_void_p(sb), cap, C.c_void_p(sc.data_ptr()),
-                                                              C.c_void_p(so), oc, C.c_void_p(soc.data_ptr()),
-                                                              C.c_void_p(cnt.data_ptr())), "selectBuckets")
-            if self._p2p_add(sel, nbases):
+            if getattr(self, "_reserved", False) or self.reserve(nbases):
+                check(self._lib.modgpuShardedAdd(self._sh, C.c_void_p(host_ptr), C.c_void_p(offsets_ptr), nseq, is_ascii), "shardedAdd")
                 return 0
         if self.fused and self.fused_mode == "peer":
             self._ensure_peer(nbases)

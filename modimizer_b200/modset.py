@@ -48,6 +48,34 @@ def concat(seqs):
     return np.ascontiguousarray(data, np.uint8), offs, is_ascii
 
 
+def seqio_pack(codes, offsets):
+    """sqioSeqPack (reference seqio.c:557-570) over a batch of code sequences: four bases per byte, first base in the
+    top two bits, every sequence on its own bytes, a short last byte right-aligned.  Returns (packed, byte_offsets)."""
+    codes = np.ascontiguousarray(codes, np.uint8)
+    offsets = np.ascontiguousarray(offsets, np.uint64)
+    lens = (offsets[1:] - offsets[:-1]).astype(np.int64)
+    nbytes = (lens + 3) // 4
+    boffs = np.zeros(len(lens) + 1, np.uint64)
+    boffs[1:] = np.cumsum(nbytes).astype(np.uint64)
+    out = np.zeros(int(boffs[-1]), np.uint8)
+    for r in range(len(lens)):
+        s = codes[int(offsets[r]):int(offsets[r + 1])] & 3
+        L = len(s)
+        if not L:
+            continue
+        full = (L - 1) // 4 * 4 if L % 4 else L          # `while (len > 4)`: the last byte is the remainder loop's, even when it has four bases
+        q = s[:full].reshape(-1, 4)
+        b = (q[:, 0] << 6) | (q[:, 1] << 4) | (q[:, 2] << 2) | q[:, 3]
+        o = int(boffs[r])
+        out[o:o + len(b)] = b
+        if L > full:
+            v = 0
+            for c in s[full:]:
+                v = (v << 2) | int(c)
+            out[o + len(b)] = v
+    return out, boffs
+
+
 class Seqhash:
     """seqhashCreate (reference seqhash.c:20-37): k, w (modulus), seed -> multiplier from libc random()"""
 
@@ -141,6 +169,26 @@ class Modset:
         n = self._lib.modgpuModsetAdd(self._p, C.c_void_p(host_ptr), C.c_void_p(offsets_ptr), nseq, is_ascii)
         if n == U64MAX:
             raise ModgpuError("modsetAdd: " + _lib.last_error())
+        self.total_hashes += n
+        return int(n)
+
+    def add_packed(self, packed, byte_offsets, offsets):
+        """the batch in the reference's own 2-bit packing (sqioSeqPack, seqio.c:557-570; see seqio_pack): a quarter
+        of the bytes cross PCIe, the device expands them"""
+        packed = np.ascontiguousarray(packed, np.uint8)
+        byte_offsets = np.ascontiguousarray(byte_offsets, np.uint64)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        n = self._lib.modgpuModsetAddPacked(self._p, packed.ctypes.data if packed.size else None, byte_offsets.ctypes.data,
+                                            offsets.ctypes.data, len(offsets) - 1)
+        if n == U64MAX:
+            raise ModgpuError("modsetAddPacked: " + _lib.last_error())
+        self.total_hashes += n
+        return int(n)
+
+    def add_packed_pointers(self, packed_ptr, byte_offsets_ptr, offsets_ptr, nseq):
+        n = self._lib.modgpuModsetAddPacked(self._p, C.c_void_p(packed_ptr), C.c_void_p(byte_offsets_ptr), C.c_void_p(offsets_ptr), nseq)
+        if n == U64MAX:
+            raise ModgpuError("modsetAddPacked: " + _lib.last_error())
         self.total_hashes += n
         return int(n)
 

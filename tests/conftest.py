@@ -12,10 +12,19 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-@pytest.fixture(scope="session")
-def orc():
+# Every test that takes `orc` runs twice: against oracle/liboracle.so (the restatement, always there) and against
+# oracle/_ref/libmodref.so (the UNMODIFIED reference objects behind the same harness API) wherever that was
+# built - the GPU box receives the prebuilt file with the snapshot, so the parity tests compare the CUDA path
+# with the reference itself, not only with its restatement.
+@pytest.fixture(scope="session", params=["port", "reference"])
+def orc(request):
     import harness
-    return harness.oracle()
+    if request.param == "port":
+        return harness.oracle()
+    r = harness.reference()
+    if r is None:
+        pytest.skip("oracle/_ref not built (no /root/reference on this box)")
+    return r
 
 
 @pytest.fixture(scope="session")

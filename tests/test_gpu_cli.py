@@ -1,5 +1,11 @@
 """The C host side of the drop-in boundary on a GPU box:
 
+  * modimizer_b200/modutils_shim, modmap_shim - the reference's modutils.c / modmap.c, UNMODIFIED, linked against
+    libmodshim.so (seqhash.h + modset.h under their own names, served by the GPU) instead of seqhash.o / modset.o;
+  * modimizer_b200/modutils_dropin, modmap_dropin - the same sources with the caller loops of INTEGRATION.md sections
+    1-2 swapped in at build time (csrc/shim/Makefile: sed + modutils_hot.c / modmap_hot.c): the batched path;
+  both against the STOCK tools (oracle/_ref/modutils, modmap): every file and every stable output line byte-identical;
+
   * modimizer_b200/modutils_gpu - a C modutils (our own command interpreter) in which the reference's seqio parses the
     files and libmodgpu does the rest - against the STOCK modutils (oracle/_ref/modutils) on the same files: every file
     they write and every stable line they print must be byte-identical, and each reads the other's .mod files;
@@ -22,6 +28,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GPU_CLI = os.path.join(ROOT, "modimizer_b200", "modutils_gpu")
 GPU_MODMAP = os.path.join(ROOT, "modimizer_b200", "modmap_gpu")
+TOOL = lambda name: os.path.join(ROOT, "modimizer_b200", name)
 SHIM = os.path.join(ROOT, "modimizer_b200", "libmodshim.so")
 
 
@@ -47,15 +54,23 @@ def make_reads(rng, genome, n, lo, hi):
     return reads
 
 
-def test_c_modutils_matches_stock_modutils(tmp_path):
+@pytest.mark.parametrize("tool", ["modutils_gpu", "modutils_dropin", "modutils_shim"])
+def test_c_modutils_matches_stock_modutils(tmp_path, tool):
+    """modutils_gpu: own driver over the ABI; modutils_dropin: the reference's modutils.c with addSequenceFile swapped at
+    build time; modutils_shim: the reference's modutils.c unmodified on libmodshim (one device call per k-mer: smaller
+    input).  The last two also run the commands our own driver does not have (-rt, -m, -d): reference code on
+    libmodshim's modset.h symbols."""
     stock = H.ref_cli("modutils")
-    if not stock or not os.path.exists(GPU_CLI):
-        pytest.skip("stock modutils / modutils_gpu not built (no /root/reference in the build container)")
+    exe = TOOL(tool)
+    if not stock or not os.path.exists(exe):
+        pytest.skip("stock modutils / %s not built (no /root/reference in the build container)" % tool)
+    ref_source = tool != "modutils_gpu"
+    small = tool == "modutils_shim"
     rng = np.random.default_rng(21)
     genome = rng.integers(0, 4, 300000).astype(np.uint8)
     genome[200000:220000] = genome[20000:40000]                      # a duplication: copy-2 k-mers
-    reads = make_reads(rng, genome, 9000, 20, 2500) + [genome[:18], genome[:19], genome[5:5]]   # incl. len < k, == k, empty
-    more = make_reads(rng, genome, 800, 100, 1500)
+    reads = make_reads(rng, genome, 1200 if small else 9000, 20, 2500) + [genome[:18], genome[:19], genome[5:5]]   # incl. len < k, == k, empty
+    more = make_reads(rng, genome, 150 if small else 800, 100, 1500)
     d = str(tmp_path)
     H.write_fasta(os.path.join(d, "r.fa"), reads, width=0)
     H.write_fasta(os.path.join(d, "m.fa"), more, width=70)
@@ -64,6 +79,7 @@ def test_c_modutils_matches_stock_modutils(tmp_path):
     txt = open(os.path.join(d, "r.fa")).read().split("\n")
     txt[1] = txt[1][:50] + "NNNNNNNNnnnn" + txt[1][62:].lower()
     open(os.path.join(d, "r.fa"), "w").write("\n".join(txt))
+    rd = lambda name: open(os.path.join(d, name), "rb").read()
 
     for (k, w) in ((19, 31), (31, 64)):
         def script(p):
@@ -72,7 +88,7 @@ def test_c_modutils_matches_stock_modutils(tmp_path):
                     "-p", "2", "30", "-wt", p + "3.txt"]
         a, b = script("a"), script("b")
         run(stock, a, d)
-        run(GPU_CLI, b, d)
+        run(exe, b, d)
         for f in ("his", "txt"):
             for n in ("", "2", "3") if f == "txt" else ("", "2"):
                 fa, fb = os.path.join(d, "a%s.%s" % (n, f)), os.path.join(d, "b%s.%s" % (n, f))
@@ -80,22 +96,76 @@ def test_c_modutils_matches_stock_modutils(tmp_path):
         assert stable(open(os.path.join(d, "a.out")).read()) == stable(open(os.path.join(d, "b.out")).read()), (k, w)
         # each tool reads the other's .mod (gzip'd by fzopen, modutils.c:165) and prints the same set
         run(stock, ["-o", "c.out", "-r", "b.mod", "-H", "c.his", "-wt", "c.txt"], d)
-        run(GPU_CLI, ["-o", "d.out", "-r", "a.mod", "-H", "d.his", "-wt", "d.txt"], d)
-        assert open(os.path.join(d, "c.his"), "rb").read() == open(os.path.join(d, "d.his"), "rb").read() == open(os.path.join(d, "a2.his"), "rb").read()
-        assert open(os.path.join(d, "c.txt"), "rb").read() == open(os.path.join(d, "d.txt"), "rb").read()
+        run(exe, ["-o", "d.out", "-r", "a.mod", "-H", "d.his", "-wt", "d.txt"], d)
+        assert rd("c.his") == rd("d.his") == rd("a2.his")
+        assert rd("c.txt") == rd("d.txt")
         assert stable(open(os.path.join(d, "c.out")).read()) == stable(open(os.path.join(d, "d.out")).read())
         # refpaint (-P, modutils.c:260-273) prints position and depth of every hit along a reference, to stdout
         pa = run(stock, ["-r", "a.mod", "-P", "g.fa"], d).stdout
-        pb = run(GPU_CLI, ["-r", "a.mod", "-P", "g.fa"], d).stdout
+        pb = run(exe, ["-r", "a.mod", "-P", "g.fa"], d).stdout
         assert stable(pa) == stable(pb) and any(l.startswith("  ") for l in pa.splitlines()), (k, w)
+        if ref_source:
+            # the whole .mod, index[] included (built on the device with the reference's probe rule); value[0] is
+            # uninitialised heap in the reference (modset.c:27): masked
+            import gzip
+            ma, mb = bytearray(gzip.decompress(rd("a.mod"))), bytearray(gzip.decompress(rd("b.mod")))
+            v0 = 8 + 4 + 4 + 8 + 80 + 4 * (1 << 22)
+            ma[v0:v0 + 8] = bytes(8); mb[v0:v0 + 8] = bytes(8)
+            assert ma == mb, (k, w, ".mod bytes")
+            # commands only the reference's interpreter has: text round trip (modsetIndexFind (.., true) per line), merge
+            # of a second set built from m.fa, per-mod depths in other sets - all on libmodshim's modset.h symbols
+            # (the merge goes into a set made by -c: merging into an -rt / -r set reads uninitialised memory in the
+            # reference - resize() does not zero the grown depth[] / info[], utils.h:54, modset.c:116-121)
+            def script2(t, p):
+                run(t, ["-c", "22", str(k), str(w), "17", "-a", "m.fa", "-w", p + "m.mod"], d)
+                subprocess.run(["gunzip", "-c", p + "m.mod"], cwd=d, stdout=open(os.path.join(d, p + "m.raw"), "wb"), check=True)
+                run(t, ["-o", p + "f.out", "-rt", "a3.txt", "-wt", p + "e.txt", "-s", "2", "5", "9", "-w", p + "f.mod"], d)
+                return run(t, ["-o", p + "e.out", "-c", "22", str(k), str(w), "17", "-a", "r.fa", "-s", "3", "9", "14", "-m", p + "m.raw",
+                               "-wt", p + "e2.txt", "-H", p + "e.his", "-d", p + "e.dep", p + "m.raw"], d)
+            script2(stock, "a"); script2(exe, "b")
+            for f in ("e.txt", "e2.txt", "e.his", "e.dep"):
+                assert rd("a" + f) == rd("b" + f), (k, w, f)
+            for o in ("e.out", "f.out"):
+                assert stable(open(os.path.join(d, "a" + o)).read()) == stable(open(os.path.join(d, "b" + o)).read()), (k, w, o)
 
 
-def test_c_modmap_matches_stock_modmap(tmp_path):
+@pytest.mark.parametrize("tool", ["modmap_gpu", "modmap_dropin", "modmap_shim"])
+def test_c_modmap_matches_stock_modmap(tmp_path, tool):
     stock = H.ref_cli("modmap")
-    if not stock or not os.path.exists(GPU_MODMAP):
-        pytest.skip("stock modmap / modmap_gpu not built (no /root/reference in the build container)")
+    exe = TOOL(tool)
+    if not stock or not os.path.exists(exe):
+        pytest.skip("stock modmap / %s not built (no /root/reference in the build container)" % tool)
     H.modmap_case(str(tmp_path))
-    H.modmap_driver_vs_stock(stock, GPU_MODMAP, str(tmp_path), check_mod=True)
+    H.modmap_driver_vs_stock(stock, exe, str(tmp_path), check_mod=True)
+    if tool != "modmap_gpu":                         # -r is the reference's own referenceRead on libmodshim's modsetRead
+        d = str(tmp_path)
+        a = run(stock, ["-o", "ra.out", "-r", "a", "-q", "r.fa"], d)
+        b = run(exe, ["-o", "rb.out", "-r", "a", "-q", "r.fa"], d)
+        assert stable(open(os.path.join(d, "ra.out")).read()) == stable(open(os.path.join(d, "rb.out")).read())
+
+
+def test_c_sharded_host(tmp_path):
+    """modimizer_b200/sharded_host: the multi-GPU build as a C host (modgpuSharded* + NCCL, one process per GPU, no
+    Python in the data path).  On a box with >= 2 GPUs: sharded over 2 GPUs == one modset on one GPU (entry totals and
+    the whole depth histogram on a 48-Mbase sample per rank), a skewed group is skipped on every rank (transactional)
+    and fits after modgpuShardedSetRobust.  On a 1-GPU box the same program runs with world 1."""
+    import json
+    import torch
+    exe = TOOL("sharded_host")
+    if not os.path.exists(exe):
+        pytest.skip("sharded_host not built")
+    n = 2 if torch.cuda.device_count() >= 2 else 1
+    for (k, d) in ((31, 64), (19, 31)):
+        args = ["--gpus", str(n), "--gbases", "0.4", "--k", str(k), "--d", str(d), "--bits", "26", "--steps", "2", "--warmup", "1", "--check", "48"]
+        if n > 1:
+            args.append("--skew")
+        r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, (r.stdout[-800:], r.stderr[-800:])
+        out = json.loads(r.stdout.strip().splitlines()[-1])
+        assert out["n_gpus"] == n and out["parity"]["ok"] is True, out
+        assert abs(out["selected"] - n * 0.4e9 / d) < 0.02 * n * 0.4e9 / d, out
+        if n > 1:
+            assert out["skew_transactional"] is True, out
 
 
 class Seqhash(C.Structure):                      # reference seqhash.h:15-23

@@ -590,6 +590,115 @@ def test_prune_and_merge(mg, orc):
         orc._modset_free(oa); orc._modset_free(ob)
 
 
+def test_add_packed_is_add(mg, orc):
+    """modgpuModsetAddPacked: the batch in the reference's own 2-bit packing (sqioSeqPack, seqio.c:557-570) gives the
+    modset of the same batch as bytes - ragged lengths around the byte and k boundaries, empty sequences, and a batch
+    of 150-base reads where nearly every 16-base group of the expansion touches a sequence boundary"""
+    rng = np.random.default_rng(5)
+    lens = [0, 1, 2, 3, 4, 5, 7, 8, 17, 18, 19, 20, 30, 31, 32, 33, 63, 64, 65, 150, 151, 1000, 0, 4097] + [int(x) for x in rng.integers(0, 400, 300)]
+    for case in range(2):
+        if case == 1:
+            lens = [150] * 20000 + [149, 151, 2]
+        offs = np.zeros(len(lens) + 1, np.uint64); offs[1:] = np.cumsum(lens)
+        codes = rng.integers(0, 4, int(offs[-1])).astype(np.uint8)
+        packed, boffs = mg.seqio_pack(codes, offs)
+        for (k, d) in ((19, 31), (31, 64), (1, 1), (4, 3)):
+            a = mg.Modset(22, k, d, 17); b = mg.Modset(22, k, d, 17); o = orc.modset_new(22, k, d, 17)
+            ta = a.add(codes, offs, is_ascii=0)
+            tb = b.add_packed(packed, boffs, offs)
+            to = orc.modset_add(o, codes, offs)
+            assert ta == tb == to, (case, k, d)
+            for x, y in zip(a.sorted_dump(), b.sorted_dump()):
+                assert np.array_equal(x, y), (case, k, d)
+            ov, od, oi = orc.modset_sorted(o)
+            gv, gd, gi = b.sorted_dump()
+            assert np.array_equal(gv, ov) and np.array_equal(gd, od), (case, k, d)
+            a.close(); b.close(); orc._modset_free(o)
+    # packed bytes shorter than (len+3)/4 are refused
+    bad = mg.Modset(22, 19, 31, 17)
+    with pytest.raises(mg.ModgpuError):
+        bad.add_packed(packed, np.zeros(len(boffs), np.uint64), offs)
+    bad.close()
+
+
+def test_info_flags_survive_device_ops(mg, tmp_path):
+    """Modset.info is a whole byte (modset.h:49-52: MS_MINOR 4, MS_REPEAT 8, MS_INTERNAL 0x10, MS_RDNA 0x20 beside the
+    two copy bits): import / export, prune (modset.c:73), merge (modset.c:124-125: touched entries are masked to the
+    copy bits, the others keep their flags) and the .mod round trip keep it; with the stock modutils on the box the
+    same through its -rt / -p / -m / -wt commands"""
+    import subprocess
+    rng = np.random.default_rng(99)
+    sp = he.read_spec(777, 120000, 5, 2000, 2000)
+    d1 = he.reads(sp, 0, 900); o1 = np.arange(901, dtype=np.uint64) * np.uint64(2000)
+    d2 = he.reads(sp, 600, 700); o2 = np.arange(701, dtype=np.uint64) * np.uint64(2000)
+    flags = np.array([0, 4, 8, 0x10, 0x20, 0x3C, 0x14, 0], np.uint8)
+
+    def flagged(data, offs):
+        t = mg.Modset(20, 19, 31, 17)
+        t.add(data, offs, is_ascii=0)
+        t.set_copy(3, 20, 40)
+        v, d, i = t.export()
+        t.close()
+        i = (i | flags[rng.integers(0, len(flags), len(i))]).astype(np.uint8)
+        m = mg.Modset(20, 19, 31, 17)
+        m.import_entries(v, d, i)
+        return m, v, d, i
+
+    a, va, da, ia = flagged(d1, o1)
+    b, vb, db, ib = flagged(d2, o2)
+    assert (ia >= 4).sum() > 100 and (ib >= 4).sum() > 100
+    for x, y in zip(a.export(), (va, da, ia)):
+        assert np.array_equal(x, y), "import/export"
+    # .mod round trip (modsetWrite / modsetRead, modset.c:79-104)
+    path = str(tmp_path / "flags.mod")
+    a.write_mod(path, gzip=True)
+    back = mg.Modset.read_mod(path)
+    for x, y in zip(back.export(), (va, da, ia)):
+        assert np.array_equal(x, y), "mod round trip"
+    back.close()
+    # prune: survivors in their old order with their whole info byte
+    keep = (db >= 3) & (db < 25)
+    b.prune(3, 25)
+    for x, y in zip(b.export(), (vb[keep], db[keep], ib[keep])):
+        assert np.array_equal(x, y), "prune"
+    vb, db, ib = vb[keep], db[keep], ib[keep]
+    # merge b into a: the reference's loop restated on the arrays
+    pos = {int(k): j for j, k in enumerate(va)}
+    ev, ed, ei = list(va), [int(x) for x in da], [int(x) for x in ia]
+    for k, d, i in zip(vb, db, ib):
+        j = pos.get(int(k))
+        if j is None:
+            j = len(ev); pos[int(k)] = j
+            ev.append(k); ed.append(0); ei.append(0)
+        ed[j] = min(ed[j] + int(d), 65535)
+        ei[j] = (ei[j] & 3) | min((ei[j] & 3) + (int(i) & 3), 3)
+    assert a.merge(b)
+    gv, gd, gi = a.export()
+    assert np.array_equal(gv, np.array(ev, np.uint64)) and np.array_equal(gd, np.array(ed, np.uint16)), "merge"
+    assert np.array_equal(gi, np.array(ei, np.uint8)), "merge info"
+    assert (gi >= 4).sum() > 50                                        # untouched entries kept their flags
+    a.close(); b.close()
+    # the stock tool on a flagged set: -rt reads any info value, -p / -wt carry it
+    modutils = H.ref_cli("modutils")
+    if modutils:
+        txt = str(tmp_path / "flags.txt")
+        with open(txt, "w") as f:
+            f.write("modset bits 20 size %d k 19 w 31 seed 17\n" % (len(va) + 1))
+            for j in range(len(va)):
+                f.write("%d\t%s\t%d\t%d\n" % (j + 1, H.kmer_string(va[j], 19), da[j], ia[j]))
+        smod, sout = str(tmp_path / "stock.mod"), str(tmp_path / "stock_pruned.txt")
+        r = subprocess.run([modutils, "-rt", txt, "-w", smod, "-p", "4", "30", "-wt", sout], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        g = mg.Modset.read_mod(smod)
+        for x, y in zip(g.export(), (va, da, ia)):
+            assert np.array_equal(x, y), "stock .mod with flags"
+        g.prune(4, 30)
+        gout = str(tmp_path / "gpu_pruned.txt")
+        g.write_text(gout)
+        assert open(gout).read() == open(sout).read()
+        g.close()
+
+
 def test_mod_file_roundtrip_with_stock_modutils(mg, orc, tmp_path):
     """modsetWrite / modsetRead (modset.c:79-104): a GPU-built .mod is loaded by the UNMODIFIED reference tool
     (oracle/_ref/modutils -r), and a .mod written by the reference tool is loaded by us"""

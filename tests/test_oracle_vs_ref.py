@@ -236,3 +236,24 @@ def test_stock_cli_byte_level(orc, ref, tmp_path):
     for key in e1:
         assert np.array_equal(e1[key], e2[key]), key
     ref._ref_free(rf); ref._ref_free(rm)
+
+
+def test_seqio_pack_is_the_references(ref):
+    """modimizer_b200.seqio_pack (the layout modgpuModsetAddPacked expands on the device) against the reference's own
+    sqioSeqPack (seqio.c:557-570), called in oracle/_ref/libmodref.so"""
+    import ctypes as C
+    import modimizer_b200 as mg
+    pack = ref.lib.sqioSeqPack
+    pack.restype = C.c_uint64
+    pack.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    ident = (C.c_int * 256)(*[i & 3 for i in range(256)])           # `convert`: codes are already 0..3
+    rng = np.random.default_rng(3)
+    lens = list(range(0, 40)) + [150, 151, 1000, 1001, 1002, 1003]
+    offs = np.zeros(len(lens) + 1, np.uint64); offs[1:] = np.cumsum(lens)
+    codes = rng.integers(0, 4, int(offs[-1])).astype(np.uint8)
+    packed, boffs = mg.seqio_pack(codes, offs)
+    for r, L in enumerate(lens):
+        buf = (C.c_uint8 * (L // 4 + 2))()
+        n = pack(codes[int(offs[r]):int(offs[r + 1])].tobytes(), buf, L, ident)
+        assert n == (L + 3) // 4 == int(boffs[r + 1] - boffs[r]), L
+        assert bytes(buf[:n]) == packed[int(boffs[r]):int(boffs[r + 1])].tobytes(), L
