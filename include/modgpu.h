@@ -172,6 +172,8 @@ ModgpuModset *modgpuModsetCreate(int bits, int k, int w, int seed);   /* modsetC
 void modgpuModsetDestroy(ModgpuModset *ms);
 const ModgpuHasher *modgpuModsetHasher(const ModgpuModset *ms);
 int modgpuModsetBits(const ModgpuModset *ms);                          /* ms->tableBits */
+/* the CUDA device the set lives on: a thread other than its creator calls modgpuSetDevice(this) before using it */
+int modgpuModsetDevice(const ModgpuModset *ms);
 ModgpuTable *modgpuModsetTable(ModgpuModset *ms);
 /* use the caller's stream (e.g. torch's current stream) for all work */
 int modgpuModsetSetStream(ModgpuModset *ms, void *stream);

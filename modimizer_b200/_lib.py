@@ -65,6 +65,7 @@ _SIGS = {
     "modgpuModsetHasher": (C.POINTER(Hasher), [vp]),
     "modgpuModsetTable": (vp, [vp]),
     "modgpuModsetBits": (C.c_int, [vp]),
+    "modgpuModsetDevice": (C.c_int, [vp]),
     "modgpuModsetSetStream": (C.c_int, [vp, vp]),
     "modgpuModsetSetFlags": (C.c_int, [vp, C.c_int]),
     "modgpuModsetSetExactOrder": (C.c_int, [vp, C.c_int]),

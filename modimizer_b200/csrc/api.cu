@@ -39,6 +39,7 @@ extern "C" ModgpuModset *modgpuModsetCreateWithHasher(int bits, const ModgpuHash
   ModgpuModset *ms = new ModgpuModset();
   ms->hasher = *hasher;
   ms->bits = bits;
+  cudaGetDevice(&ms->device);
   if (mg_check_cuda(cudaStreamCreateWithFlags(&ms->stream, cudaStreamNonBlocking), "cudaStreamCreate", __FILE__, __LINE__) ||
       mg_check_cuda(cudaStreamCreateWithFlags(&ms->copyStream, cudaStreamNonBlocking), "cudaStreamCreate", __FILE__, __LINE__))
     { delete ms; return nullptr; }
@@ -74,6 +75,7 @@ extern "C" void modgpuModsetDestroy(ModgpuModset *ms)
 }
 
 extern "C" const ModgpuHasher *modgpuModsetHasher(const ModgpuModset *ms) { return &ms->hasher; }
+extern "C" int modgpuModsetDevice(const ModgpuModset *ms) { return ms->device; }
 extern "C" ModgpuTable *modgpuModsetTable(ModgpuModset *ms) { return ms->table; }
 
 extern "C" int modgpuModsetSetStream(ModgpuModset *ms, void *stream)

@@ -94,6 +94,7 @@ struct ModgpuModset {
   ModgpuHasher hasher;
   ModgpuTable *table = nullptr;
   int bits = 0;
+  int device = 0;                   // the CUDA device the set lives on (threads other than the creator select it first)
   cudaStream_t stream = nullptr, copyStream = nullptr;
   bool ownStream = false;
   int selFlags = 0;

@@ -135,8 +135,19 @@ extern "C" int modgpuShardedReserve(ModgpuSharded *s, uint64_t maxBasesPerBatch)
   uint64_t cap = ((uint64_t)(1.1 * mean + 4.0 * sqrt(mean) + 8.0) + 1) & ~1ull;
   if (cap > 0x7FFFFFFFull) { mg_set_error("modgpuShardedReserve: bucket capacity overflow"); return MODGPU_EINVAL; }
   s->cap = (uint32_t)cap;
-  s->ovfCap = s->robust ? expected + 65536 : (expected / 4 > 65536 ? expected / 4 : 65536);
+  // robust: skewed input also selects more than 1/w of its windows (poly-A: every window is the same modimizer), so the
+  // worst case is every window of a group, all to one owner
+  s->ovfCap = s->robust ? nb * s->accumulate + 65536 : (expected / 4 > 65536 ? expected / 4 : 65536);
   if (s->ovfCap > 0xFFFFFFF0ull) s->ovfCap = 0xFFFFFFF0ull;
+  if (s->robust)
+    { size_t freeB = 0, totalB = 0;
+      cudaMemGetInfo(&freeB, &totalB);
+      if ((double)G * (double)s->ovfCap * 16.0 > 0.5 * (double)freeB)
+        { mg_set_error("modgpuShardedReserve: robust overflow segments for batches of %llu bases need %.1f GB per GPU: feed smaller batches",
+                       (unsigned long long)nb, (double)G * (double)s->ovfCap * 16.0 / 1e9);
+          return MODGPU_ENOMEM;
+        }
+    }
   const size_t bBytes = (size_t)G * s->R * cap * 8, oBytes = (size_t)G * s->ovfCap * 8;
   int ok = 1;
   for (int i = 0; i < 4; ++i) { s->mine[i] = modgpuPeerAlloc(i < 2 ? bBytes : oBytes); if (!s->mine[i]) ok = 0; }

@@ -37,11 +37,12 @@ typedef struct Twin {
   Modset *ms ;
   ModgpuModset *g ;
   int indexStale ;                   /* ms->index[] does not describe value[1..max] */
-  /* pinned batch of sequences waiting for modshimBatchFlush */
-  char *bases ; U64 *off ; size_t cap, used, nSeq, capSeq ; U64 hashes ;
+  void *feeder ;                     /* the double-buffered pinned batches of modshimBatchPut + their worker thread */
+  int inGroup ;                      /* sequences were put since the last flush */
   struct Twin *next ;
 } Twin ;
 
+static void feederDestroy (struct Twin *t) ;
 static Twin *twins ;
 
 static Twin *twinOf (Modset *ms)
@@ -113,9 +114,9 @@ void modsetDestroy (Modset *ms)
   Twin **p, *t = 0 ;
   for (p = &twins ; *p ; p = &(*p)->next) if ((*p)->ms == ms) { t = *p ; *p = t->next ; break ; }
   if (t)
-    { modgpuModsetDestroy (t->g) ;
-      if (t->bases) modgpuHostFree (t->bases) ;
-      free (t->off) ; free (t) ;
+    { feederDestroy (t) ;
+      modgpuModsetDestroy (t->g) ;
+      free (t) ;
     }
   free (ms->index) ; free (ms->value) ; free (ms->depth) ; free (ms->info) ; free (ms) ;
 }
@@ -231,43 +232,131 @@ void modsetSummary (Modset *ms, FILE *f)
 }
 
 /* ---- the batched add: == the addSequence loop of modutils.c:19-31 --------------------------------------------
- * seqio reuses its buffer on the next seqIOread (seqio.h:46-48), so every sequence is copied into a pinned batch;
- * full batches go through modgpuModsetAdd; modshimBatchFlush adds what is left, syncs the host arrays and returns
- * the number of hashes added since the previous flush (the reference's totHash). */
-static void batchSend (Twin *t)
+ * seqio reuses its buffer on the next seqIOread (seqio.h:46-48), so every sequence is copied into a pinned batch.
+ * Two batches: while the caller's thread parses into one (seqIOread is the slow side: ~0.17 Gbases/s per core), a
+ * worker thread feeds the other through modgpuModsetAdd (H2D + kernels), so the file reader never waits for the GPU
+ * and the GPU never waits for more than one batch.  Only the worker touches the twin between two flushes.
+ * modshimBatchFlush adds what is left, joins the worker, syncs the host arrays and returns the number of hashes added
+ * since the previous flush (the reference's totHash). */
+#include <pthread.h>
+
+typedef struct { char *bases ; U64 *off ; size_t cap, used, nSeq ; } Half ;
+
+typedef struct Feeder {
+  Twin *t ;
+  Half h[2] ; int cur ;              /* the half being filled by the caller */
+  size_t capSeq ;
+  pthread_t th ; int started ;
+  pthread_mutex_t mu ; pthread_cond_t cv ;
+  int job ;                          /* half handed to the worker, -1 none, -2 quit */
+  int busy ;
+  U64 hashes ;
+  char err[512] ;
+} Feeder ;
+
+static void *feederMain (void *arg)
 {
-  if (!t->nSeq) return ;
-  U64 n = modgpuModsetAdd (t->g, t->bases, (uint64_t*) t->off, t->nSeq, 0) ;     /* 0: the bytes are codes 0..3 */
-  if (n == UINT64_MAX) GDIE () ;
-  t->hashes += n ; t->used = 0 ; t->nSeq = 0 ;
+  Feeder *f = (Feeder*) arg ;
+  modgpuSetDevice (modgpuModsetDevice (f->t->g)) ;       /* the current device is per thread */
+  pthread_mutex_lock (&f->mu) ;
+  for (;;)
+    { while (f->job == -1) pthread_cond_wait (&f->cv, &f->mu) ;
+      if (f->job == -2) break ;
+      Half *h = &f->h[f->job] ;
+      pthread_mutex_unlock (&f->mu) ;
+      U64 n = modgpuModsetAdd (f->t->g, h->bases, (uint64_t*) h->off, h->nSeq, 0) ;     /* 0: the bytes are codes 0..3 */
+      pthread_mutex_lock (&f->mu) ;
+      if (n == UINT64_MAX) { if (!f->err[0]) snprintf (f->err, sizeof (f->err), "%s", modgpuLastError ()) ; }
+      else f->hashes += n ;
+      h->used = 0 ; h->nSeq = 0 ;
+      f->job = -1 ; f->busy = 0 ;
+      pthread_cond_broadcast (&f->cv) ;
+    }
+  pthread_mutex_unlock (&f->mu) ;
+  return 0 ;
+}
+
+static void feederWait (Feeder *f)                /* until the worker is idle; its error becomes ours */
+{
+  pthread_mutex_lock (&f->mu) ;
+  while (f->busy) pthread_cond_wait (&f->cv, &f->mu) ;
+  pthread_mutex_unlock (&f->mu) ;
+  if (f->err[0]) die ("%s", f->err) ;
+}
+
+static void feederSend (Feeder *f)                /* hand the current half to the worker, continue in the other */
+{
+  if (!f->h[f->cur].nSeq) return ;
+  feederWait (f) ;                                /* the other half is free again */
+  pthread_mutex_lock (&f->mu) ;
+  f->job = f->cur ; f->busy = 1 ;
+  pthread_cond_broadcast (&f->cv) ;
+  pthread_mutex_unlock (&f->mu) ;
+  f->cur ^= 1 ;
+}
+
+static Feeder *feederOf (Twin *t)
+{
+  if (t->feeder) return (Feeder*) t->feeder ;
+  Feeder *f = (Feeder*) calloc (1, sizeof (Feeder)) ;
+  if (!f) die ("modshim: out of memory") ;
+  f->t = t ; f->job = -1 ; f->capSeq = 1 << 22 ;
+  pthread_mutex_init (&f->mu, 0) ; pthread_cond_init (&f->cv, 0) ;
+  for (int i = 0 ; i < 2 ; ++i)
+    { f->h[i].cap = (size_t) 1 << 28 ;
+      if (!(f->h[i].bases = (char*) modgpuHostAlloc (f->h[i].cap))) GDIE () ;
+      if (!(f->h[i].off = (U64*) calloc (f->capSeq + 1, sizeof (U64)))) die ("modshim: out of memory") ;
+    }
+  if (pthread_create (&f->th, 0, feederMain, f)) die ("modshim: cannot start the feeder thread") ;
+  f->started = 1 ;
+  t->feeder = f ;
+  return f ;
+}
+
+static void feederDestroy (Twin *t)
+{
+  Feeder *f = (Feeder*) t->feeder ;
+  if (!f) return ;
+  pthread_mutex_lock (&f->mu) ;
+  while (f->busy) pthread_cond_wait (&f->cv, &f->mu) ;
+  f->job = -2 ;
+  pthread_cond_broadcast (&f->cv) ;
+  pthread_mutex_unlock (&f->mu) ;
+  pthread_join (f->th, 0) ;
+  for (int i = 0 ; i < 2 ; ++i) { modgpuHostFree (f->h[i].bases) ; free (f->h[i].off) ; }
+  free (f) ; t->feeder = 0 ;
 }
 
 void modshimBatchPut (void *vms, const char *s, long long len)
 {
   Twin *t = twinOf ((Modset*) vms) ;
+  Feeder *f = feederOf (t) ;
   if (len < 0) len = 0 ;                           /* int len < k has no k-mer (seqhash.c:162) */
-  if (!t->off)
-    { t->capSeq = 1 << 22 ;
-      if (!(t->off = (U64*) calloc (t->capSeq + 1, sizeof (U64)))) die ("modshim: out of memory") ;
-      push (t) ;                                   /* first sequence of a group: the caller's depths are current */
+  if (!t->inGroup) { push (t) ; t->inGroup = 1 ; } /* first sequence of a group: the caller's depths are current */
+  Half *h = &f->h[f->cur] ;
+  if (h->used + (size_t) len > h->cap || h->nSeq == f->capSeq)
+    { feederSend (f) ; h = &f->h[f->cur] ; }
+  if ((size_t) len > h->cap)                       /* one sequence longer than a batch: grow this half (it is empty) */
+    { feederWait (f) ;
+      modgpuHostFree (h->bases) ;
+      h->cap = (size_t) len + (size_t) len / 4 ;
+      if (!(h->bases = (char*) modgpuHostAlloc (h->cap))) GDIE () ;
     }
-  if ((size_t) len > t->cap || !t->bases)
-    { batchSend (t) ;
-      if (t->bases) modgpuHostFree (t->bases) ;
-      t->cap = (size_t) len + (size_t) len / 4 ; if (t->cap < ((size_t) 1 << 28)) t->cap = (size_t) 1 << 28 ;
-      if (!(t->bases = (char*) modgpuHostAlloc (t->cap))) GDIE () ;
-    }
-  if (t->used + (size_t) len > t->cap || t->nSeq == t->capSeq) batchSend (t) ;
-  memcpy (t->bases + t->used, s, (size_t) len) ;
-  t->used += (size_t) len ; t->off[++t->nSeq] = t->used ;
+  memcpy (h->bases + h->used, s, (size_t) len) ;
+  h->used += (size_t) len ; h->off[++h->nSeq] = h->used ;
 }
 
 unsigned long long modshimBatchFlush (void *vms)
 {
   Twin *t = twinOf ((Modset*) vms) ;
-  batchSend (t) ;
-  U64 n = t->hashes ; t->hashes = 0 ;
-  free (t->off) ; t->off = 0 ;                     /* the next group pushes the caller's depths again */
+  U64 n = 0 ;
+  if (t->feeder)
+    { Feeder *f = (Feeder*) t->feeder ;
+      feederSend (f) ;
+      feederWait (f) ;
+      n = f->hashes ; f->hashes = 0 ;
+    }
+  t->inGroup = 0 ;                                 /* the next group pushes the caller's depths again */
   pull (t) ;
   return n ;
 }

@@ -43,6 +43,8 @@ int64_t HX(mod_scan)(int k, int w, int seed, const char *codes, int len,
 /* modset (modset.c) */
 HxModset *HX(modset_new)(int bits, int k, int w, int seed);
 void HX(modset_free)(HxModset *ms);
+/* touch every page of the index table (no semantic change; for timing bounded samples) */
+void HX(modset_prefault)(HxModset *ms);
 /* the addSequence loop of modutils.c:19-31 over a batch; returns total hashes */
 uint64_t HX(modset_add)(HxModset *ms, const char *codes, const uint64_t *offs, int64_t nseq);
 uint32_t HX(modset_max)(HxModset *ms);

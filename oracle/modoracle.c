@@ -161,6 +161,8 @@ HxModset *orc_modset_new(int bits, int k, int w, int seed)
   return modset_alloc(&h, bits, 0);
 }
 
+void orc_modset_prefault(HxModset *ms) { memset(ms->index, 0, (size_t)(ms->tableMask + 1) * sizeof(uint32_t)); }
+
 void orc_modset_free(HxModset *ms)
 {
   if (!ms) return;

@@ -50,6 +50,11 @@ int64_t ref_mod_scan(int k, int w, int seed, const char *codes, int len,
 HxModset *ref_modset_new(int bits, int k, int w, int seed)
 { return (HxModset *)modsetCreate(seqhashCreate(k, w, seed), bits, 0); }
 
+/* touch every page of the (calloc'ed, still unmapped) index table: a timed bounded sample then measures hashing and
+   probing, not the page faults a full-size job pays once (bench.py --impl reference) */
+void ref_modset_prefault(HxModset *h)
+{ Modset *ms = (Modset *)h; memset(ms->index, 0, ms->tableSize * sizeof(U32)); }
+
 void ref_modset_free(HxModset *h)
 { Modset *ms = (Modset *)h; if (!ms) return; free(ms->depth); modsetDestroy(ms); }
 

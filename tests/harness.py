@@ -37,6 +37,7 @@ class Checker:
         f("mod_scan", C.c_int64, [C.c_int, C.c_int, C.c_int, u8p, C.c_int, u64p, i32p, u8p, C.c_int64])
         f("modset_new", C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_int])
         f("modset_free", None, [C.c_void_p])
+        f("modset_prefault", None, [C.c_void_p])
         f("modset_add", C.c_uint64, [C.c_void_p, u8p, u64p, C.c_int64])
         f("modset_max", C.c_uint32, [C.c_void_p])
         f("modset_export", None, [C.c_void_p, u64p, u16p, u8p])
