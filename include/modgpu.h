@@ -89,6 +89,7 @@ int modgpuMarkEnds(const uint64_t *d_offs, uint64_t nSeq, uint64_t nBases,
 #define MODGPU_SEL_NOFUSE 16     /* modset add: keep K2 and the bucket scatter of K3 as separate kernels */
 #define MODGPU_SEL_NOFUSEPACK 32 /* modset add: keep K1 as a separate kernel (packed stream through HBM) */
 #define MODGPU_SEL_NOLUT 64      /* count mode: arithmetic prefilter instead of the shared-memory candidate table */
+#define MODGPU_SEL_GEN1 0x10000  /* count mode: the first-generation kernel (hash_count_kernel) for A/B runs */
 #define MODGPU_SEL_APPEND 128    /* modgpuModsetSelectBuckets*: keep the fill counts, append to the buckets of the previous
                                     batches (multi-GPU deferred build: several batches share one peer build) */
 
@@ -178,7 +179,7 @@ ModgpuTable *modgpuModsetTable(ModgpuModset *ms);
 /* use the caller's stream (e.g. torch's current stream) for all work */
 int modgpuModsetSetStream(ModgpuModset *ms, void *stream);
 /* MODGPU_SEL_* flags forwarded to the hash/select kernel (tuning, A/B tests);
- * bits 8..15 = insert-locality override + 1: 0 auto, 1 off, v = 2^(v-1) table regions */
+ * bits 8..15 = insert-locality override + 1: 0 auto, 1 off, v = 2^(v-1) table regions; bits 16.. = more MODGPU_SEL_* flags */
 int modgpuModsetSetFlags(ModgpuModset *ms, int flags);
 /* exactOrder != 0: keep the reference's first-occurrence index numbering */
 int modgpuModsetSetExactOrder(ModgpuModset *ms, int exactOrder);

@@ -89,7 +89,7 @@ extern "C" int modgpuModsetSetStream(ModgpuModset *ms, void *stream)
 
 extern "C" int modgpuModsetSetFlags(ModgpuModset *ms, int flags)
 {
-  ms->selFlags = flags & 0xFF;
+  ms->selFlags = flags & 0xFF00FF;
   // bits 8..15: insert locality override + 1 (0 = auto): 1 = off, 2.. = 2^(v-1) regions
   const int v = (flags >> 8) & 0xFF;
   ms->regionBits = v ? v - 1 : -1;
@@ -119,17 +119,22 @@ extern "C" int modgpuModsetTimes(ModgpuModset *ms, double ms_out[MODGPU_T_N], ui
 // 3.1 Gbases).  Any early return between the two leaves endsCleanCap at 0 and the next batch clears the buffer.
 static int ends_mark(ModgpuModset *ms, const uint64_t *d_offs, uint64_t nSeq, uint64_t nBases, cudaStream_t st)
 {
-  int rc = ms->ends.ensure(modgpuEndsWords(nBases) * 4);
+  // the per-base flag words, then one byte per 2048-base tile of the count kernels (set and cleared with the flags)
+  const uint64_t flagBytes = modgpuEndsWords(nBases) * 4, nTiles = (nBases + 2047) / 2048;
+  int rc = ms->ends.ensure(flagBytes + nTiles + 64);
   if (rc) return rc;
   if (ms->endsCleanCap != ms->ends.cap) MG_CUDA(cudaMemsetAsync(ms->ends.p, 0, ms->ends.cap, st));
   ms->endsCleanCap = 0;
-  return mg_ends_sparse(d_offs, nSeq, (uint32_t *)ms->ends.p, 1, st);
+  // sparse when at most one tile in four can hold a sequence end (genomes, long reads); short reads keep per-tile staging
+  ms->tileFlags = (nSeq * 4 <= nTiles) ? (uint8_t *)ms->ends.p + flagBytes : nullptr;
+  ms->tileFlagsAt = (uint8_t *)ms->ends.p + flagBytes;
+  return mg_ends_sparse(d_offs, nSeq, (uint32_t *)ms->ends.p, ms->tileFlags, 1, st);
 }
 
 static int ends_unmark(ModgpuModset *ms, const uint64_t *d_offs, uint64_t nSeq, cudaStream_t st)
 {
   ProfScope p(ms, MODGPU_T_PACK, 1);
-  int rc = mg_ends_sparse(d_offs, nSeq, (uint32_t *)ms->ends.p, 0, st);
+  int rc = mg_ends_sparse(d_offs, nSeq, (uint32_t *)ms->ends.p, ms->tileFlags, 0, st);
   if (rc) return rc;
   ms->endsCleanCap = ms->ends.cap;
   return MODGPU_OK;
@@ -240,7 +245,7 @@ static int add_chunk_fused(ModgpuModset *ms, const uint8_t *d_bases, const uint6
   { ProfScope p(ms, MODGPU_T_SELECT, mg_select_launches(&ms->hasher, ms->selFlags | (ms->exactOrder ? MODGPU_SEL_ORDERED : 0)));
     if ((rc = mg_hash_select_scatter(&ms->hasher, (const uint64_t *)ms->packed.p, (const uint32_t *)ms->ends.p, nBases, dCount,
                                      ms->work.p, ms->selFlags, b.slotBits, b.regionBits, b.cap, b.cursors, b.buckets,
-                                     b.overflow, b.overflowCap, fusePack ? d_bases : nullptr, isAscii, st)))
+                                     b.overflow, b.overflowCap, fusePack ? d_bases : nullptr, isAscii, ms->tileFlags, st)))
       return rc;
   }
   // the build follows without a host round trip: its kernels check on the device that the overflow list was
@@ -725,7 +730,7 @@ extern "C" int modgpuModsetSelectBucketsDevice(ModgpuModset *ms, const uint8_t *
   { ProfScope p(ms, MODGPU_T_SELECT, mg_select_launches(&ms->hasher, ms->selFlags | (ms->exactOrder ? MODGPU_SEL_ORDERED : 0)));
     if ((rc = mg_hash_select_peer(&ms->hasher, (const uint64_t *)ms->packed.p, (const uint32_t *)ms->ends.p, nBases, d_count, ms->work.p,
                                   ms->selFlags, mg_table_slot_bits(ms->table), 11, nOwners, bucketCap, d_cursors, d_buckets,
-                                  d_overflow, overflowCap, d_ovfCounts, fusePack ? d_bases : nullptr, isAscii, st)))
+                                  d_overflow, overflowCap, d_ovfCounts, fusePack ? d_bases : nullptr, isAscii, ms->tileFlags, st)))
       return rc;
   }
   return ends_unmark(ms, d_offs, nSeq, st);

@@ -27,54 +27,10 @@
 #include <string.h>
 #include <stdlib.h>
 #include "mg_device.cuh"
+#include "mg_select.cuh"
 
 #define MG_TILE_PACK_BYTES (MG_TILE_THREADS * 8 + 16)     // 256 words + overlap word, 16 B multiple (258 words)
 #define MG_TILE_ENDS_BYTES (MG_TILE_THREADS * 4 + 16)
-
-struct SelectParams {
-  MgKHasher H;
-  const uint64_t *packed;
-  const uint32_t *ends;
-  uint64_t nBases;
-  uint32_t nTiles;
-  uint32_t strandBit;          // MODGPU_SEL_STRAND
-  uint64_t *outKmer;
-  uint32_t *outPos;            // nullable
-  uint64_t cap;
-  unsigned long long *count;   // device total
-  uint64_t *status;            // look-back descriptors [nTiles]
-  uint32_t *ticket;            // tile ticket
-  // SCATTER: selected k-mers go straight into the table's per-region buckets
-  // (table.cu bulk insert) instead of a list
-  uint32_t slotBits, regionBits, nRegions, bucketCap;
-  uint32_t *cursors;           // [nRegions] fill counts, [nRegions] = overflow count
-  uint64_t *buckets;
-  uint64_t *overflow;
-  uint64_t overflowCap;
-  // OUT == 2: selected k-mers go into nOwners contiguous segments of a send
-  // buffer (multi-GPU: one segment per owner GPU), ownerCursor[o] counts them
-  uint32_t nOwners;
-  uint32_t *ownerCursor;
-  uint64_t *ownerBuf;
-  uint64_t ownerCap;
-  // LOAD == 2: the batch as bytes (16-byte aligned), K1 fused into the tile loader
-  const uint8_t *raw;
-  uint32_t rawAscii;
-  // LUTK != 0: the 16 KiB candidate table of mg_lut_entry (built per launch into the workspace)
-  const uint8_t *lut;
-  uint32_t keepBuckets;        // 1: bucket stores ask L2 to keep the line (evict-last)
-};
-
-// workspace layout: [0, 64) ticket and scratch counters, [64, 64 + MG_LUT_SIZE) candidate table, then the
-// look-back descriptors of the ordered kernel
-#define MG_WS_LUT 64
-#define MG_WS_STATUS (64 + MG_LUT_SIZE)
-
-__global__ void __launch_bounds__(256) lut_build_kernel(const MgKHasher H, uint8_t *lut)
-{
-  const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
-  if (x < MG_LUT_SIZE) lut[x] = (uint8_t)mg_lut_entry(H, x);
-}
 
 // Phase 2 helper: evaluate queue entry e = (source thread << 5 | window) of the
 // current tile from the shared-memory copy of the packed words.
@@ -351,47 +307,6 @@ __global__ void __launch_bounds__(MG_SEL_THREADS) hash_select_ordered_kernel(con
 // OUT: 0 = list, 1 = scatter into the table's region buckets, 2 = per-owner segments,
 //      3 = per-(owner, region) buckets: what the owner's region build consumes directly
 // RAW: the batch as bytes (codes or ASCII, 16-byte aligned) instead of the packed stream
-#define MG_CNT_WARPS 16
-#define MG_CNT_THREADS (MG_CNT_WARPS * 32)
-#define MG_CNT_CHUNK 4                                          // warp tiles per scheduling chunk (power of two)
-#define MG_WT_RUNS 64                                          // runs per warp tile
-#define MG_WT_BASES (MG_WT_RUNS * MG_RUN)                      // 2048
-#define MG_WQ_CAP 256                                          // queue entries per warp (of its 2048 windows)
-#define MG_WS_RAW_BYTES (MG_WT_BASES + 32)                     // the tile + the overlap word's 32 bases
-#define MG_WS_PACK_BYTES (MG_WT_RUNS * 8 + 16)                 // 64 words + overlap word (+ pad to 16 B)
-#define MG_WS_ENDS_BYTES (MG_WT_RUNS * 4 + 16)                 // 64 flag words + 2 (+ pad)
-
-// 16 bytes -> 16 two-bit codes, first base in the top bits (K1 arithmetic, mg_pack4;
-// the four gathered bytes are merged with three byte permutes instead of shifts and masks)
-template <bool ASCII>
-__device__ __forceinline__ uint32_t pack16_dev(const uint4 q)
-{
-  uint32_t c0, c1, c2, c3;
-  if (ASCII)
-    { c0 = ((q.x >> 1) ^ (q.x >> 2)) & 0x03030303u; c1 = ((q.y >> 1) ^ (q.y >> 2)) & 0x03030303u;
-      c2 = ((q.z >> 1) ^ (q.z >> 2)) & 0x03030303u; c3 = ((q.w >> 1) ^ (q.w >> 2)) & 0x03030303u;
-    }
-  else
-    { c0 = q.x & 0x03030303u; c1 = q.y & 0x03030303u; c2 = q.z & 0x03030303u; c3 = q.w & 0x03030303u; }
-  const uint32_t p0 = c0 * 0x40100401u, p1 = c1 * 0x40100401u, p2 = c2 * 0x40100401u, p3 = c3 * 0x40100401u;
-  const uint32_t t = __byte_perm(p0, p1, 0x3700), u = __byte_perm(p2, p3, 0x0037);
-  return __byte_perm(t, u, 0x3254);
-}
-
-// 32 bases starting at b0 of the raw batch, with bounds (the ragged last tile only)
-template <bool ASCII>
-__device__ __forceinline__ uint64_t pack32_raw(const uint8_t *raw, uint64_t b0, uint64_t nBases)
-{
-  if (b0 + 32 <= nBases)
-    { const uint4 *src = reinterpret_cast<const uint4 *>(raw + b0);
-      return ((uint64_t)pack16_dev<ASCII>(__ldg(src)) << 32) | pack16_dev<ASCII>(__ldg(src + 1));
-    }
-  uint64_t w = 0;
-  for (uint32_t j = 0; j < 32 && b0 + j < nBases; ++j)
-    w |= (uint64_t)mg_code_of(raw[b0 + j], ASCII) << (62 - 2 * j);
-  return w;
-}
-
 template <bool RAW> struct CountWarpSmem {
   __align__(16) uint8_t stage[RAW ? MG_WS_RAW_BYTES : MG_WS_PACK_BYTES];
   __align__(16) uint32_t ends[MG_WS_ENDS_BYTES / 4];
@@ -779,6 +694,10 @@ static int dispatch_count_load(const SelectParams &P, cudaStream_t st)
 template <int OUT>
 static int dispatch_count(const SelectParams &P, bool pf, int flags, cudaStream_t st)
 {
+  // raw bytes with the table-driven or the full 32-bit scan: the second-generation kernel (hash_count2.cu)
+  { const int rc = mg_count2_launch(P, OUT, flags, st);
+    if (rc != 1) return rc;
+  }
   if (!pf) return dispatch_count_load<OUT, false, 0>(P, st);
   if (P.H.lut && !(flags & MODGPU_SEL_NOLUT))
     return P.H.k == 31 ? dispatch_count_load<OUT, true, 31>(P, st) : dispatch_count_load<OUT, true, 30>(P, st);
@@ -820,7 +739,7 @@ extern "C" int modgpuHashSelect(const ModgpuHasher *h, const uint64_t *d_packed,
 int mg_hash_select_scatter(const ModgpuHasher *h, const uint64_t *d_packed, const uint32_t *d_ends, uint64_t nBases,
                            uint64_t *d_count, void *d_workspace, int flags, uint32_t slotBits, uint32_t regionBits,
                            uint32_t bucketCap, uint32_t *d_cursors, uint64_t *d_buckets, uint64_t *d_overflow,
-                           uint64_t overflowCap, const uint8_t *d_raw, int rawAscii, cudaStream_t st)
+                           uint64_t overflowCap, const uint8_t *d_raw, int rawAscii, const uint8_t *d_tileFlags, cudaStream_t st)
 {
   if (nBases >= (1ull << 32)) { mg_set_error("hash_select: batch of %llu bases exceeds 2^32-1", (unsigned long long)nBases); return MODGPU_EINVAL; }
   MG_CUDA(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
@@ -842,6 +761,7 @@ int mg_hash_select_scatter(const ModgpuHasher *h, const uint64_t *d_packed, cons
   const bool pf = P.H.prefilter && !(flags & MODGPU_SEL_NOPREFILTER);
   const bool tma = !(flags & MODGPU_SEL_NOTMA);
   if (d_raw) { P.raw = d_raw; P.rawAscii = rawAscii ? 1u : 0u; }
+  P.tileFlags = d_tileFlags;
   return dispatch_count<1>(P, pf, flags, st);
 }
 
@@ -881,7 +801,7 @@ int mg_hash_select_peer(const ModgpuHasher *h, const uint64_t *d_packed, const u
                         uint64_t *d_count, void *d_workspace, int flags, uint32_t slotBits, uint32_t regionBits,
                         uint32_t nOwners, uint32_t bucketCap, uint32_t *d_cursors, uint64_t *d_buckets,
                         uint64_t *d_overflow, uint64_t overflowCap, uint32_t *d_ovfCounts,
-                        const uint8_t *d_raw, int rawAscii, cudaStream_t st)
+                        const uint8_t *d_raw, int rawAscii, const uint8_t *d_tileFlags, cudaStream_t st)
 {
   if (nBases >= (1ull << 32)) { mg_set_error("hash_select: batch of %llu bases exceeds 2^32-1", (unsigned long long)nBases); return MODGPU_EINVAL; }
   if (nOwners < 1 || nOwners > 64) { mg_set_error("hash_select: nOwners %u out of range 1..64", nOwners); return MODGPU_EINVAL; }
@@ -910,6 +830,7 @@ int mg_hash_select_peer(const ModgpuHasher *h, const uint64_t *d_packed, const u
   const bool pf = P.H.prefilter && !(flags & MODGPU_SEL_NOPREFILTER);
   const bool tma = !(flags & MODGPU_SEL_NOTMA);
   if (d_raw) { P.raw = d_raw; P.rawAscii = rawAscii ? 1u : 0u; }
+  P.tileFlags = d_tileFlags;
   return dispatch_count<3>(P, pf, flags, st);
 }
 

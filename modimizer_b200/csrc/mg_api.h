@@ -7,7 +7,7 @@
 #include "mg_device.cuh"
 
 MgKHasher mg_khasher_from(const ModgpuHasher *h);
-int mg_ends_sparse(const uint64_t *d_offs, uint64_t nSeq, uint32_t *d_ends, int set, cudaStream_t st);
+int mg_ends_sparse(const uint64_t *d_offs, uint64_t nSeq, uint32_t *d_ends, uint8_t *d_tileFlags, int set, cudaStream_t st);
 bool mg_table_clear_pending(const ModgpuTable *t);
 void mg_table_bulk_abort(ModgpuTable *t, bool wasPending);
 int mg_select_launches(const ModgpuHasher *h, int flags);      // kernels one hash/select call launches
@@ -31,7 +31,7 @@ int mg_hash_select_peer(const ModgpuHasher *h, const uint64_t *d_packed, const u
                         uint64_t *d_count, void *d_workspace, int flags, uint32_t slotBits, uint32_t regionBits,
                         uint32_t nOwners, uint32_t bucketCap, uint32_t *d_cursors, uint64_t *d_buckets,
                         uint64_t *d_overflow, uint64_t overflowCap, uint32_t *d_ovfCounts,
-                        const uint8_t *d_raw, int rawAscii, cudaStream_t st);
+                        const uint8_t *d_raw, int rawAscii, const uint8_t *d_tileFlags, cudaStream_t st);
 int mg_table_build_from_buckets(ModgpuTable *t, const uint64_t *d_buckets, const uint32_t *d_cursors, uint32_t cap, uint32_t nSrc,
                                 const uint64_t *d_overflow, uint64_t overflowCap, const uint32_t *d_ovfCounts, cudaStream_t st);
 int mg_table_build_from_peers(ModgpuTable *t, const uint64_t *const *d_buckets, const uint32_t *d_cursors, uint32_t cap, uint32_t nSrc,
@@ -46,7 +46,7 @@ int mg_table_insert_segments(ModgpuTable *t, const uint64_t *d_segs, uint32_t nS
 int mg_hash_select_scatter(const ModgpuHasher *h, const uint64_t *d_packed, const uint32_t *d_ends, uint64_t nBases,
                            uint64_t *d_count, void *d_workspace, int flags, uint32_t slotBits, uint32_t regionBits,
                            uint32_t bucketCap, uint32_t *d_cursors, uint64_t *d_buckets, uint64_t *d_overflow,
-                           uint64_t overflowCap, const uint8_t *d_raw, int rawAscii, cudaStream_t st);
+                           uint64_t overflowCap, const uint8_t *d_raw, int rawAscii, const uint8_t *d_tileFlags, cudaStream_t st);
 uint64_t mg_table_bulk_threshold(const ModgpuTable *t);
 int mg_slot_partition(const uint64_t *d_kmers, uint64_t n, uint32_t slotBits, uint32_t bucketBits,
                       uint64_t *d_out, uint64_t *d_scratch, cudaStream_t st);
@@ -103,6 +103,9 @@ struct ModgpuModset {
   bool dirty = false;               // entries inserted since the last numbering
   DevBuf bases[2], offs[2], pk[2], packed, ends, kmers, kmers2, gpos, slot, work, misc, expo;
   size_t endsCleanCap = 0;          // ms->ends is all zero over this capacity (0: unknown / flags of a batch still set)
+  uint8_t *tileFlagsAt = nullptr;
+  uint8_t *tileFlags = nullptr;     // the current batch's per-tile "a sequence ends here" bytes (tail of ms->ends), or null:
+                                    // many short sequences - the count kernel stages the per-base flags with every tile
   int regionBits = -1;              // -1 auto: partition inserts by table region when the table exceeds L2
   PinBuf hOffs[2], hMisc;
   cudaEvent_t evCopied[2] = { nullptr, nullptr }, evFree[2] = { nullptr, nullptr };

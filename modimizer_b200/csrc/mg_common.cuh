@@ -320,6 +320,62 @@ MGHD bool mg_eval_single_pow2(const MgKHasher &H, uint64_t w0, uint64_t w1, uint
   return ((uint32_t)pm & (((1u << H.tz) - 1u) << S)) == 0u;    // the tz low hash bits are zero
 }
 
+// ---- one window in 32-bit pieces (k >= 16): what the second-generation count kernel evaluates per queue entry.
+// Same result as mg_eval_single (canonical k-mer, strand with ties going reverse, hash % d == 0), branch-free:
+// the window is a funnel-shifted field of the run's two packed words held as four 32-bit halves, the reverse
+// complement comes from two BREVs, the two 64-bit products are one wide multiply and two multiply-adds each, and
+// the tests run on the masked product as in mg_eval_window.  POW2: d is a power of two (no odd-part test).
+MGHD uint32_t mg_frc32(uint32_t lo, uint32_t hi, uint32_t s)   // low word of (hi:lo) >> s, 0 <= s <= 32 (32 gives hi)
+{
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_rc(lo, hi, s);
+#else
+  return s >= 32 ? hi : (s ? ((lo >> s) | (hi << (32 - s))) : lo);
+#endif
+}
+
+MGHD uint32_t mg_pairrev32(uint32_t x)                          // reverse the order of the sixteen 2-bit groups
+{
+#if defined(__CUDA_ARCH__)
+  const uint32_t y = __brev(x);
+#else
+  uint32_t y = x;
+  y = ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
+  y = ((y >> 2) & 0x33333333u) | ((y & 0x33333333u) << 2);
+  y = ((y >> 4) & 0x0F0F0F0Fu) | ((y & 0x0F0F0F0Fu) << 4);
+  y = ((y >> 8) & 0x00FF00FFu) | ((y & 0x00FF00FFu) << 8);
+  y = (y >> 16) | (y << 16);
+#endif
+  return ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
+}
+
+template <bool POW2>
+MGHD bool mg_eval32_single(const MgEval32 &E, uint32_t shift, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t i,
+                           uint32_t *kmLo, uint32_t *kmHi, bool *isF)
+{ // the run's words w0 = a:b, w1 = c:d; the window starts 2i bits below the top of w0
+  const uint32_t sl = 2 * i;
+  const bool up = sl >= 32;
+  const uint32_t x0 = up ? b : a, x1 = up ? c : b, x2 = up ? d : c;
+  const uint32_t tHi = mg_fl32(x1, x0, sl & 31u), tLo = mg_fl32(x2, x1, sl & 31u);     // top 64 bits of (w0:w1) << 2i
+  const uint32_t fLo = mg_frc32(tLo, tHi, shift), fHi = mg_frc32(tHi, 0u, shift);     // >> (64 - 2k): the forward k-mer
+  const uint32_t qHi = ~mg_pairrev32(fLo), qLo = ~mg_pairrev32(fHi);                  // complement of the reversed k-mer, at the top
+  const uint32_t rLo = mg_frc32(qLo, qHi, shift), rHi = mg_frc32(qHi, 0u, shift);
+  uint32_t pfl, pfh, prl, prh;
+  mg_mul64lo(fLo, fHi, E.fLo, E.fHi, &pfl, &pfh);
+  mg_mul64lo(rLo, rHi, E.fLo, E.fHi, &prl, &prh);
+  pfl &= E.keepLo; prl &= E.keepLo;                           // the hashes, still shifted up: compared as masked products
+  const bool fw = (pfh < prh) || (pfh == prh && pfl < prl);   // hashF < hashR; ties go reverse (seqhash.c:66-67)
+  const uint32_t ml = fw ? pfl : prl, mh = fw ? pfh : prh;
+  *kmLo = fw ? fLo : rLo; *kmHi = fw ? fHi : rHi; *isF = fw;
+  bool ok = ((ml & E.lowLo) | (mh & E.lowHi)) == 0u;          // the tz low hash bits are zero
+  if (!POW2)
+    { uint32_t ql, qh;
+      mg_mul64lo(ml, mh, E.invLo, E.invHi, &ql, &qh);         // exact division by the odd part
+      ok = ok && ((qh < E.limHi) || (qh == E.limHi && ql <= E.limLo));
+    }
+  return ok;
+}
+
 // power-of-two prefilter (H.prefilter): a window can only be selected if the tz
 // low bits of hash(fwd) or of hash(rc) are zero, and with 64-2k+tz <= 32 those
 // bits live in the LOW 32-bit word of the product, which depends only on the low

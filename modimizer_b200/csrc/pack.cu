@@ -49,8 +49,11 @@ __global__ void __launch_bounds__(256) pack2bit_kernel(const uint8_t *__restrict
 }
 
 // one thread per sequence: flag its last base.  d_ends must be zeroed first.
+// tileFlags (nullable): one byte per 2048-base warp tile of the count kernels, set for the tile that holds the flag and
+// for the tile before it when the flag lies within that tile's 64-base lookahead (hash_count2.cu reads the per-base
+// flags only for tiles whose byte is set)
 __global__ void __launch_bounds__(256) mark_ends_kernel(const uint64_t *__restrict__ offs, uint64_t nSeq,
-                                                        uint32_t *__restrict__ ends)
+                                                        uint32_t *__restrict__ ends, uint8_t *__restrict__ tileFlags)
 {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nSeq; r += stride)
@@ -58,6 +61,11 @@ __global__ void __launch_bounds__(256) mark_ends_kernel(const uint64_t *__restri
       if (b > a)
         { uint64_t g = b - 1;
           atomicOr(ends + (g >> 5), 1u << (g & 31));
+          if (tileFlags)
+            { const uint64_t t = g >> 11;
+              tileFlags[t] = 1;
+              if (t && (g & 2047) < 64) tileFlags[t - 1] = 1;
+            }
         }
     }
 }
@@ -65,24 +73,32 @@ __global__ void __launch_bounds__(256) mark_ends_kernel(const uint64_t *__restri
 // the same flags cleared again (every touched word becomes 0: with the clean-buffer invariant of api.cu the
 // whole array is zero again afterwards, without a 1-bit-per-base memset per batch)
 __global__ void __launch_bounds__(256) unmark_ends_kernel(const uint64_t *__restrict__ offs, uint64_t nSeq,
-                                                          uint32_t *__restrict__ ends)
+                                                          uint32_t *__restrict__ ends, uint8_t *__restrict__ tileFlags)
 {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nSeq; r += stride)
     { uint64_t a = offs[r], b = offs[r + 1];
-      if (b > a) ends[(b - 1) >> 5] = 0u;
+      if (b > a)
+        { const uint64_t g = b - 1;
+          ends[g >> 5] = 0u;
+          if (tileFlags)
+            { const uint64_t t = g >> 11;
+              tileFlags[t] = 0;
+              if (t && (g & 2047) < 64) tileFlags[t - 1] = 0;
+            }
+        }
     }
 }
 
 // set (1) or clear (0) the end flags of nSeq sequences in a buffer that is otherwise all zero
-int mg_ends_sparse(const uint64_t *d_offs, uint64_t nSeq, uint32_t *d_ends, int set, cudaStream_t st)
+int mg_ends_sparse(const uint64_t *d_offs, uint64_t nSeq, uint32_t *d_ends, uint8_t *d_tileFlags, int set, cudaStream_t st)
 {
   if (!nSeq) return MODGPU_OK;
   uint64_t blocks = (nSeq + 255) / 256;
   uint64_t maxBlocks = (uint64_t)mg_num_sms() * 8;
   if (blocks > maxBlocks) blocks = maxBlocks;
-  if (set) mark_ends_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_offs, nSeq, d_ends);
-  else unmark_ends_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_offs, nSeq, d_ends);
+  if (set) mark_ends_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_offs, nSeq, d_ends, d_tileFlags);
+  else unmark_ends_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_offs, nSeq, d_ends, d_tileFlags);
   MG_LAUNCH_CHECK("mark_ends");
   return MODGPU_OK;
 }
@@ -131,7 +147,7 @@ extern "C" int modgpuMarkEnds(const uint64_t *d_offs, uint64_t nSeq, uint64_t nB
   uint64_t blocks = (nSeq + 255) / 256;
   uint64_t maxBlocks = (uint64_t)mg_num_sms() * 8;
   if (blocks > maxBlocks) blocks = maxBlocks;
-  mark_ends_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_offs, nSeq, d_ends);
+  mark_ends_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_offs, nSeq, d_ends, nullptr);
   MG_LAUNCH_CHECK("mark_ends");
   return MODGPU_OK;
 }

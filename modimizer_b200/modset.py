@@ -296,9 +296,7 @@ class Modset:
         p = lib.modgpuModsetReadMod(str(path).encode())
         if not p:
             raise ModgpuError("modsetRead: " + _lib.last_error())
-        bits = 0
-        ms = cls(bits, _handle=p)
-        return ms
+        return cls(int(lib.modgpuModsetBits(p)), _handle=p)
 
     def readset(self, data, offsets=None, is_ascii=None, reset_depth=True, cap=None):
         """hot loop of modasm's readsetFileRead (reference modasm.c:151-191)"""

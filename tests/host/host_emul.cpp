@@ -85,6 +85,20 @@ int64_t hm_select(int k, int d, uint64_t factor1, const uint8_t *bytes, uint64_t
             }
           sel &= usable;
         }
+      if (H.shift <= 32)                   // the count kernel's per-entry evaluation in 32-bit pieces: every window, both forms
+        { const MgEval32 E = mg_eval32_prepare(H);
+          const uint64_t w0 = words[T], w1 = words[T + 1];
+          for (uint32_t i = 0; i < 32; ++i)
+            { uint64_t km; bool f; uint32_t kl, kh; bool f3;
+              const bool a = mg_eval_single(H, w0, w1, i, &km, &f);
+              const bool b3 = mg_eval32_single<false>(E, H.shift, (uint32_t)(w0 >> 32), (uint32_t)w0, (uint32_t)(w1 >> 32), (uint32_t)w1, i, &kl, &kh, &f3);
+              if (a != b3 || km != (((uint64_t)kh << 32) | kl) || f != f3) return -4000000 - (int64_t)(p0 + i);
+              if (H.oddInv == 1)
+                { const bool b4 = mg_eval32_single<true>(E, H.shift, (uint32_t)(w0 >> 32), (uint32_t)w0, (uint32_t)(w1 >> 32), (uint32_t)w1, i, &kl, &kh, &f3);
+                  if (a != b4 || km != (((uint64_t)kh << 32) | kl) || f != f3) return -5000000 - (int64_t)(p0 + i);
+                }
+            }
+        }
       for (uint32_t i = 0; i < 32; ++i)
         if (sel >> i & 1)
           { uint64_t km; bool f;
