@@ -15,8 +15,10 @@
 //     reads keep the staged flags (ENDS);
 //   - the tile is read TRANSPOSED: lane l packs the 16-byte chunks l, l+32, l+64, l+96 (conflict-free as they lie)
 //     and stores the four half-words where the packed tile wants them, instead of rotating its reads and the results;
-//   - the queue is filled through ONE shared-memory atomic per lane (order is irrelevant in count mode) instead of
-//     a warp scan, and drained from the top bit (FLO alone, no BREV);
+//   - the queue offsets come from three ballots of the (small) per-lane counts instead of a shuffle scan, and the
+//     masks are drained from the top bit (FLO alone, no BREV);
+//   - evaluation and output run round by round with the bucket store one round behind its atomic, so that the L2
+//     round trip of the position is hidden behind the next evaluation;
 //   - a queue entry is evaluated in 32-bit pieces without a branch (mg_eval32_single: funnel-shifted window, the
 //     reverse complement from two BREVs, three multiply-adds per 64-bit product);
 //   - the region of a selected k-mer is one shift of the high product word.
@@ -28,14 +30,12 @@
 #include <stdlib.h>
 #include "mg_select.cuh"
 
-#define C2_ROUNDS 4                                             // queue entries a lane keeps in registers
 
 template <bool ENDS> struct C2WarpSmem {
   __align__(16) uint8_t stage[MG_WS_RAW_BYTES];                // the raw tile + 32 bytes of overlap (TMA destination)
   __align__(16) uint32_t ends[ENDS ? MG_WS_ENDS_BYTES / 4 : 4];
   __align__(16) uint32_t half[2 * (MG_WT_RUNS + 2)];           // the packed tile as 32-bit halves (word w = half[2w+1] : half[2w])
   __align__(8) uint64_t bar;
-  uint32_t qn[2];                                              // queue fill of this tile / the next one
   uint16_t queue[MG_WQ_CAP];
 };
 
@@ -54,7 +54,8 @@ __device__ __forceinline__ void c2_issue_tile(const SelectParams &P, C2WarpSmem<
   if (ENDS) mg_tma_load_1d_hint(S->ends, P.ends + tile * MG_WT_RUNS, MG_WS_ENDS_BYTES, &S->bar, MG_L2_EVICT_FIRST);
 }
 
-// SCAN: 0 = every window evaluated in full (32-bit pieces, k >= 16), 1 = table-driven candidates (LUTK = k)
+// SCAN: 0 = every window evaluated in full (32-bit pieces, k >= 16; LUTK = 1 when d is odd: no low-bit test),
+//       1 = table-driven candidates (LUTK = k)
 // OUT:  0 = list, 1 = the table's region buckets, 3 = per-(owner, region) buckets
 template <int SCAN, int LUTK, int OUT, bool ASCII, bool ENDS>
 __global__ void __launch_bounds__(MG_CNT_THREADS, SCAN ? 3 : 2) hash_count2_kernel(const SelectParams P)
@@ -80,13 +81,12 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, SCAN ? 3 : 2) hash_count2_kern
   // a tile can be bulk-copied when all of it and its overlap lie inside the batch (the raw bytes carry no slack)
   const uint64_t nBulk = P.nBases >= MG_WS_RAW_BYTES ? (P.nBases - MG_WS_RAW_BYTES) / MG_WT_BASES + 1 : 0;
   uint32_t nSelectedLocal = 0;
-  uint32_t phase = 0, qp = 0;
+  uint32_t phase = 0;
 
   if (lane == 0)
     { mg_mbar_init(&S->bar, 1);
       mg_fence_barrier_init();
       mg_fence_proxy_async();
-      S->qn[0] = 0; S->qn[1] = 0;
       if (tile < nBulk) c2_issue_tile<ENDS>(P, S, tile);
     }
   if (SCAN)
@@ -96,12 +96,12 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, SCAN ? 3 : 2) hash_count2_kern
     }
   __syncthreads();
 
-  for (; tile < P.nTiles; tile = tileNext, qp ^= 1)
+  for (; tile < P.nTiles; tile = tileNext)
     { const uint32_t run0 = lane * 2;
       const uint64_t tileBase = tile * MG_WT_BASES;
       uint32_t tflag = 0;
       if (!ENDS) tflag = __ldg(P.tileFlags + tile);         // warp-uniform; consumed after the scan
-      uint32_t e0 = 0, e1 = 0, e2 = 0;
+      uint32_t e0 = 0, e1 = 0, e2 = 0, bl0 = 0, bl1 = 0;
       uint64_t *W = reinterpret_cast<uint64_t *>(S->half);
       if (tile < nBulk)
         { mg_mbar_wait(&S->bar, phase);
@@ -113,7 +113,13 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, SCAN ? 3 : 2) hash_count2_kern
           const uint32_t at = lane ^ 1u;                     // little-endian halves of a 64-bit word: the first chunk is the high one
           S->half[at] = h0; S->half[32 + at] = h1; S->half[64 + at] = h2; S->half[96 + at] = h3;
           if (lane < 2) S->half[128 + at] = pack16_dev<ASCII>(src[128 + lane]);
-          if (ENDS) { e0 = S->ends[run0]; e1 = S->ends[run0 + 1]; e2 = S->ends[run0 + 2]; }
+          if (ENDS)
+            { // the staged flags are turned into the blocked masks HERE, before the warp barrier that frees the staging
+              // buffers for the next bulk copy: a load the compiler sinks below the copy's issue would read the next tile
+              e0 = S->ends[run0]; e1 = S->ends[run0 + 1]; e2 = S->ends[run0 + 2];
+              bl0 = mg_blocked_mask((uint64_t)e0 | ((uint64_t)e1 << 32), H.k);
+              bl1 = mg_blocked_mask((uint64_t)e1 | ((uint64_t)e2 << 32), H.k);
+            }
         }
       else
         { // the ragged end of the batch: guarded loads
@@ -122,8 +128,11 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, SCAN ? 3 : 2) hash_count2_kern
           W[run0 + 1] = pack32_raw<ASCII>(P.raw, word * MG_RUN + 32, P.nBases);
           if (lane == 31) W[MG_WT_RUNS] = pack32_raw<ASCII>(P.raw, word * MG_RUN + 64, P.nBases);
           e0 = __ldg(P.ends + word); e1 = __ldg(P.ends + word + 1); e2 = __ldg(P.ends + word + 2);
+          bl0 = mg_blocked_mask((uint64_t)e0 | ((uint64_t)e1 << 32), H.k);
+          bl1 = mg_blocked_mask((uint64_t)e1 | ((uint64_t)e2 << 32), H.k);
           tflag = 1;
         }
+      asm volatile("" : "+r"(bl0), "+r"(bl1) :: "memory");      // (the masks exist in registers before the barrier)
       __syncwarp();
       // every lane has consumed the staged tile: the next tile's copy streams in behind the computation of this one
       tileNext = tile + 1;
@@ -131,10 +140,7 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, SCAN ? 3 : 2) hash_count2_kern
         { tileNext = (uint64_t)__shfl_sync(0xffffffffu, pendingChunk, 0) * MG_CNT_CHUNK;
           if (lane == 0 && tileNext < P.nTiles) pendingChunk = nWarps + atomicAdd(P.ticket, 1u);
         }
-      if (lane == 0)
-        { S->qn[qp ^ 1] = 0;                                 // the next tile's queue counter (last used two tiles ago)
-          if (tileNext < nBulk) c2_issue_tile<ENDS>(P, S, tileNext);
-        }
+      if (lane == 0 && tileNext < nBulk) c2_issue_tile<ENDS>(P, S, tileNext);
       const uint4 w01 = *reinterpret_cast<const uint4 *>(S->half + 2 * run0);       // words run0, run0 + 1
       const uint2 w2h = *reinterpret_cast<const uint2 *>(S->half + 2 * run0 + 4);   // word run0 + 2
       // 32-bit halves of the three words, most significant first: a:b = w0, c:d = w1, e:f = w2
@@ -153,188 +159,149 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, SCAN ? 3 : 2) hash_count2_kern
             { const MgRun RR = mg_run_prepare(wa, wb, H.k);
               const MgRun32 Q = mg_run32(RR);
               uint32_t mh = 0;
-              if (H.tz == 0)
-                {
 #pragma unroll
-                  for (int i = 0; i < MG_RUN; ++i)
-                    { const bool ok = mg_selected32<true>(E, Q, i);
-                      asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p or.b32 %0, %0, %2;\n\t}" : "+r"(mh) : "r"((uint32_t)ok), "r"(1u << i));
-                    }
-                }
-              else
-                {
-#pragma unroll
-                  for (int i = 0; i < MG_RUN; ++i)
-                    { const bool ok = mg_selected32<false>(E, Q, i);
-                      asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p or.b32 %0, %0, %2;\n\t}" : "+r"(mh) : "r"((uint32_t)ok), "r"(1u << i));
-                    }
+              for (int i = 0; i < MG_RUN; ++i)
+                { const bool ok = mg_selected32<LUTK == 1>(E, Q, i);
+                  asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p or.b32 %0, %0, %2;\n\t}" : "+r"(mh) : "r"((uint32_t)ok), "r"(1u << i));
                 }
               if (h == 0) m0 = mh; else m1 = mh;
               wa = wb; wb = wc;
             }
         }
       // windows that would span two sequences or run off the batch are not usable
-      { bool plain = tileBase + MG_WT_BASES + MG_RUN <= P.nBases;
-        if (ENDS) plain = plain && !__any_sync(0xffffffffu, (e0 | e1 | e2) != 0u);
-        else plain = plain && !tflag;
-        if (!plain)
-          { if (!ENDS && tile < nBulk)
-              { const uint64_t word = tile * MG_WT_RUNS + run0;
-                e0 = __ldg(P.ends + word); e1 = __ldg(P.ends + word + 1); e2 = __ldg(P.ends + word + 2);
-              }
-            const uint64_t p0 = tileBase + (uint64_t)run0 * MG_RUN;
-            m0 &= mg_run_usable((uint64_t)e0 | ((uint64_t)e1 << 32), H.k, p0, P.nBases);
-            m1 &= mg_run_usable((uint64_t)e1 | ((uint64_t)e2 << 32), H.k, p0 + MG_RUN, P.nBases);
+      { const bool inside = tileBase + MG_WT_BASES + MG_RUN <= P.nBases;
+        if (!ENDS && tflag && tile < nBulk)                  // sparse flags: this tile has a sequence end in reach (warp-uniform)
+          { const uint64_t word = tile * MG_WT_RUNS + run0;
+            e0 = __ldg(P.ends + word); e1 = __ldg(P.ends + word + 1); e2 = __ldg(P.ends + word + 2);
+            bl0 = mg_blocked_mask((uint64_t)e0 | ((uint64_t)e1 << 32), H.k);
+            bl1 = mg_blocked_mask((uint64_t)e1 | ((uint64_t)e2 << 32), H.k);
+          }
+        m0 &= ~bl0; m1 &= ~bl1;
+        if (!inside)                                         // the last tiles: window starts beyond the batch
+          { const uint64_t p0 = tileBase + (uint64_t)run0 * MG_RUN;
+            m0 &= mg_run_usable(0ull, H.k, p0, P.nBases);
+            m1 &= mg_run_usable(0ull, H.k, p0 + MG_RUN, P.nBases);
           }
       }
 
-      // ---- the warp's queue of (run, window): one shared-memory atomic per lane reserves its entries
+      // ---- the warp's queue of (run, window).  Order is irrelevant in count mode: a lane's entries go behind those of the
+      // lower lanes; the prefix of the (small) per-lane counts comes from three ballots, no shuffle and no shared memory
       const uint32_t cnt = __popc(m0) + __popc(m1);
       uint16_t *wq = S->queue;
-      { uint32_t qoff = 0;
-        if (cnt) qoff = atomicAdd(&S->qn[qp], cnt);
-        if (cnt && qoff + cnt <= MG_WQ_CAP)
-          { uint32_t mm = m1;                                // from the top bit down: FLO alone finds it
-            const uint32_t eb1 = (run0 + 1) << 5, eb0 = run0 << 5;
-            while (mm) { const uint32_t i = c2_top_bit(mm); mm ^= 1u << i; wq[qoff++] = (uint16_t)(eb1 | i); }
-            mm = m0;
-            while (mm) { const uint32_t i = c2_top_bit(mm); mm ^= 1u << i; wq[qoff++] = (uint16_t)(eb0 | i); }
+      uint32_t nW, qoff;
+      { const uint32_t lt = (1u << lane) - 1u;
+        const uint32_t big = __ballot_sync(0xffffffffu, cnt > 7u);
+        if (big == 0)
+          { const uint32_t b0 = __ballot_sync(0xffffffffu, cnt & 1u), b1 = __ballot_sync(0xffffffffu, cnt & 2u), b2 = __ballot_sync(0xffffffffu, cnt & 4u);
+            qoff = __popc(b0 & lt) + 2u * __popc(b1 & lt) + 4u * __popc(b2 & lt);
+            nW = __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
+          }
+        else
+          { const uint32_t incl = mg_warp_incl_scan(cnt);
+            qoff = incl - cnt;
+            nW = __shfl_sync(0xffffffffu, incl, 31);
           }
       }
-      __syncwarp();
-      const uint32_t nW = S->qn[qp];
       if (nW == 0) { __syncwarp(); continue; }
       const bool queued = nW <= MG_WQ_CAP;                   // warp-uniform
+      if (queued)
+        { uint32_t mm = m1;                                  // from the top bit down: FLO alone finds it
+          const uint32_t eb1 = (run0 + 1) << 5, eb0 = run0 << 5;
+          while (mm) { const uint32_t i = c2_top_bit(mm); mm ^= 1u << i; wq[qoff++] = (uint16_t)(eb1 | i); }
+          mm = m0;
+          while (mm) { const uint32_t i = c2_top_bit(mm); mm ^= 1u << i; wq[qoff++] = (uint16_t)(eb0 | i); }
+        }
+      __syncwarp();
 
-      // ---- evaluation and output
-      if (queued && nW <= C2_ROUNDS * 32)
-        { // the usual case: every lane evaluates its (<= C2_ROUNDS) queue entries into registers first
-          uint32_t kl[C2_ROUNDS], kh[C2_ROUNDS], ent[C2_ROUNDS];
-          uint32_t okMask = 0, fMask = 0;
-#pragma unroll
-          for (int r = 0; r < C2_ROUNDS; ++r)
-            { kl[r] = 0; kh[r] = 0; ent[r] = 0;
-              if (r * 32 < nW)                               // warp-uniform
-                { const uint32_t q = r * 32 + lane;
-                  if (q < nW)
-                    { ent[r] = wq[q];
-                      const uint32_t src = ent[r] >> 5, bit = ent[r] & 31u;
-                      const uint2 x0 = *reinterpret_cast<const uint2 *>(S->half + 2 * src), x1 = *reinterpret_cast<const uint2 *>(S->half + 2 * src + 2);
-                      bool isF, ok;
-                      if (pow2) ok = mg_eval32_single<true>(E, H.shift, x0.y, x0.x, x1.y, x1.x, bit, &kl[r], &kh[r], &isF);
-                      else ok = mg_eval32_single<false>(E, H.shift, x0.y, x0.x, x1.y, x1.x, bit, &kl[r], &kh[r], &isF);
-                      if (ok) { okMask |= 1u << r; if (isF) fMask |= 1u << r; }
-                    }
-                }
-            }
-          if (SCATTER)
-            { nSelectedLocal += __popc(okMask);
-              uint32_t pos[C2_ROUNDS], region[C2_ROUNDS];
-#pragma unroll
-              for (int r = 0; r < C2_ROUNDS; ++r)
-                if ((okMask >> r) & 1u)
-                  { const uint64_t km = ((uint64_t)kh[r] << 32) | kl[r];
-                    region[r] = (uint32_t)((km * 0x9E3779B97F4A7C15ull) >> 32) >> regionShift;       // mg_slot_hash >> regionBits
-                    if (PEER) region[r] += mg_owner(km, P.nOwners) * P.nRegions;                      // bucket index = owner * R + region
-                    pos[r] = atomicAdd(&P.cursors[region[r]], 1u);
-                  }
-#pragma unroll
-              for (int r = 0; r < C2_ROUNDS; ++r)
-                if ((okMask >> r) & 1u)
-                  { const uint64_t km = ((uint64_t)kh[r] << 32) | kl[r];
-                    if (pos[r] < P.bucketCap)
-                      { uint64_t *bp = P.buckets + (uint64_t)region[r] * P.bucketCap + pos[r];
-                        if (P.keepBuckets) mg_st_keep(bp, km); else *bp = km;
-                      }
-                    else if (PEER)
-                      { const uint32_t ow = region[r] / P.nRegions;
-                        const uint32_t o = atomicAdd(&P.ownerCursor[ow], 1u);
-                        if (o < P.overflowCap) P.overflow[(uint64_t)ow * P.overflowCap + o] = km;
-                      }
-                    else
-                      { const uint32_t o = atomicAdd(&P.cursors[P.nRegions], 1u);
-                        if (o < P.overflowCap) P.overflow[o] = km;
-                      }
-                  }
+      // ---- evaluation and output, round by round (32 queue entries each).  Scatter: the store of a k-mer waits for the
+      // position its bucket atomic returns, so it is issued one round later (the last one after the loop): the L2 round
+      // trip hides behind the evaluation of the next entries instead of stalling the warp (ncu r02: 8 % of all stall
+      // samples sat on that compare)
+      uint32_t own0 = m0, own1 = m1;
+      uint32_t pKl = 0, pKh = 0, pRegion = 0, pPos = 0;
+      bool pOn = false;
+      for (uint32_t base = 0;; base += 32)
+        { uint32_t ent = 0;
+          bool have;
+          if (queued)
+            { if (base >= nW) break;
+              have = base + lane < nW;
+              if (have) ent = wq[base + lane];
             }
           else
-            { // list: one reservation per warp and tile
-              const uint32_t cs = __popc(okMask);
-              const uint32_t inc2 = mg_warp_incl_scan(cs);
-              const uint32_t total = __shfl_sync(0xffffffffu, inc2, 31);
-              unsigned long long wbase = 0;
-              if (lane == 0 && total) wbase = atomicAdd(P.count, (unsigned long long)total);
-              wbase = __shfl_sync(0xffffffffu, wbase, 0);
-              uint64_t dst = wbase + inc2 - cs;
-#pragma unroll
-              for (int r = 0; r < C2_ROUNDS; ++r)
-                if ((okMask >> r) & 1u)
-                  { if (dst < P.cap)
-                      { const uint64_t km = ((uint64_t)kh[r] << 32) | kl[r];
-                        P.outKmer[dst] = (P.strandBit && ((fMask >> r) & 1u)) ? (km | (1ull << 63)) : km;
-                        if (P.outPos) P.outPos[dst] = (uint32_t)(tileBase + ent[r]);   // ent = run*32 + window
-                      }
-                    ++dst;
-                  }
+            { // more candidates than the queue holds (d < 8, pathological sequence): every lane walks its own
+              have = (own0 | own1) != 0;
+              if (!__any_sync(0xffffffffu, have)) break;
+              if (own0) { const uint32_t i = __ffs(own0) - 1; own0 &= own0 - 1; ent = (run0 << 5) | i; }
+              else if (own1) { const uint32_t i = __ffs(own1) - 1; own1 &= own1 - 1; ent = ((run0 + 1) << 5) | i; }
             }
-        }
-      else
-        { // crowded warp: warp-aggregated reservations per round; per-lane loop when even the queue overflowed
-          uint32_t own0 = m0, own1 = m1;
-          for (uint32_t base = 0;; base += 32)
-            { uint32_t ent = 0;
-              bool have;
-              if (queued)
-                { if (base >= nW) break;
-                  have = base + lane < nW;
-                  if (have) ent = wq[base + lane];
+          uint32_t kl = 0, kh = 0;
+          bool isF = false, ok = false;
+          if (have)
+            { const uint32_t src = ent >> 5, bit = ent & 31u;
+              const uint2 x0 = *reinterpret_cast<const uint2 *>(S->half + 2 * src), x1 = *reinterpret_cast<const uint2 *>(S->half + 2 * src + 2);
+              if (SCAN == 1 && pow2) ok = mg_eval32_single<true>(E, H.shift, x0.y, x0.x, x1.y, x1.x, bit, &kl, &kh, &isF);
+              else ok = mg_eval32_single<false>(E, H.shift, x0.y, x0.x, x1.y, x1.x, bit, &kl, &kh, &isF);
+            }
+          if (SCATTER)
+            { if (pOn)                                       // the previous round's k-mer: its position has arrived by now
+                { const uint64_t km = ((uint64_t)pKh << 32) | pKl;
+                  if (pPos < P.bucketCap)
+                    { uint64_t *bp = P.buckets + (uint64_t)pRegion * P.bucketCap + pPos;
+                      if (P.keepBuckets) mg_st_keep(bp, km); else *bp = km;
+                    }
+                  else if (PEER)
+                    { const uint32_t ow = pRegion / P.nRegions;
+                      const uint32_t o = atomicAdd(&P.ownerCursor[ow], 1u);
+                      if (o < P.overflowCap) P.overflow[(uint64_t)ow * P.overflowCap + o] = km;
+                    }
+                  else
+                    { const uint32_t o = atomicAdd(&P.cursors[P.nRegions], 1u);
+                      if (o < P.overflowCap) P.overflow[o] = km;
+                    }
                 }
-              else
-                { have = (own0 | own1) != 0;
-                  if (!__any_sync(0xffffffffu, have)) break;
-                  if (own0) { const uint32_t i = __ffs(own0) - 1; own0 &= own0 - 1; ent = (run0 << 5) | i; }
-                  else if (own1) { const uint32_t i = __ffs(own1) - 1; own1 &= own1 - 1; ent = ((run0 + 1) << 5) | i; }
+              pOn = ok;
+              if (ok)
+                { ++nSelectedLocal;
+                  const uint64_t km = ((uint64_t)kh << 32) | kl;
+                  pRegion = (uint32_t)((km * 0x9E3779B97F4A7C15ull) >> 32) >> regionShift;            // mg_slot_hash >> regionBits
+                  if (PEER) pRegion += mg_owner(km, P.nOwners) * P.nRegions;                           // bucket index = owner * R + region
+                  pPos = atomicAdd(&P.cursors[pRegion], 1u);
+                  pKl = kl; pKh = kh;
                 }
-              uint32_t kl = 0, kh = 0;
-              bool isF = false, ok = false;
-              if (have)
-                { const uint32_t src = ent >> 5, bit = ent & 31u;
-                  const uint2 x0 = *reinterpret_cast<const uint2 *>(S->half + 2 * src), x1 = *reinterpret_cast<const uint2 *>(S->half + 2 * src + 2);
-                  ok = mg_eval32_single<false>(E, H.shift, x0.y, x0.x, x1.y, x1.x, bit, &kl, &kh, &isF);
-                }
-              uint64_t km = ((uint64_t)kh << 32) | kl;
+            }
+          else
+            { // list: one reservation per warp and round
               const uint32_t ballot = __ballot_sync(0xffffffffu, ok);
               if (!ballot) continue;
-              if (SCATTER)
-                { if (ok)
-                    { ++nSelectedLocal;
-                      uint32_t region = (uint32_t)((km * 0x9E3779B97F4A7C15ull) >> 32) >> regionShift;
-                      const uint32_t ow = PEER ? mg_owner(km, P.nOwners) : 0u;
-                      if (PEER) region += ow * P.nRegions;
-                      const uint32_t pos = atomicAdd(&P.cursors[region], 1u);
-                      if (pos < P.bucketCap) { uint64_t *bp = P.buckets + (uint64_t)region * P.bucketCap + pos; if (P.keepBuckets) mg_st_keep(bp, km); else *bp = km; }
-                      else if (PEER)
-                        { const uint32_t o = atomicAdd(&P.ownerCursor[ow], 1u);
-                          if (o < P.overflowCap) P.overflow[(uint64_t)ow * P.overflowCap + o] = km;
-                        }
-                      else
-                        { const uint32_t o = atomicAdd(&P.cursors[P.nRegions], 1u);
-                          if (o < P.overflowCap) P.overflow[o] = km;
-                        }
-                    }
-                  continue;
-                }
               unsigned long long wbase = 0;
               if (lane == 0) wbase = atomicAdd(P.count, (unsigned long long)__popc(ballot));
               wbase = __shfl_sync(0xffffffffu, wbase, 0);
               if (ok)
                 { const uint64_t dst = wbase + __popc(ballot & ((1u << lane) - 1u));
                   if (dst < P.cap)
-                    { if (P.strandBit && isF) km |= 1ull << 63;
+                    { uint64_t km = ((uint64_t)kh << 32) | kl;
+                      if (P.strandBit && isF) km |= 1ull << 63;
                       P.outKmer[dst] = km;
-                      if (P.outPos) P.outPos[dst] = (uint32_t)(tileBase + ent);
+                      if (P.outPos) P.outPos[dst] = (uint32_t)(tileBase + ent);   // ent = run*32 + window
                     }
                 }
+            }
+        }
+      if (SCATTER && pOn)
+        { const uint64_t km = ((uint64_t)pKh << 32) | pKl;
+          if (pPos < P.bucketCap)
+            { uint64_t *bp = P.buckets + (uint64_t)pRegion * P.bucketCap + pPos;
+              if (P.keepBuckets) mg_st_keep(bp, km); else *bp = km;
+            }
+          else if (PEER)
+            { const uint32_t ow = pRegion / P.nRegions;
+              const uint32_t o = atomicAdd(&P.ownerCursor[ow], 1u);
+              if (o < P.overflowCap) P.overflow[(uint64_t)ow * P.overflowCap + o] = km;
+            }
+          else
+            { const uint32_t o = atomicAdd(&P.cursors[P.nRegions], 1u);
+              if (o < P.overflowCap) P.overflow[o] = km;
             }
         }
       __syncwarp();                                         // the queue and the packed tile are free again
@@ -380,7 +347,7 @@ static int c2_dispatch_io(const SelectParams &P, bool ends, cudaStream_t st)
 template <int OUT>
 static int c2_dispatch_scan(const SelectParams &P, int scan, bool ends, cudaStream_t st)
 {
-  if (scan == 0) return c2_dispatch_io<0, 0, OUT>(P, ends, st);
+  if (scan == 0) return P.H.tz == 0 ? c2_dispatch_io<0, 1, OUT>(P, ends, st) : c2_dispatch_io<0, 0, OUT>(P, ends, st);
   return P.H.k == 31 ? c2_dispatch_io<1, 31, OUT>(P, ends, st) : c2_dispatch_io<1, 30, OUT>(P, ends, st);
 }
 

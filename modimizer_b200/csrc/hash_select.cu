@@ -400,6 +400,9 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, LUTK ? 3 : 2) hash_count_kerne
             }
           S->words[run0] = w0; S->words[run0 + 1] = w1;
           if (lane == 0) S->words[MG_WT_RUNS] = wx;
+          // the staged flags must sit in registers before the warp barrier below frees the staging buffers for the next
+          // bulk copy: a load the compiler sinks past the copy's issue reads the NEXT tile's flags (seen in hash_count2.cu)
+          asm volatile("" : "+r"(e0), "+r"(e1), "+r"(e2) :: "memory");
         }
       else
         { // the ragged end of a raw batch: guarded loads
