@@ -82,6 +82,9 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, SCAN ? 3 : 2) hash_count2_kern
   const uint64_t nBulk = P.nBases >= MG_WS_RAW_BYTES ? (P.nBases - MG_WS_RAW_BYTES) / MG_WT_BASES + 1 : 0;
   uint32_t nSelectedLocal = 0;
   uint32_t phase = 0;
+  // scatter: the k-mer whose bucket position is still on its way (stored one round later, also across tiles)
+  uint32_t pKl = 0, pKh = 0, pRegion = 0, pPos = 0;
+  bool pOn = false;
 
   if (lane == 0)
     { mg_mbar_init(&S->bar, 1);
@@ -160,9 +163,11 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, SCAN ? 3 : 2) hash_count2_kern
               const MgRun32 Q = mg_run32(RR);
               uint32_t mh = 0;
 #pragma unroll
-              for (int i = 0; i < MG_RUN; ++i)
-                { const bool ok = mg_selected32<LUTK == 1>(E, Q, i);
-                  asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p or.b32 %0, %0, %2;\n\t}" : "+r"(mh) : "r"((uint32_t)ok), "r"(1u << i));
+              for (int i = 0; i < MG_RUN / 2; ++i)             // windows i and i + 16 share their middle funnel shifts
+                { bool s0, s16;
+                  mg_selected32_pair<LUTK == 1>(E, Q, i, &s0, &s16);
+                  asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p or.b32 %0, %0, %2;\n\t}" : "+r"(mh) : "r"((uint32_t)s0), "r"(1u << i));
+                  asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p or.b32 %0, %0, %2;\n\t}" : "+r"(mh) : "r"((uint32_t)s16), "r"(1u << (i + 16)));
                 }
               if (h == 0) m0 = mh; else m1 = mh;
               wa = wb; wb = wc;
@@ -218,8 +223,6 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, SCAN ? 3 : 2) hash_count2_kern
       // trip hides behind the evaluation of the next entries instead of stalling the warp (ncu r02: 8 % of all stall
       // samples sat on that compare)
       uint32_t own0 = m0, own1 = m1;
-      uint32_t pKl = 0, pKh = 0, pRegion = 0, pPos = 0;
-      bool pOn = false;
       for (uint32_t base = 0;; base += 32)
         { uint32_t ent = 0;
           bool have;
@@ -244,7 +247,8 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, SCAN ? 3 : 2) hash_count2_kern
               else ok = mg_eval32_single<false>(E, H.shift, x0.y, x0.x, x1.y, x1.x, bit, &kl, &kh, &isF);
             }
           if (SCATTER)
-            { if (pOn)                                       // the previous round's k-mer: its position has arrived by now
+            { asm volatile("" : "+r"(pPos));                 // (keeps the compiler from testing the position before the evaluation above)
+              if (pOn)                                       // the previous round's k-mer: its position has arrived by now
                 { const uint64_t km = ((uint64_t)pKh << 32) | pKl;
                   if (pPos < P.bucketCap)
                     { uint64_t *bp = P.buckets + (uint64_t)pRegion * P.bucketCap + pPos;
@@ -288,23 +292,24 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, SCAN ? 3 : 2) hash_count2_kern
                 }
             }
         }
-      if (SCATTER && pOn)
-        { const uint64_t km = ((uint64_t)pKh << 32) | pKl;
-          if (pPos < P.bucketCap)
-            { uint64_t *bp = P.buckets + (uint64_t)pRegion * P.bucketCap + pPos;
-              if (P.keepBuckets) mg_st_keep(bp, km); else *bp = km;
-            }
-          else if (PEER)
-            { const uint32_t ow = pRegion / P.nRegions;
-              const uint32_t o = atomicAdd(&P.ownerCursor[ow], 1u);
-              if (o < P.overflowCap) P.overflow[(uint64_t)ow * P.overflowCap + o] = km;
-            }
-          else
-            { const uint32_t o = atomicAdd(&P.cursors[P.nRegions], 1u);
-              if (o < P.overflowCap) P.overflow[o] = km;
-            }
-        }
       __syncwarp();                                         // the queue and the packed tile are free again
+    }
+  // the last pending bucket store
+  if (SCATTER && pOn)
+    { const uint64_t km = ((uint64_t)pKh << 32) | pKl;
+      if (pPos < P.bucketCap)
+        { uint64_t *bp = P.buckets + (uint64_t)pRegion * P.bucketCap + pPos;
+          if (P.keepBuckets) mg_st_keep(bp, km); else *bp = km;
+        }
+      else if (PEER)
+        { const uint32_t ow = pRegion / P.nRegions;
+          const uint32_t o = atomicAdd(&P.ownerCursor[ow], 1u);
+          if (o < P.overflowCap) P.overflow[(uint64_t)ow * P.overflowCap + o] = km;
+        }
+      else
+        { const uint32_t o = atomicAdd(&P.cursors[P.nRegions], 1u);
+          if (o < P.overflowCap) P.overflow[o] = km;
+        }
     }
   if (SCATTER)
     { nSelectedLocal = mg_warp_sum(nSelectedLocal);

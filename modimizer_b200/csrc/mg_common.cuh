@@ -277,6 +277,40 @@ MGHD bool mg_selected32(const MgEval32 &E, const MgRun32 &Q, uint32_t i)
   return ok;
 }
 
+// The same decision for TWO windows at once, i and i + 16 (i < 16), as a SUPERSET of the selected windows (the count
+// kernel re-evaluates every flagged window exactly, mg_eval32_single):
+//  - windows i and i + 16 lie exactly one 32-bit word apart, so the middle funnel shift of each strand serves both
+//    (the low word of one window is the unmasked high word of the other): three shifts per strand for two windows;
+//  - the exact-division test compares the HIGH product word only (q <= lim iff qh < limHi, or qh == limHi and
+//    ql <= limLo: qh <= limHi can only add windows), which needs the high half of ONE partial product instead of a
+//    64-bit compare.
+template <bool ODD>
+MGHD void mg_selected32_pair(const MgEval32 &E, const MgRun32 &Q, uint32_t i, bool *sel0, bool *sel16)
+{
+  const uint32_t s = 2 * i;                                   // 0 .. 30
+  const uint32_t fA = mg_fl32(Q.y[0], Q.y[1], s), fB = mg_fl32(Q.y[1], Q.y[2], s), fC = mg_fl32(Q.y[2], Q.y[3], s);
+  const uint32_t rA = mg_fr32(Q.r[0], Q.r[1], s), rB = mg_fr32(Q.r[1], Q.r[2], s), rC = mg_fr32(Q.r[2], Q.r[3], s);
+  // window i: forward (fB, fC & m), reverse (rA, rB & m); window i + 16: forward (fA, fB & m), reverse (rB, rC & m)
+  for (int h = 0; h < 2; ++h)
+    { const uint32_t fl = h ? fA : fB, fh = (h ? fB : fC) & E.maskHi;
+      const uint32_t rl = h ? rB : rA, rh = (h ? rC : rB) & E.maskHi;
+      uint32_t pfl, pfh, prl, prh;
+      mg_mul64lo(fl, fh, E.fLo, E.fHi, &pfl, &pfh);
+      mg_mul64lo(rl, rh, E.fLo, E.fHi, &prl, &prh);
+      const uint64_t pf = ((uint64_t)pfh << 32) | pfl, pr = ((uint64_t)prh << 32) | prl;
+      const uint64_t pm = (pf < pr) ? pf : pr;                // the smaller product carries the smaller hash (see mg_selected32)
+      const uint32_t ml = (uint32_t)pm & E.keepLo, mh = (uint32_t)(pm >> 32);
+#if defined(__CUDA_ARCH__)
+      const uint32_t qh = __umulhi(ml, E.invLo) + ml * E.invHi + mh * E.invLo;
+#else
+      const uint32_t qh = (uint32_t)(((uint64_t)ml * E.invLo) >> 32) + ml * E.invHi + mh * E.invLo;
+#endif
+      bool ok = qh <= E.limHi;
+      if (!ODD) ok = ok & (((ml & E.lowLo) | (mh & E.lowHi)) == 0u);
+      if (h) *sel16 = ok; else *sel0 = ok;
+    }
+}
+
 // The same for ONE window given the run's two packed words (phase 3 of the
 // kernel, where only the few queued windows are evaluated): the forward k-mer
 // is a bit field of w0:w1 and the reverse complement is computed from the k-mer

@@ -8,7 +8,11 @@
 #include <vector>
 #include "../../modimizer_b200/csrc/mg_common.cuh"
 
+static long long g_superset_extra = 0;        // windows the paired superset scan flags beyond the exact ones
+
 extern "C" {
+
+long long hm_superset_extra(void) { return g_superset_extra; }
 
 void hm_khasher(int k, int d, uint64_t factor1, uint64_t out[8])
 {
@@ -82,6 +86,17 @@ int64_t hm_select(int k, int d, uint64_t factor1, const uint8_t *bytes, uint64_t
                   if (H.tz == 0 && mg_selected32<true>(E, Q, i)) s32b |= 1u << i;
                 }
               if (s32 != sel || (H.tz == 0 && s32b != sel)) return -3000000 - (int64_t)p0;
+              // the paired superset form of the second-generation kernel: never misses a selected window, and what it
+              // adds must be rare (the high-word comparison of the exact-division test)
+              uint32_t sp = 0, spb = 0;
+              for (uint32_t i = 0; i < 16; ++i)
+                { bool a, b;
+                  mg_selected32_pair<false>(E, Q, i, &a, &b);
+                  sp |= (a ? 1u : 0u) << i; sp |= (b ? 1u : 0u) << (i + 16);
+                  if (H.tz == 0) { mg_selected32_pair<true>(E, Q, i, &a, &b); spb |= (a ? 1u : 0u) << i; spb |= (b ? 1u : 0u) << (i + 16); }
+                }
+              if ((sp & sel) != sel || (H.tz == 0 && (spb & sel) != sel)) return -6000000 - (int64_t)p0;
+              if (sp != sel || (H.tz == 0 && spb != sel)) ++g_superset_extra;
             }
           sel &= usable;
         }
