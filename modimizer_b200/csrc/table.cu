@@ -228,9 +228,13 @@ __device__ __forceinline__ unsigned long long mg_ld_peer(const uint64_t *p)
 // latency (local source) sits on the critical path.  Work split: a warp owns (source, part) units - with
 // nSrc <= 8 sources every bucket is read by 8 / nSrc warps, lanes on consecutive k-mers (coalesced
 // 256-byte requests over NVLink), no search for the source of an element.  PEER: loads bypass this SM's L1.
-#define MG_PIPE_PRELOAD 3                                       // k-mers per lane and unit kept in registers
-template <bool FRESH, bool PEER, int MG_PIPE_UNITS>             // units per warp: 1 for nSrc <= 8, 2 up to 16
-__global__ void __launch_bounds__(256, 5) region_build_pipe_kernel(MgSlot *slots, uint32_t slotBits, const MgPeerSrc src,
+// Geometry: NW warps per block, PRE k-mers per lane and unit kept in registers.  A bucket part that holds more than 32 PRE
+// k-mers makes its warp fetch the rest with the latency exposed, and the block barrier makes the whole block wait for it:
+// with 8 warps a part holds 740 / 8 = 92 k-mers on average (the genome build at load 0.36), so three preloads (96) miss
+// for every third part; 16 warps halve the parts (46 +- 7 against 64) - measured (r02): 0.63 ms against 0.53 ms with 8
+// warps and 5 blocks per SM on the local genome build, and four preloads spill: the 8-warp form stays the default.
+template <bool FRESH, bool PEER, int MG_PIPE_UNITS, int NW = 8, int MG_PIPE_PRELOAD = 3>   // units per warp: 1 for nSrc <= NW, 2 up to 2 NW
+__global__ void __launch_bounds__(NW * 32, NW == 16 ? 3 : 5) region_build_pipe_kernel(MgSlot *slots, uint32_t slotBits, const MgPeerSrc src,
                                                                 const uint32_t *__restrict__ cursors, uint32_t cap, uint32_t nSrc,
                                                                 uint64_t srcStride, uint32_t nRegions,
                                                                 unsigned long long *entries, uint32_t *error,
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__(256, 5) region_build_pipe_kernel(MgSlot *slots
       for (int i = 0; i < MODGPU_MAX_PEERS; ++i) sSrc[i] = src.p[i];
     }
   __syncthreads();
-  const uint32_t parts = nSrc >= 8 ? 1u : 8u / nSrc;            // warps per bucket
+  const uint32_t parts = nSrc >= NW ? 1u : (uint32_t)NW / nSrc;   // warps per bucket
   const uint32_t nUnits = nSrc * parts;
   // this warp's units: u = warp, warp + 8
   const uint64_t *uBase[MG_PIPE_UNITS];
@@ -262,7 +266,7 @@ __global__ void __launch_bounds__(256, 5) region_build_pipe_kernel(MgSlot *slots
   bool uOn[MG_PIPE_UNITS];
 #pragma unroll
   for (int q = 0; q < MG_PIPE_UNITS; ++q)
-    { const uint32_t u = warp + 8 * q;
+    { const uint32_t u = warp + NW * q;
       uOn[q] = u < nUnits;
       const uint32_t sIdx = uOn[q] ? u % nSrc : 0u;
       uBase[q] = sSrc[sIdx];
@@ -335,8 +339,8 @@ __global__ void __launch_bounds__(256, 5) region_build_pipe_kernel(MgSlot *slots
         { uint4 e;
           e.x = 0xFFFFFFFFu; e.y = 0xFFFFFFFFu; e.z = 0u; e.w = MG_AUX_FRESH;
 #pragma unroll
-          for (int i = 0; i < MG_REGION_SLOTS / 256; ++i)
-            sR[i * 256 + tid] = FRESH ? e : __ldcs(g + i * 256 + tid);
+          for (int i = 0; i < MG_REGION_SLOTS / (NW * 32); ++i)
+            sR[i * (NW * 32) + tid] = FRESH ? e : __ldcs(g + i * (NW * 32) + tid);
         }
       // the next region's k-mers: in flight while this one is built
       unsigned long long nxt[MG_PIPE_UNITS][MG_PIPE_PRELOAD];
@@ -366,7 +370,7 @@ __global__ void __launch_bounds__(256, 5) region_build_pipe_kernel(MgSlot *slots
       if (any)
         {
 #pragma unroll
-          for (int i = 0; i < MG_REGION_SLOTS / 256; ++i) __stcs(g + i * 256 + tid, sR[i * 256 + tid]);
+          for (int i = 0; i < MG_REGION_SLOTS / (NW * 32); ++i) __stcs(g + i * (NW * 32) + tid, sR[i * (NW * 32) + tid]);
         }
 #pragma unroll
       for (int q = 0; q < MG_PIPE_UNITS; ++q)
@@ -737,23 +741,23 @@ int mg_table_bulk_finish(ModgpuTable *t, const MgBulk *b, cudaStream_t st)
     { // default: the persistent, software-pipelined build (the kernel of the peer-memory exchange) on the one local
       // source.  Same speed as the one-block-per-region kernel when that one is at its best (0.53-0.55 ms), but it
       // stays there: the block-per-region kernel was measured at 1.1 ms on some boxes / days with nothing else changed
-      static int blocksPerSm = 0;
+      static int blocksPerSm = 0, nw = 0;
       if (!blocksPerSm)
-        { MG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, region_build_pipe_kernel<true, false, 1>, 256, 0));
+        { const char *v = getenv("MODGPU_BUILD_NW");
+          nw = (v && atoi(v) == 16) ? 16 : 8;     // 16 warps measured slower (0.63 against 0.53 ms on the local genome build): kept for A/B
+          if (nw == 16) MG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, region_build_pipe_kernel<true, false, 1, 16, 2>, 512, 0));
+          else MG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, region_build_pipe_kernel<true, false, 1>, 256, 0));
           if (blocksPerSm < 1) blocksPerSm = 1;
         }
       uint32_t grid = (uint32_t)mg_num_sms() * (uint32_t)blocksPerSm;
       if (grid > b->nRegions) grid = b->nRegions;
       MgPeerSrc src;
       for (uint32_t s2 = 0; s2 < MODGPU_MAX_PEERS; ++s2) src.p[s2] = b->buckets;
-      if (t->clearPending)
-        { region_build_pipe_kernel<true, false, 1><<<grid, 256, 0, st>>>(t->slots, t->slotBits, src, b->cursors, b->cap, 1, b->nRegions, b->nRegions,
-                                                                        t->dEntries, t->dError, b->cursors + b->nRegions, guardLimit);
-          t->clearPending = false;
-        }
-      else
-        region_build_pipe_kernel<false, false, 1><<<grid, 256, 0, st>>>(t->slots, t->slotBits, src, b->cursors, b->cap, 1, b->nRegions, b->nRegions,
-                                                                       t->dEntries, t->dError, b->cursors + b->nRegions, guardLimit);
+#define MG_LOCAL_LAUNCH(FR) do { if (nw == 16) region_build_pipe_kernel<FR, false, 1, 16, 2><<<grid, 512, 0, st>>>(t->slots, t->slotBits, src, b->cursors, b->cap, 1, b->nRegions, b->nRegions, t->dEntries, t->dError, b->cursors + b->nRegions, guardLimit); \
+                                 else region_build_pipe_kernel<FR, false, 1><<<grid, 256, 0, st>>>(t->slots, t->slotBits, src, b->cursors, b->cap, 1, b->nRegions, b->nRegions, t->dEntries, t->dError, b->cursors + b->nRegions, guardLimit); } while (0)
+      if (t->clearPending) { MG_LOCAL_LAUNCH(true); t->clearPending = false; }
+      else MG_LOCAL_LAUNCH(false);
+#undef MG_LOCAL_LAUNCH
     }
   else
     {
@@ -898,21 +902,24 @@ int mg_table_build_from_peers_ex(ModgpuTable *t, const uint64_t *const *d_bucket
   if (!cursorStride) cursorStride = nRegions;
   MgPeerSrc src;
   for (uint32_t s = 0; s < MODGPU_MAX_PEERS; ++s) src.p[s] = d_buckets[s < nSrc ? s : 0];
-  static int blocksPerSm = 0;
+  static int blocksPerSm = 0, nw = 0;
   if (!blocksPerSm)
-    { MG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, region_build_pipe_kernel<true, true, 1>, 256, 0));
+    { const char *v = getenv("MODGPU_BUILD_NW");
+      nw = (v && atoi(v) == 16) ? 16 : 8;     // 16 warps measured slower (0.63 against 0.53 ms on the local genome build): kept for A/B
+      if (nw == 16) MG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, region_build_pipe_kernel<true, true, 1, 16, 2>, 512, 0));
+      else MG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, region_build_pipe_kernel<true, true, 1>, 256, 0));
       if (blocksPerSm < 1) blocksPerSm = 1;
     }
   uint32_t grid = (uint32_t)mg_num_sms() * (uint32_t)blocksPerSm;
   if (grid > nRegions) grid = nRegions;
-#define MG_PIPE_LAUNCH(FR, UN) region_build_pipe_kernel<FR, true, UN><<<grid, 256, 0, st>>>(t->slots, t->slotBits, src, d_cursors, cap, nSrc, cursorStride, nRegions, t->dEntries, t->dError, d_guard, 0u, 1)
-  if (t->clearPending)
-    { if (nSrc <= 8) MG_PIPE_LAUNCH(true, 1); else MG_PIPE_LAUNCH(true, 2);
-      t->clearPending = false;
-    }
-  else
-    { if (nSrc <= 8) MG_PIPE_LAUNCH(false, 1); else MG_PIPE_LAUNCH(false, 2); }
+#define MG_PIPE_ARGS t->slots, t->slotBits, src, d_cursors, cap, nSrc, cursorStride, nRegions, t->dEntries, t->dError, d_guard, 0u, 1
+#define MG_PIPE_LAUNCH(FR) do { if (nw == 16) region_build_pipe_kernel<FR, true, 1, 16, 2><<<grid, 512, 0, st>>>(MG_PIPE_ARGS); \
+                                else if (nSrc <= 8) region_build_pipe_kernel<FR, true, 1><<<grid, 256, 0, st>>>(MG_PIPE_ARGS); \
+                                else region_build_pipe_kernel<FR, true, 2><<<grid, 256, 0, st>>>(MG_PIPE_ARGS); } while (0)
+  if (t->clearPending) { MG_PIPE_LAUNCH(true); t->clearPending = false; }
+  else MG_PIPE_LAUNCH(false);
 #undef MG_PIPE_LAUNCH
+#undef MG_PIPE_ARGS
   MG_LAUNCH_CHECK("region_build_peer");
   // the (rare) k-mers that did not fit their bucket at the sender: direct inserts reading the peer's segment
   for (uint32_t s = 0; d_overflow && s < nSrc; ++s)
