@@ -383,6 +383,112 @@ __global__ void __launch_bounds__(NW * 32, NW == 16 ? 3 : 5) region_build_pipe_k
   if (mg_lane() == 0 && fresh) atomicAdd(entries, (unsigned long long)fresh);
 }
 
+// The peer build with the transfer on the TMA engine: the filled part of every source bucket of a region comes over
+// NVLink as ONE bulk copy (cp.async.bulk from the peer-mapped pointer into a shared-memory ring, two regions ahead,
+// completion on an mbarrier) instead of 8-byte loads of the lanes - a few large NVLink reads per region instead of many
+// 256-byte ones, no registers tied up by k-mers in flight, and two regions of prefetch distance.  Warp 0 issues the
+// copies for region i+2 when region i has been consumed (it reads the fill counts then: local memory, behind the
+// write-back of the other threads); a warp inserts one (source, part) unit from the ring.
+template <bool FRESH>
+__global__ void __launch_bounds__(256, 4) region_build_tma_kernel(MgSlot *slots, uint32_t slotBits, const MgPeerSrc src,
+                                                                  const uint32_t *__restrict__ cursors, uint32_t cap, uint32_t nSrc,
+                                                                  uint64_t srcStride, uint32_t nRegions, unsigned long long *entries,
+                                                                  uint32_t *error, const uint32_t *__restrict__ guard)
+{
+  __shared__ uint4 sR[MG_REGION_SLOTS];
+  __shared__ __align__(8) uint64_t sBar[2];
+  __shared__ uint32_t sCnt[2][MODGPU_MAX_PEERS];
+  extern __shared__ __align__(128) uint8_t sDynRing[];                 // 2 stages x nSrc x cap k-mers
+  const bool skip = guard && __ldg(guard) > 0u;
+  if (skip && !FRESH) return;
+  MgSlot *sS = reinterpret_cast<MgSlot *>(sR);
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint64_t *ring = reinterpret_cast<uint64_t *>(sDynRing);
+  const uint32_t stageWords = nSrc * cap;
+  if (blockIdx.x >= nRegions) return;
+
+  auto issue = [&](uint32_t region, uint32_t stage) {                  // warp 0: lane s serves source s
+    if (lane < nSrc)
+      { uint32_t c = 0;
+        if (region < nRegions && !skip) { c = __ldg(cursors + lane * srcStride + region); if (c > cap) c = cap; }
+        sCnt[stage][lane] = c;
+        const uint32_t bytes = (c * 8u + 15u) & ~15u;                  // (cap is even: a whole bucket is a multiple of 16 bytes)
+        if (bytes)
+          mg_tma_load_1d(ring + (size_t)stage * stageWords + (size_t)lane * cap, src.p[lane] + (uint64_t)region * cap, bytes, &sBar[stage]);
+        mg_mbar_expect_tx(&sBar[stage], bytes);                        // one arrival per source, with its bytes
+      }
+  };
+
+  if (tid == 0)
+    { mg_mbar_init(&sBar[0], nSrc); mg_mbar_init(&sBar[1], nSrc);
+      mg_fence_barrier_init();
+      mg_fence_proxy_async();
+    }
+  __syncthreads();
+  if (warp == 0) { issue(blockIdx.x, 0); issue(blockIdx.x + gridDim.x, 1); }
+  const uint32_t parts = nSrc >= 8 ? 1u : 8u / nSrc;                    // warps per bucket
+  const uint32_t nUnits = nSrc * parts;
+  uint32_t fresh = 0;
+  uint32_t it = 0;
+  for (uint32_t region = blockIdx.x; region < nRegions; region += gridDim.x, ++it)
+    { const uint32_t stage = it & 1;
+      uint4 *g = reinterpret_cast<uint4 *>(slots) + (uint64_t)region * MG_REGION_SLOTS;
+      mg_mbar_wait(&sBar[stage], (it >> 1) & 1);                       // this region's k-mers have landed (and sCnt is two barriers old)
+      bool any = FRESH;
+      if (!FRESH)
+        { uint32_t c = 0;
+          for (uint32_t s = 0; s < nSrc; ++s) c |= sCnt[stage][s];
+          any = c != 0;                                                // block-uniform: nothing to add leaves the region alone
+        }
+      if (any)
+        { uint4 e;
+          e.x = 0xFFFFFFFFu; e.y = 0xFFFFFFFFu; e.z = 0u; e.w = MG_AUX_FRESH;
+#pragma unroll
+          for (int i = 0; i < MG_REGION_SLOTS / 256; ++i)
+            sR[i * 256 + tid] = FRESH ? e : __ldcs(g + i * 256 + tid);
+        }
+      __syncthreads();                                                 // the region is initialised
+      if (any)
+        for (uint32_t u = warp; u < nUnits; u += 8)
+          { const uint32_t s = u % nSrc, part = u / nSrc, cnt = sCnt[stage][s];
+            const uint64_t *b = ring + (size_t)stage * stageWords + (size_t)s * cap;
+            for (uint32_t j = part * 32 + lane; j < cnt; j += parts * 32)
+              { const unsigned long long key = b[j] & 0x3FFFFFFFFFFFFFFFull;
+                uint32_t sl = (uint32_t)mg_slot_hash(key, slotBits) & (MG_REGION_SLOTS - 1);
+                uint32_t probes = 0;
+#pragma unroll 1
+                for (; probes < MG_REGION_SLOTS; ++probes, sl = (sl + 1) & (MG_REGION_SLOTS - 1))
+                  { unsigned long long *kp = reinterpret_cast<unsigned long long *>(&sS[sl].key);
+                    if (FRESH)
+                      { const unsigned long long old = atomicCAS(kp, MG_EMPTY, key);
+                        if (old == MG_EMPTY) { ++fresh; break; }
+                        if (old == key) break;
+                        continue;
+                      }
+                    unsigned long long cu = *reinterpret_cast<volatile unsigned long long *>(kp);
+                    if (cu == key) break;
+                    if (cu == MG_EMPTY)
+                      { unsigned long long old = atomicCAS(kp, MG_EMPTY, key);
+                        if (old == MG_EMPTY) { ++fresh; break; }
+                        if (old == key) break;
+                      }
+                  }
+                if (probes == MG_REGION_SLOTS) { atomicExch(error, 1u); continue; }
+                atomicAdd(&sS[sl].count, 1u);
+              }
+          }
+      __syncthreads();                                                 // the region is complete, the ring stage consumed
+      if (warp == 0) issue(region + 2 * gridDim.x, stage);             // two regions ahead, behind the write-back below
+      if (any)
+        {
+#pragma unroll
+          for (int i = 0; i < MG_REGION_SLOTS / 256; ++i) __stcs(g + i * 256 + tid, sR[i * 256 + tid]);
+        }
+    }
+  fresh = mg_warp_sum(fresh);
+  if (mg_lane() == 0 && fresh) atomicAdd(entries, (unsigned long long)fresh);
+}
+
 template <bool FRESH, int PRELOAD>
 __global__ void __launch_bounds__(256) region_build_kernel(MgSlot *slots, uint32_t slotBits, const uint64_t *__restrict__ buckets,
                                                               const uint32_t *__restrict__ cursors, uint32_t cap,
@@ -916,7 +1022,29 @@ int mg_table_build_from_peers_ex(ModgpuTable *t, const uint64_t *const *d_bucket
 #define MG_PIPE_LAUNCH(FR) do { if (nw == 16) region_build_pipe_kernel<FR, true, 1, 16, 2><<<grid, 512, 0, st>>>(MG_PIPE_ARGS); \
                                 else if (nSrc <= 8) region_build_pipe_kernel<FR, true, 1><<<grid, 256, 0, st>>>(MG_PIPE_ARGS); \
                                 else region_build_pipe_kernel<FR, true, 2><<<grid, 256, 0, st>>>(MG_PIPE_ARGS); } while (0)
-  if (t->clearPending) { MG_PIPE_LAUNCH(true); t->clearPending = false; }
+  static int useTma = -1, tmaBlocks = 0;
+  if (useTma < 0) { const char *v = getenv("MODGPU_PEER_TMA"); useTma = v ? atoi(v) : 1; }
+  const size_t ringBytes = 2 * (size_t)nSrc * cap * 8;
+  if (useTma && nSrc >= 2 && nSrc <= 8 && ringBytes <= 96 * 1024)
+    { // the transfer on the TMA engine (bulk copies from the peers into a shared-memory ring)
+      static size_t ringSet = 0;
+      if (ringBytes > ringSet)
+        { MG_CUDA(cudaFuncSetAttribute(region_build_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ringBytes));
+          MG_CUDA(cudaFuncSetAttribute(region_build_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ringBytes));
+          MG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tmaBlocks, region_build_tma_kernel<true>, 256, ringBytes));
+          if (tmaBlocks < 1) tmaBlocks = 1;
+          ringSet = ringBytes;
+        }
+      uint32_t tgrid = (uint32_t)mg_num_sms() * (uint32_t)tmaBlocks;
+      if (tgrid > nRegions) tgrid = nRegions;
+      if (t->clearPending)
+        { region_build_tma_kernel<true><<<tgrid, 256, ringBytes, st>>>(t->slots, t->slotBits, src, d_cursors, cap, nSrc, cursorStride, nRegions, t->dEntries, t->dError, d_guard);
+          t->clearPending = false;
+        }
+      else
+        region_build_tma_kernel<false><<<tgrid, 256, ringBytes, st>>>(t->slots, t->slotBits, src, d_cursors, cap, nSrc, cursorStride, nRegions, t->dEntries, t->dError, d_guard);
+    }
+  else if (t->clearPending) { MG_PIPE_LAUNCH(true); t->clearPending = false; }
   else MG_PIPE_LAUNCH(false);
 #undef MG_PIPE_LAUNCH
 #undef MG_PIPE_ARGS
