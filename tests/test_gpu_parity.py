@@ -905,11 +905,39 @@ def _sharded_worker(rank, world, port, tmpdir):
     for _ in range(4):
         sm.add_device(d_b.data_ptr(), d_o.data_ptr(), per, len(data))
     assert sm.synchronize() == 4 * n1
+    # a skewed group is transactional: rank 0 adds poly-A (every window selected, one k-mer: bucket and overflow
+    # segment run over), rank 1 its normal chunk - synchronize() raises on BOTH ranks and NOTHING was applied on either;
+    # after set_robust() the same group goes through
+    skew_ok = True
+    if p2p:
+        from modimizer_b200._lib import ModgpuError
+        sm.set_accumulate(1)
+        skew = np.zeros(len(data), np.uint8)
+        d_s = torch.from_numpy(skew).cuda(); d_so = torch.tensor([0, len(skew)], dtype=torch.int64).cuda()
+        before = (sm.local.max, sm.histogram().copy())
+        def group():
+            if rank == 0:
+                sm.add_device(d_s.data_ptr(), d_so.data_ptr(), 1, len(skew))
+            else:
+                sm.add_device(d_b.data_ptr(), d_o.data_ptr(), per, len(data))
+        group()
+        try:
+            sm.synchronize()
+            skew_ok = False                                   # must not pass
+        except ModgpuError:
+            pass
+        skew_ok = skew_ok and sm.local.max == before[0] and np.array_equal(sm.histogram(), before[1])
+        sm.set_robust(True)
+        group()
+        sm.synchronize()
+        flag = torch.tensor([1 if skew_ok else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        skew_ok = bool(flag.item())
     v, d, i = sm.gather_sorted_dump()
     h = sm.histogram()
     gmax = sm.global_max()
     if rank == 0:
-        np.savez(os.path.join(tmpdir, "sharded.npz"), v=v, d=d, h=h, gmax=gmax, sel=n1, p2p=p2p)
+        np.savez(os.path.join(tmpdir, "sharded.npz"), v=v, d=d, h=h, gmax=gmax, sel=n1, p2p=p2p, skew_ok=skew_ok)
     sm.close()
     dist.destroy_process_group()
 
@@ -931,6 +959,9 @@ def test_sharded_modset_two_gpus(mg, torch_cuda, orc, tmp_path):
     assert bool(r["p2p"]), "the peer-memory exchange fell back to NCCL"
     for _ in range(9):                                        # every rank added its chunk nine times
         orc.modset_add(oms, data, offs)
+    assert bool(r["skew_ok"]), "a skewed group was not skipped on every rank with the tables untouched"
+    orc.modset_add(oms, np.zeros(300 * 5000, np.uint8), np.array([0, 300 * 5000], np.uint64))      # rank 0's poly-A batch
+    orc.modset_add(oms, data[300 * 5000:], offs[:301])                                             # rank 1's chunk of that group
     ov, od, _ = orc.modset_sorted(oms)
     assert np.array_equal(r["v"], ov) and np.array_equal(r["d"], od)
     assert np.array_equal(r["h"], orc.modset_hist(oms)) and int(r["gmax"]) == len(ov)
