@@ -68,10 +68,10 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, SCAN ? 3 : 2) hash_count2_kern
 
   const MgKHasher &H = P.H;
   const uint32_t tid = threadIdx.x, lane = tid & 31;
-  const MgEval32 E = mg_eval32_prepare(H);
+  const MgEval32 &E = P.E;                                 // prepared on the host: constant-bank operands, nothing to rebuild per round
   const bool pow2 = H.oddInv == 1;                         // kernel-uniform: no odd-part test
   // region of a k-mer = the top (slotBits - regionBits) bits of its slot hash = one shift of the high product word
-  const uint32_t regionShift = 32u - (P.slotBits - P.regionBits);
+  const uint32_t regionShift = P.regionShift;
   // tile schedule (as in the first generation): chunks of MG_CNT_CHUNK consecutive warp tiles, the first by warp index,
   // the following ones from an atomic ticket requested a whole chunk ahead
   const uint32_t nWarps = gridDim.x * MG_CNT_WARPS;
@@ -218,10 +218,9 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, SCAN ? 3 : 2) hash_count2_kern
         }
       __syncwarp();
 
-      // ---- evaluation and output, round by round (32 queue entries each).  Scatter: the store of a k-mer waits for the
-      // position its bucket atomic returns, so it is issued one round later (the last one after the loop): the L2 round
-      // trip hides behind the evaluation of the next entries instead of stalling the warp (ncu r02: 8 % of all stall
-      // samples sat on that compare)
+      // ---- evaluation and output, round by round (32 queue entries each).  Scatter: a selected k-mer is carried into the
+      // next round (also across tiles; the last one is placed after the tile loop), where its bucket atomic is issued
+      // before and its store behind that round's evaluation
       uint32_t own0 = m0, own1 = m1;
       for (uint32_t base = 0;; base += 32)
         { uint32_t ent = 0;
@@ -238,6 +237,14 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, SCAN ? 3 : 2) hash_count2_kern
               if (own0) { const uint32_t i = __ffs(own0) - 1; own0 &= own0 - 1; ent = (run0 << 5) | i; }
               else if (own1) { const uint32_t i = __ffs(own1) - 1; own1 &= own1 - 1; ent = ((run0 + 1) << 5) | i; }
             }
+          if (SCATTER)
+            { // the bucket position of the k-mer the previous round selected is requested HERE, at the top of the body, and
+              // used below, after this round's evaluation: the L2 round trip of the atomic hides behind the evaluation and
+              // no scoreboard is outstanding at the loop's back edge (where ptxas waits for every one: ncu r02, 19 % of all
+              // stall samples sat on that wait when the atomic was issued at the end of the body)
+              if (pOn) pPos = atomicAdd(&P.cursors[pRegion], 1u);
+              asm volatile("" : "+r"(ent) :: "memory");
+            }
           uint32_t kl = 0, kh = 0;
           bool isF = false, ok = false;
           if (have)
@@ -247,7 +254,7 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, SCAN ? 3 : 2) hash_count2_kern
               else ok = mg_eval32_single<false>(E, H.shift, x0.y, x0.x, x1.y, x1.x, bit, &kl, &kh, &isF);
             }
           if (SCATTER)
-            { asm volatile("" : "+r"(pPos));                 // (keeps the compiler from testing the position before the evaluation above)
+            { asm volatile("" : "+r"(pPos), "+r"(kl), "+r"(kh) :: "memory");   // (the store below stays behind the evaluation)
               if (pOn)                                       // the previous round's k-mer: its position has arrived by now
                 { const uint64_t km = ((uint64_t)pKh << 32) | pKl;
                   if (pPos < P.bucketCap)
@@ -270,7 +277,6 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, SCAN ? 3 : 2) hash_count2_kern
                   const uint64_t km = ((uint64_t)kh << 32) | kl;
                   pRegion = (uint32_t)((km * 0x9E3779B97F4A7C15ull) >> 32) >> regionShift;            // mg_slot_hash >> regionBits
                   if (PEER) pRegion += mg_owner(km, P.nOwners) * P.nRegions;                           // bucket index = owner * R + region
-                  pPos = atomicAdd(&P.cursors[pRegion], 1u);
                   pKl = kl; pKh = kh;
                 }
             }
@@ -294,9 +300,10 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, SCAN ? 3 : 2) hash_count2_kern
         }
       __syncwarp();                                         // the queue and the packed tile are free again
     }
-  // the last pending bucket store
+  // the last pending k-mer
   if (SCATTER && pOn)
     { const uint64_t km = ((uint64_t)pKh << 32) | pKl;
+      pPos = atomicAdd(&P.cursors[pRegion], 1u);
       if (pPos < P.bucketCap)
         { uint64_t *bp = P.buckets + (uint64_t)pRegion * P.bucketCap + pPos;
           if (P.keepBuckets) mg_st_keep(bp, km); else *bp = km;
@@ -330,6 +337,8 @@ static int c2_launch(const SelectParams &P0, cudaStream_t st)
     }
   SelectParams P = P0;
   P.nTiles = (uint32_t)((P.nBases + MG_WT_BASES - 1) / MG_WT_BASES);         // warp tiles
+  P.E = mg_eval32_prepare(P.H);
+  P.regionShift = 32u - (P.slotBits - P.regionBits);
   uint64_t grid = (uint64_t)mg_num_sms() * blocksPerSm;
   const uint64_t need = ((uint64_t)P.nTiles + MG_CNT_WARPS * MG_CNT_CHUNK - 1) / (MG_CNT_WARPS * MG_CNT_CHUNK);
   if (grid > need) grid = need;

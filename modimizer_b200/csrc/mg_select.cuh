@@ -37,6 +37,8 @@ struct SelectParams {
   // second-generation count kernel (hash_count2.cu): one byte per 2048-base warp tile, non-zero when a sequence ends in
   // (or just before the end of) the tile - the per-base end flags are then only read for those tiles
   const uint8_t *tileFlags;
+  MgEval32 E;                  // mg_eval32_prepare(H), computed once on the host: operands straight from the constant bank
+  uint32_t regionShift;        // region of a k-mer = high word of its slot-hash product >> regionShift
 };
 
 // count mode, second generation (hash_count2.cu); returns MODGPU_OK, or 1 when the configuration is not covered
