@@ -31,12 +31,36 @@
 #include "mg_select.cuh"
 
 
+// resident blocks per SM the kernels are compiled for (register budget = 65536 / (blocks x threads))
+#ifndef C2_LUT_BLOCKS
+#define C2_LUT_BLOCKS 3
+#endif
+#ifndef C2_GEN_BLOCKS
+#define C2_GEN_BLOCKS 2
+#endif
+
+// warps per block: measured on B200 (profiles/geometry_r02.txt), 3.1 Gbases.  Table-driven kernel, 3 blocks per SM:
+// 10 / 11 / 12 / 13 / 14 / 15 / 16 warps -> 1.254 / 1.223 / 1.203 / 1.192 / 1.193 / 1.182 / 1.257 ms (16 warps need the
+// 228 KiB shared-memory carve-out, up to 15 fit the 196 KiB one and leave 60 KiB of L1); full scan, 2 blocks per SM:
+// 12 / 13 / 14 / 15 / 16 warps -> 3.648 / 3.609 / 3.592 / 3.667 / 3.656 ms (72 registers at 14 warps)
+#ifndef C2_LUT_WARPS
+#define C2_LUT_WARPS 15
+#endif
+#ifndef C2_GEN_WARPS
+#define C2_GEN_WARPS 14
+#endif
+#ifndef C2_WQ_CAP
+#define C2_WQ_CAP MG_WQ_CAP                                    // queue entries per warp
+#endif
+#define C2_WARPS(SCAN) ((SCAN) ? C2_LUT_WARPS : C2_GEN_WARPS)
+#define C2_BOUNDS(SCAN) __launch_bounds__(C2_WARPS(SCAN) * 32, SCAN ? C2_LUT_BLOCKS : C2_GEN_BLOCKS)
+
 template <bool ENDS> struct C2WarpSmem {
   __align__(16) uint8_t stage[MG_WS_RAW_BYTES];                // the raw tile + 32 bytes of overlap (TMA destination)
   __align__(16) uint32_t ends[ENDS ? MG_WS_ENDS_BYTES / 4 : 4];
   __align__(16) uint32_t half[2 * (MG_WT_RUNS + 2)];           // the packed tile as 32-bit halves (word w = half[2w+1] : half[2w])
   __align__(8) uint64_t bar;
-  uint16_t queue[MG_WQ_CAP];
+  uint16_t queue[C2_WQ_CAP];
 };
 
 __device__ __forceinline__ uint32_t c2_top_bit(uint32_t x)     // position of the highest set bit (x != 0): FLO
@@ -58,7 +82,7 @@ __device__ __forceinline__ void c2_issue_tile(const SelectParams &P, C2WarpSmem<
 //       1 = table-driven candidates (LUTK = k)
 // OUT:  0 = list, 1 = the table's region buckets, 3 = per-(owner, region) buckets
 template <int SCAN, int LUTK, int OUT, bool ASCII, bool ENDS>
-__global__ void __launch_bounds__(MG_CNT_THREADS, SCAN ? 3 : 2) hash_count2_kernel(const SelectParams P)
+__global__ void C2_BOUNDS(SCAN) hash_count2_kernel(const SelectParams P)
 {
   constexpr bool SCATTER = (OUT == 1 || OUT == 3);
   constexpr bool PEER = (OUT == 3);
@@ -74,8 +98,9 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, SCAN ? 3 : 2) hash_count2_kern
   const uint32_t regionShift = P.regionShift;
   // tile schedule (as in the first generation): chunks of MG_CNT_CHUNK consecutive warp tiles, the first by warp index,
   // the following ones from an atomic ticket requested a whole chunk ahead
-  const uint32_t nWarps = gridDim.x * MG_CNT_WARPS;
-  uint64_t tile = (uint64_t)(blockIdx.x * MG_CNT_WARPS + (tid >> 5)) * MG_CNT_CHUNK, tileNext = 0;
+  constexpr uint32_t WARPS = C2_WARPS(SCAN);
+  const uint32_t nWarps = gridDim.x * WARPS;
+  uint64_t tile = (uint64_t)(blockIdx.x * WARPS + (tid >> 5)) * MG_CNT_CHUNK, tileNext = 0;
   uint32_t pendingChunk = 0;
   if (lane == 0) pendingChunk = nWarps + atomicAdd(P.ticket, 1u);
   // a tile can be bulk-copied when all of it and its overlap lie inside the batch (the raw bytes carry no slack)
@@ -95,7 +120,7 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, SCAN ? 3 : 2) hash_count2_kern
   if (SCAN)
     { const uint4 *src = reinterpret_cast<const uint4 *>(P.lut);
       uint4 *dst = reinterpret_cast<uint4 *>(sLut);
-      for (uint32_t i = tid; i < MG_LUT_SIZE / 16; i += MG_CNT_THREADS) dst[i] = __ldg(src + i);
+      for (uint32_t i = tid; i < MG_LUT_SIZE / 16; i += WARPS * 32) dst[i] = __ldg(src + i);
     }
   __syncthreads();
 
@@ -208,7 +233,7 @@ __global__ void __launch_bounds__(MG_CNT_THREADS, SCAN ? 3 : 2) hash_count2_kern
           }
       }
       if (nW == 0) { __syncwarp(); continue; }
-      const bool queued = nW <= MG_WQ_CAP;                   // warp-uniform
+      const bool queued = nW <= C2_WQ_CAP;                   // warp-uniform
       if (queued)
         { uint32_t mm = m1;                                  // from the top bit down: FLO alone finds it
           const uint32_t eb1 = (run0 + 1) << 5, eb0 = run0 << 5;
@@ -329,10 +354,11 @@ template <int SCAN, int LUTK, int OUT, bool ASCII, bool ENDS>
 static int c2_launch(const SelectParams &P0, cudaStream_t st)
 {
   static int blocksPerSm = 0;
-  const size_t smem = (SCAN ? MG_LUT_SIZE : 0) + MG_CNT_WARPS * sizeof(C2WarpSmem<ENDS>);
+  constexpr int WARPS = C2_WARPS(SCAN);
+  const size_t smem = (SCAN ? MG_LUT_SIZE : 0) + WARPS * sizeof(C2WarpSmem<ENDS>);
   if (!blocksPerSm)
     { MG_CUDA(cudaFuncSetAttribute(hash_count2_kernel<SCAN, LUTK, OUT, ASCII, ENDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      MG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, hash_count2_kernel<SCAN, LUTK, OUT, ASCII, ENDS>, MG_CNT_THREADS, smem));
+      MG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, hash_count2_kernel<SCAN, LUTK, OUT, ASCII, ENDS>, WARPS * 32, smem));
       if (blocksPerSm < 1) blocksPerSm = 1;
     }
   SelectParams P = P0;
@@ -340,13 +366,13 @@ static int c2_launch(const SelectParams &P0, cudaStream_t st)
   P.E = mg_eval32_prepare(P.H);
   P.regionShift = 32u - (P.slotBits - P.regionBits);
   uint64_t grid = (uint64_t)mg_num_sms() * blocksPerSm;
-  const uint64_t need = ((uint64_t)P.nTiles + MG_CNT_WARPS * MG_CNT_CHUNK - 1) / (MG_CNT_WARPS * MG_CNT_CHUNK);
+  const uint64_t need = ((uint64_t)P.nTiles + WARPS * MG_CNT_CHUNK - 1) / (WARPS * MG_CNT_CHUNK);
   if (grid > need) grid = need;
   if (SCAN)
     { lut_build_kernel<<<MG_LUT_SIZE / 256, 256, 0, st>>>(P.H, const_cast<uint8_t *>(P.lut));
       MG_LAUNCH_CHECK("lut_build");
     }
-  hash_count2_kernel<SCAN, LUTK, OUT, ASCII, ENDS><<<(unsigned)grid, MG_CNT_THREADS, smem, st>>>(P);
+  hash_count2_kernel<SCAN, LUTK, OUT, ASCII, ENDS><<<(unsigned)grid, WARPS * 32, smem, st>>>(P);
   MG_LAUNCH_CHECK("hash_count2");
   return MODGPU_OK;
 }

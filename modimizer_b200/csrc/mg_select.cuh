@@ -60,7 +60,9 @@ static __global__ void __launch_bounds__(256) lut_build_kernel(const MgKHasher H
 }
 
 // ---- geometry of the count kernels: every warp owns tiles of 64 runs = 2048 window starts
+#ifndef MG_CNT_WARPS
 #define MG_CNT_WARPS 16
+#endif
 #define MG_CNT_THREADS (MG_CNT_WARPS * 32)
 #define MG_CNT_CHUNK 4                                          // warp tiles per scheduling chunk (power of two)
 #define MG_WT_RUNS 64                                          // runs per warp tile
