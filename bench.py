@@ -480,12 +480,13 @@ def run_ours(args):
                       "achieved_gbs": (alg[name] / (ms_k * 1e-3) / 1e9) if ms_k > 0 else None}
     kern["pack"]["what"] = "mark_ends_kernel + unmark_ends_kernel: one flag per sequence set and cleared again (K1 itself runs inside the select kernel)"
     kern["select"]["what"] = "lut_build_kernel + hash_count2_kernel: fused K1 pack2bit + K2 hash/select + K3 bucket scatter"
-    kern["insert"]["what"] = ("region_build_pipe_kernel: persistent, pipelined region build in shared memory (+ overflow inserts)" +
-                              (", reading every rank's buckets over NVLink" if world > 1 else "; writes the 2 GiB table once"))
+    kern["insert"]["what"] = (("region_build_tma_kernel: persistent region build in shared memory (+ overflow inserts), every rank's buckets "
+                               "pulled over NVLink by TMA bulk copies into a shared-memory ring") if world > 1 else
+                              "region_build_pipe_kernel: persistent, pipelined region build in shared memory (+ overflow inserts); writes the 2 GiB table once")
     dom = max(("pack", "select", "insert"), key=lambda n: kern[n]["ms_per_step"])
     launches_per_step = sum(times[n][1] for n in times) // prof_steps
     kname = {"pack": "mark_ends_kernel", "select": "hash_count2_kernel",
-             "insert": "region_build_pipe_kernel"}
+             "insert": "region_build_tma_kernel" if world > 1 else "region_build_pipe_kernel"}
     # dram__bytes_read + dram__bytes_write of the dominant kernel: NOT measured by this run (ncu cannot ride along a timed
     # run); it is the committed `ncu --set full` capture of the same kernel at this same configuration, named beside it
     traffic, traffic_src = None, None
@@ -502,8 +503,8 @@ def run_ours(args):
                 "frac": (kern[dom]["achieved_gbs"] / peak) if kern[dom]["achieved_gbs"] else None,
                 "traffic": traffic, "traffic_source": traffic_src, "kernels": kern,
                 "note": "hash_count2_kernel (fused pack + hash/select + scatter) is bound by instruction issue and the shared-memory "
-                        "pipe, not by HBM (ncu r02, profiles/ncu_summary_r02_lut.json: issue 78 %, ALU pipe 68 %, shared-memory pipe 59 %, "
-                        "11.8 thread instructions per base, DRAM traffic 1.06x the algorithmic bytes); 1 + 8/d algorithmic bytes per base; "
+                        "pipe, not by HBM (ncu r02, profiles/ncu_summary_r02_lut.json: issue 84 %, ALU pipe 74 %, shared-memory pipe 64 %, "
+                        "11.7 thread instructions per base, DRAM traffic 1.05x the algorithmic bytes); 1 + 8/d algorithmic bytes per base; "
                         "see DESIGN.md section 3 and profiles/"}
 
     # ---- e2e: host buffers through the C ABI, H2D inside the timed region
