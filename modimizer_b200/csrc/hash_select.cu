@@ -828,7 +828,8 @@ int mg_hash_select_peer(const ModgpuHasher *h, const uint64_t *d_packed, const u
   P.slotBits = slotBits; P.regionBits = regionBits; P.nRegions = nRegions; P.bucketCap = bucketCap;
   P.cursors = d_cursors; P.buckets = d_buckets; P.overflow = d_overflow; P.overflowCap = overflowCap;
   P.nOwners = nOwners; P.ownerCursor = d_ovfCounts;
-  P.keepBuckets = 1u;                                  // many small buckets: their tail sectors must survive in L2
+  { static int keep = -1; if (keep < 0) { const char *v = getenv("MODGPU_KEEP_PEER_BUCKETS"); keep = v ? atoi(v) : 1; }
+    P.keepBuckets = (uint32_t)keep; }                  // many small buckets: their tail sectors must survive in L2
   MG_CUDA(cudaMemsetAsync(d_workspace, 0, 64, st));
   const bool pf = P.H.prefilter && !(flags & MODGPU_SEL_NOPREFILTER);
   const bool tma = !(flags & MODGPU_SEL_NOTMA);

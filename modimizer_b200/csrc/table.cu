@@ -393,7 +393,7 @@ template <bool FRESH>
 __global__ void __launch_bounds__(256, 4) region_build_tma_kernel(MgSlot *slots, uint32_t slotBits, const MgPeerSrc src,
                                                                   const uint32_t *__restrict__ cursors, uint32_t cap, uint32_t nSrc,
                                                                   uint64_t srcStride, uint32_t nRegions, unsigned long long *entries,
-                                                                  uint32_t *error, const uint32_t *__restrict__ guard)
+                                                                  uint32_t *error, const uint32_t *__restrict__ guard, const uint32_t hint)
 {
   __shared__ uint4 sR[MG_REGION_SLOTS];
   __shared__ __align__(8) uint64_t sBar[2];
@@ -414,7 +414,10 @@ __global__ void __launch_bounds__(256, 4) region_build_tma_kernel(MgSlot *slots,
         sCnt[stage][lane] = c;
         const uint32_t bytes = (c * 8u + 15u) & ~15u;                  // (cap is even: a whole bucket is a multiple of 16 bytes)
         if (bytes)
-          mg_tma_load_1d(ring + (size_t)stage * stageWords + (size_t)lane * cap, src.p[lane] + (uint64_t)region * cap, bytes, &sBar[stage]);
+          { // the buckets are read once: evict-first releases their lines (the select pass stored them evict-last)
+            if (hint) mg_tma_load_1d_hint(ring + (size_t)stage * stageWords + (size_t)lane * cap, src.p[lane] + (uint64_t)region * cap, bytes, &sBar[stage], MG_L2_EVICT_FIRST);
+            else mg_tma_load_1d(ring + (size_t)stage * stageWords + (size_t)lane * cap, src.p[lane] + (uint64_t)region * cap, bytes, &sBar[stage]);
+          }
         mg_mbar_expect_tx(&sBar[stage], bytes);                        // one arrival per source, with its bytes
       }
   };
@@ -995,8 +998,32 @@ int mg_table_build_from_buckets(ModgpuTable *t, const uint64_t *d_buckets, const
 // d_cursors: [nSrc][cursorStride] fill counts (cursorStride >= nRegions; 0 = nRegions); d_ovfCounts[s * ovfStride];
 // d_guard (nullable): a device word > 0 means "some rank lost k-mers of this group": build nothing (a fresh table is
 // created empty) - every rank sees the same flags, so the group is applied everywhere or nowhere.
-__global__ void peer_ovf_count_kernel(unsigned long long *wide, const uint32_t *count, const uint32_t *guard)
-{ *wide = (guard && *guard) ? 0ull : (unsigned long long)*count; }
+// the overflow segments of ALL sources in one launch (one count word and one direct-insert launch per source were 16
+// serialised 6-microsecond kernels behind the build at 8 GPUs: 0.1 ms of a 0.84 ms build)
+__global__ void __launch_bounds__(256) peer_overflow_insert_kernel(MgSlot *slots, uint32_t slotBits, const MgPeerSrc ovf,
+                                                                   const uint32_t *__restrict__ counts, uint64_t ovfStride, uint32_t nSrc,
+                                                                   uint64_t cap, const uint32_t *__restrict__ guard,
+                                                                   unsigned long long *entries, uint32_t *error)
+{
+  if (guard && __ldg(guard) > 0u) return;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint32_t fresh = 0;
+  for (uint32_t s = 0; s < nSrc; ++s)
+    { uint64_t n = __ldg(counts + s * ovfStride);
+      if (n > cap) n = cap;
+      const uint64_t *kmers = ovf.p[s];
+      for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        { const uint64_t key = kmers[i] & 0x3FFFFFFFFFFFFFFFull;
+          bool isNew;
+          const uint64_t sl = probe_insert(slots, slotBits, key, &isNew);
+          if (sl == 0xFFFFFFFFFFFFFFFFull) { atomicExch(error, 1u); continue; }
+          fresh += isNew ? 1u : 0u;
+          atomicAdd(&slots[sl].count, 1u);
+        }
+    }
+  fresh = mg_warp_sum(fresh);
+  if (mg_lane() == 0 && fresh) atomicAdd(entries, (unsigned long long)fresh);
+}
 
 int mg_table_build_from_peers_ex(ModgpuTable *t, const uint64_t *const *d_buckets, const uint32_t *d_cursors, uint64_t cursorStride,
                                  uint32_t cap, uint32_t nSrc, const uint64_t *const *d_overflow, uint64_t overflowCap,
@@ -1022,8 +1049,11 @@ int mg_table_build_from_peers_ex(ModgpuTable *t, const uint64_t *const *d_bucket
 #define MG_PIPE_LAUNCH(FR) do { if (nw == 16) region_build_pipe_kernel<FR, true, 1, 16, 2><<<grid, 512, 0, st>>>(MG_PIPE_ARGS); \
                                 else if (nSrc <= 8) region_build_pipe_kernel<FR, true, 1><<<grid, 256, 0, st>>>(MG_PIPE_ARGS); \
                                 else region_build_pipe_kernel<FR, true, 2><<<grid, 256, 0, st>>>(MG_PIPE_ARGS); } while (0)
-  static int useTma = -1, tmaBlocks = 0;
-  if (useTma < 0) { const char *v = getenv("MODGPU_PEER_TMA"); useTma = v ? atoi(v) : 1; }
+  static int useTma = -1, tmaBlocks = 0, tmaHint = 0;
+  if (useTma < 0)
+    { const char *v = getenv("MODGPU_PEER_TMA"); useTma = v ? atoi(v) : 1;
+      v = getenv("MODGPU_PEER_HINT"); tmaHint = v ? atoi(v) : 0;
+    }
   const size_t ringBytes = 2 * (size_t)nSrc * cap * 8;
   if (useTma && nSrc >= 2 && nSrc <= 8 && ringBytes <= 96 * 1024)
     { // the transfer on the TMA engine (bulk copies from the peers into a shared-memory ring)
@@ -1038,11 +1068,11 @@ int mg_table_build_from_peers_ex(ModgpuTable *t, const uint64_t *const *d_bucket
       uint32_t tgrid = (uint32_t)mg_num_sms() * (uint32_t)tmaBlocks;
       if (tgrid > nRegions) tgrid = nRegions;
       if (t->clearPending)
-        { region_build_tma_kernel<true><<<tgrid, 256, ringBytes, st>>>(t->slots, t->slotBits, src, d_cursors, cap, nSrc, cursorStride, nRegions, t->dEntries, t->dError, d_guard);
+        { region_build_tma_kernel<true><<<tgrid, 256, ringBytes, st>>>(t->slots, t->slotBits, src, d_cursors, cap, nSrc, cursorStride, nRegions, t->dEntries, t->dError, d_guard, (uint32_t)tmaHint);
           t->clearPending = false;
         }
       else
-        region_build_tma_kernel<false><<<tgrid, 256, ringBytes, st>>>(t->slots, t->slotBits, src, d_cursors, cap, nSrc, cursorStride, nRegions, t->dEntries, t->dError, d_guard);
+        region_build_tma_kernel<false><<<tgrid, 256, ringBytes, st>>>(t->slots, t->slotBits, src, d_cursors, cap, nSrc, cursorStride, nRegions, t->dEntries, t->dError, d_guard, (uint32_t)tmaHint);
     }
   else if (t->clearPending) { MG_PIPE_LAUNCH(true); t->clearPending = false; }
   else MG_PIPE_LAUNCH(false);
@@ -1050,11 +1080,11 @@ int mg_table_build_from_peers_ex(ModgpuTable *t, const uint64_t *const *d_bucket
 #undef MG_PIPE_ARGS
   MG_LAUNCH_CHECK("region_build_peer");
   // the (rare) k-mers that did not fit their bucket at the sender: direct inserts reading the peer's segment
-  for (uint32_t s = 0; d_overflow && s < nSrc; ++s)
-    { unsigned long long *wide = t->dEntries + 4 + (s & 3);
-      peer_ovf_count_kernel<<<1, 1, 0, st>>>(wide, d_ovfCounts + s * ovfStride, d_guard);
-      table_insert_kernel<false><<<grid_for(65536, 4), 256, 0, st>>>(t->slots, t->slotBits, d_overflow[s], wide,
-                                                                     overflowCap, nullptr, t->dEntries, t->dError);
+  if (d_overflow)
+    { MgPeerSrc ovf;
+      for (uint32_t s = 0; s < MODGPU_MAX_PEERS; ++s) ovf.p[s] = d_overflow[s < nSrc ? s : 0];
+      peer_overflow_insert_kernel<<<grid_for(65536, 4), 256, 0, st>>>(t->slots, t->slotBits, ovf, d_ovfCounts, ovfStride, nSrc, overflowCap, d_guard,
+                                                                      t->dEntries, t->dError);
       MG_LAUNCH_CHECK("overflow_insert");
     }
   return MODGPU_OK;
