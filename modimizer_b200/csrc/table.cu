@@ -1055,7 +1055,9 @@ int mg_table_build_from_peers_ex(ModgpuTable *t, const uint64_t *const *d_bucket
       v = getenv("MODGPU_PEER_HINT"); tmaHint = v ? atoi(v) : 0;
     }
   const size_t ringBytes = 2 * (size_t)nSrc * cap * 8;
-  if (useTma && nSrc >= 2 && nSrc <= 8 && ringBytes <= 96 * 1024)
+  bool aligned = (cap & 1u) == 0;                            // bulk copies want 16-byte aligned buckets
+  for (uint32_t q = 0; q < nSrc; ++q) aligned = aligned && (reinterpret_cast<uintptr_t>(d_buckets[q]) & 15u) == 0;
+  if (useTma && aligned && nSrc >= 2 && nSrc <= 8 && ringBytes <= 96 * 1024)
     { // the transfer on the TMA engine (bulk copies from the peers into a shared-memory ring)
       static size_t ringSet = 0;
       if (ringBytes > ringSet)
