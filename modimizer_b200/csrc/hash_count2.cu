@@ -237,9 +237,18 @@ __global__ void C2_BOUNDS(SCAN) hash_count2_kernel(const SelectParams P)
       if (queued)
         { uint32_t mm = m1;                                  // from the top bit down: FLO alone finds it
           const uint32_t eb1 = (run0 + 1) << 5, eb0 = run0 << 5;
-          while (mm) { const uint32_t i = c2_top_bit(mm); mm ^= 1u << i; wq[qoff++] = (uint16_t)(eb1 | i); }
+          uint32_t qa = mg_smem_addr(wq + qoff);             // shared-memory byte address of the lane's next entry
+          while (mm)
+            { const uint32_t i = c2_top_bit(mm);
+              asm volatile("st.shared.u16 [%0], %1;" :: "r"(qa), "h"((uint16_t)(eb1 | i)) : "memory");
+              mm ^= 1u << i; qa += 2;
+            }
           mm = m0;
-          while (mm) { const uint32_t i = c2_top_bit(mm); mm ^= 1u << i; wq[qoff++] = (uint16_t)(eb0 | i); }
+          while (mm)
+            { const uint32_t i = c2_top_bit(mm);
+              asm volatile("st.shared.u16 [%0], %1;" :: "r"(qa), "h"((uint16_t)(eb0 | i)) : "memory");
+              mm ^= 1u << i; qa += 2;
+            }
         }
       __syncwarp();
 
@@ -275,8 +284,9 @@ __global__ void C2_BOUNDS(SCAN) hash_count2_kernel(const SelectParams P)
           if (have)
             { const uint32_t src = ent >> 5, bit = ent & 31u;
               const uint2 x0 = *reinterpret_cast<const uint2 *>(S->half + 2 * src), x1 = *reinterpret_cast<const uint2 *>(S->half + 2 * src + 2);
-              if (SCAN == 1 && pow2) ok = mg_eval32_single<true>(E, H.shift, x0.y, x0.x, x1.y, x1.x, bit, &kl, &kh, &isF);
-              else ok = mg_eval32_single<false>(E, H.shift, x0.y, x0.x, x1.y, x1.x, bit, &kl, &kh, &isF);
+              const uint32_t shiftK = SCAN == 1 ? (uint32_t)(64 - 2 * LUTK) : H.shift;     // the table scan knows k at compile time
+              if (SCAN == 1 && pow2) ok = mg_eval32_single<true>(E, shiftK, x0.y, x0.x, x1.y, x1.x, bit, &kl, &kh, &isF);
+              else ok = mg_eval32_single<false>(E, shiftK, x0.y, x0.x, x1.y, x1.x, bit, &kl, &kh, &isF);
             }
           if (SCATTER)
             { asm volatile("" : "+r"(pPos), "+r"(kl), "+r"(kh) :: "memory");   // (the store below stays behind the evaluation)

@@ -64,7 +64,9 @@ static __global__ void __launch_bounds__(256) lut_build_kernel(const MgKHasher H
 #define MG_CNT_WARPS 16
 #endif
 #define MG_CNT_THREADS (MG_CNT_WARPS * 32)
+#ifndef MG_CNT_CHUNK
 #define MG_CNT_CHUNK 4                                          // warp tiles per scheduling chunk (power of two)
+#endif
 #define MG_WT_RUNS 64                                          // runs per warp tile
 #define MG_WT_BASES (MG_WT_RUNS * MG_RUN)                      // 2048
 #define MG_WQ_CAP 256                                          // queue entries per warp (of its 2048 windows)
