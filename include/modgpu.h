@@ -15,7 +15,9 @@
  *   - sequences: concatenated bytes + nSeq+1 offsets (offs[0] = 0).  Bytes are
  *     either reference codes 0..3 (what seqIOread hands to addSequence after
  *     dna2indexConv, seqio.c:643-652, with N->0 as patched at modutils.c:39) or
- *     raw ASCII ACGTN/acgtn (isAscii != 0, same mapping, N/n -> a).
+ *     raw ASCII ACGTN/acgtn (isAscii != 0, same mapping, N/n -> a).  Code bytes
+ *     must be 0..3 (the reference never produces anything else: seqIOread dies on
+ *     characters dna2indexConv does not map); other values give undefined k-mers.
  *   - return value: 0 on success, a negative MODGPU_E* code otherwise; functions
  *     returning counts use UINT64_MAX for failure.
  *   - "d_" parameters are device pointers; `stream` is a cudaStream_t passed as

@@ -383,6 +383,21 @@ MGHD uint32_t mg_pairrev32(uint32_t x)                          // reverse the o
   return ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
 }
 
+// ~mg_pairrev32(x): the complement of the reversed groups (the reverse complement of sixteen bases).  On the device
+// the swap of the bits of every pair and the complement are ONE three-input logic operation on (y >> 1, y << 1,
+// 0x55555555): from C the compiler emits and / or-and / not
+MGHD uint32_t mg_pairrev32_not(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+  const uint32_t y = __brev(x);
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, 0x55555555, 0x1B;" : "=r"(r) : "r"(y >> 1), "r"(y << 1));      // ~((a & c) | (b & ~c))
+  return r;
+#else
+  return ~mg_pairrev32(x);
+#endif
+}
+
 template <bool POW2>
 MGHD bool mg_eval32_single(const MgEval32 &E, uint32_t shift, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t i,
                            uint32_t *kmLo, uint32_t *kmHi, bool *isF)
@@ -392,7 +407,7 @@ MGHD bool mg_eval32_single(const MgEval32 &E, uint32_t shift, uint32_t a, uint32
   const uint32_t x0 = up ? b : a, x1 = up ? c : b, x2 = up ? d : c;
   const uint32_t tHi = mg_fl32(x1, x0, sl & 31u), tLo = mg_fl32(x2, x1, sl & 31u);     // top 64 bits of (w0:w1) << 2i
   const uint32_t fLo = mg_frc32(tLo, tHi, shift), fHi = mg_frc32(tHi, 0u, shift);     // >> (64 - 2k): the forward k-mer
-  const uint32_t qHi = ~mg_pairrev32(fLo), qLo = ~mg_pairrev32(fHi);                  // complement of the reversed k-mer, at the top
+  const uint32_t qHi = mg_pairrev32_not(fLo), qLo = mg_pairrev32_not(fHi);                  // complement of the reversed k-mer, at the top
   const uint32_t rLo = mg_frc32(qLo, qHi, shift), rHi = mg_frc32(qHi, 0u, shift);
   uint32_t pfl, pfh, prl, prh;
   mg_mul64lo(fLo, fHi, E.fLo, E.fHi, &pfl, &pfh);

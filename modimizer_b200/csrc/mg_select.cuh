@@ -85,7 +85,11 @@ __device__ __forceinline__ uint32_t pack16_dev(const uint4 q)
       c2 = ((q.z >> 1) ^ (q.z >> 2)) & 0x03030303u; c3 = ((q.w >> 1) ^ (q.w >> 2)) & 0x03030303u;
     }
   else
-    { c0 = q.x & 0x03030303u; c1 = q.y & 0x03030303u; c2 = q.z & 0x03030303u; c3 = q.w & 0x03030303u; }
+    { // reference codes are 0..3 by contract (include/modgpu.h; seqIOread dies on anything dna2indexConv does not map,
+      // seqio.c:643-652, and patternRC[] has four entries, seqhash.h:22): no mask - four instructions per 16 bases of a
+      // pass that is bound by instruction issue.  Other byte values give undefined k-mers, nothing else
+      c0 = q.x; c1 = q.y; c2 = q.z; c3 = q.w;
+    }
   const uint32_t p0 = c0 * 0x40100401u, p1 = c1 * 0x40100401u, p2 = c2 * 0x40100401u, p3 = c3 * 0x40100401u;
   const uint32_t t = __byte_perm(p0, p1, 0x3700), u = __byte_perm(p2, p3, 0x0037);
   return __byte_perm(t, u, 0x3254);
