@@ -78,10 +78,33 @@ __device__ __forceinline__ void c2_issue_tile(const SelectParams &P, C2WarpSmem<
   if (ENDS) mg_tma_load_1d_hint(S->ends, P.ends + tile * MG_WT_RUNS, MG_WS_ENDS_BYTES, &S->bar, MG_L2_EVICT_FIRST);
 }
 
+// a selected k-mer goes to position pos of bucket `region` (pos from the bucket's cursor), or - bucket full - to the
+// overflow list (PEER: of its owner).  The address is two wide multiply-adds on byte offsets; PEER buckets are many and
+// small: their stores ask L2 to keep the line until its four k-mers have arrived (evict-last)
+template <bool PEER>
+__device__ __forceinline__ void c2_place(const SelectParams &P, uint32_t region, uint32_t pos, uint64_t km)
+{
+  if (pos < P.bucketCap)
+    { char *row = reinterpret_cast<char *>(P.buckets) + (uint64_t)region * (P.bucketCap * 8u);       // (cap < 2^29)
+      uint64_t *bp = reinterpret_cast<uint64_t *>(row + (uint64_t)pos * 8u);
+      if (PEER) mg_st_keep(bp, km); else *bp = km;
+    }
+  else if (PEER)
+    { const uint32_t ow = region / P.nRegions;
+      const uint32_t o = atomicAdd(&P.ownerCursor[ow], 1u);
+      if (o < P.overflowCap) P.overflow[(uint64_t)ow * P.overflowCap + o] = km;
+    }
+  else
+    { const uint32_t o = atomicAdd(&P.cursors[P.nRegions], 1u);
+      if (o < P.overflowCap) P.overflow[o] = km;
+    }
+}
+
 // SCAN: 0 = every window evaluated in full (32-bit pieces, k >= 16; LUTK = 1 when d is odd: no low-bit test),
 //       1 = table-driven candidates (LUTK = k)
 // OUT:  0 = list, 1 = the table's region buckets, 3 = per-(owner, region) buckets
-template <int SCAN, int LUTK, int OUT, bool ASCII, bool ENDS>
+//       P2 (table scan only): d is a power of two - no odd-part test in the evaluation
+template <int SCAN, int LUTK, int OUT, bool ASCII, bool ENDS, bool P2>
 __global__ void C2_BOUNDS(SCAN) hash_count2_kernel(const SelectParams P)
 {
   constexpr bool SCATTER = (OUT == 1 || OUT == 3);
@@ -93,7 +116,6 @@ __global__ void C2_BOUNDS(SCAN) hash_count2_kernel(const SelectParams P)
   const MgKHasher &H = P.H;
   const uint32_t tid = threadIdx.x, lane = tid & 31;
   const MgEval32 &E = P.E;                                 // prepared on the host: constant-bank operands, nothing to rebuild per round
-  const bool pow2 = H.oddInv == 1;                         // kernel-uniform: no odd-part test
   // region of a k-mer = the top (slotBits - regionBits) bits of its slot hash = one shift of the high product word
   const uint32_t regionShift = P.regionShift;
   // tile schedule (as in the first generation): chunks of MG_CNT_CHUNK consecutive warp tiles, the first by warp index,
@@ -255,22 +277,8 @@ __global__ void C2_BOUNDS(SCAN) hash_count2_kernel(const SelectParams P)
       // ---- evaluation and output, round by round (32 queue entries each).  Scatter: a selected k-mer is carried into the
       // next round (also across tiles; the last one is placed after the tile loop), where its bucket atomic is issued
       // before and its store behind that round's evaluation
-      uint32_t own0 = m0, own1 = m1;
-      for (uint32_t base = 0;; base += 32)
-        { uint32_t ent = 0;
-          bool have;
-          if (queued)
-            { if (base >= nW) break;
-              have = base + lane < nW;
-              if (have) ent = wq[base + lane];
-            }
-          else
-            { // more candidates than the queue holds (d < 8, pathological sequence): every lane walks its own
-              have = (own0 | own1) != 0;
-              if (!__any_sync(0xffffffffu, have)) break;
-              if (own0) { const uint32_t i = __ffs(own0) - 1; own0 &= own0 - 1; ent = (run0 << 5) | i; }
-              else if (own1) { const uint32_t i = __ffs(own1) - 1; own1 &= own1 - 1; ent = ((run0 + 1) << 5) | i; }
-            }
+      // one round: the lanes that `have` an entry evaluate it (ent = run * 32 + window)
+      auto round = [&](uint32_t ent, const bool have) {
           if (SCATTER)
             { // the bucket position of the k-mer the previous round selected is requested HERE, at the top of the body, and
               // used below, after this round's evaluation: the L2 round trip of the atomic hides behind the evaluation and
@@ -285,27 +293,11 @@ __global__ void C2_BOUNDS(SCAN) hash_count2_kernel(const SelectParams P)
             { const uint32_t src = ent >> 5, bit = ent & 31u;
               const uint2 x0 = *reinterpret_cast<const uint2 *>(S->half + 2 * src), x1 = *reinterpret_cast<const uint2 *>(S->half + 2 * src + 2);
               const uint32_t shiftK = SCAN == 1 ? (uint32_t)(64 - 2 * LUTK) : H.shift;     // the table scan knows k at compile time
-              if (SCAN == 1 && pow2) ok = mg_eval32_single<true>(E, shiftK, x0.y, x0.x, x1.y, x1.x, bit, &kl, &kh, &isF);
-              else ok = mg_eval32_single<false>(E, shiftK, x0.y, x0.x, x1.y, x1.x, bit, &kl, &kh, &isF);
+              ok = mg_eval32_single<SCAN == 1 && P2>(E, shiftK, x0.y, x0.x, x1.y, x1.x, bit, &kl, &kh, &isF);
             }
           if (SCATTER)
             { asm volatile("" : "+r"(pPos), "+r"(kl), "+r"(kh) :: "memory");   // (the store below stays behind the evaluation)
-              if (pOn)                                       // the previous round's k-mer: its position has arrived by now
-                { const uint64_t km = ((uint64_t)pKh << 32) | pKl;
-                  if (pPos < P.bucketCap)
-                    { uint64_t *bp = P.buckets + (uint64_t)pRegion * P.bucketCap + pPos;
-                      if (P.keepBuckets) mg_st_keep(bp, km); else *bp = km;
-                    }
-                  else if (PEER)
-                    { const uint32_t ow = pRegion / P.nRegions;
-                      const uint32_t o = atomicAdd(&P.ownerCursor[ow], 1u);
-                      if (o < P.overflowCap) P.overflow[(uint64_t)ow * P.overflowCap + o] = km;
-                    }
-                  else
-                    { const uint32_t o = atomicAdd(&P.cursors[P.nRegions], 1u);
-                      if (o < P.overflowCap) P.overflow[o] = km;
-                    }
-                }
+              if (pOn) c2_place<PEER>(P, pRegion, pPos, ((uint64_t)pKh << 32) | pKl);      // the previous round's k-mer
               pOn = ok;
               if (ok)
                 { ++nSelectedLocal;
@@ -318,7 +310,7 @@ __global__ void C2_BOUNDS(SCAN) hash_count2_kernel(const SelectParams P)
           else
             { // list: one reservation per warp and round
               const uint32_t ballot = __ballot_sync(0xffffffffu, ok);
-              if (!ballot) continue;
+              if (!ballot) return;
               unsigned long long wbase = 0;
               if (lane == 0) wbase = atomicAdd(P.count, (unsigned long long)__popc(ballot));
               wbase = __shfl_sync(0xffffffffu, wbase, 0);
@@ -332,26 +324,30 @@ __global__ void C2_BOUNDS(SCAN) hash_count2_kernel(const SelectParams P)
                     }
                 }
             }
+      };
+      if (queued)
+        { // the entry is read whether the lane has one or not (the queue is readable to its end: nW <= C2_WQ_CAP rounds up
+          // inside it): no divergent region around one load
+          for (uint32_t base = 0; base < nW; base += 32) round(wq[base + lane], base + lane < nW);
+        }
+      else
+        { // more candidates than the queue holds (d < 8, pathological sequence): every lane walks its own
+          uint32_t own0 = m0, own1 = m1;
+          for (;;)
+            { const bool have = (own0 | own1) != 0;
+              if (!__any_sync(0xffffffffu, have)) break;
+              uint32_t ent = 0;
+              if (own0) { const uint32_t i = __ffs(own0) - 1; own0 &= own0 - 1; ent = (run0 << 5) | i; }
+              else if (own1) { const uint32_t i = __ffs(own1) - 1; own1 &= own1 - 1; ent = ((run0 + 1) << 5) | i; }
+              round(ent, have);
+            }
         }
       __syncwarp();                                         // the queue and the packed tile are free again
     }
   // the last pending k-mer
   if (SCATTER && pOn)
-    { const uint64_t km = ((uint64_t)pKh << 32) | pKl;
-      pPos = atomicAdd(&P.cursors[pRegion], 1u);
-      if (pPos < P.bucketCap)
-        { uint64_t *bp = P.buckets + (uint64_t)pRegion * P.bucketCap + pPos;
-          if (P.keepBuckets) mg_st_keep(bp, km); else *bp = km;
-        }
-      else if (PEER)
-        { const uint32_t ow = pRegion / P.nRegions;
-          const uint32_t o = atomicAdd(&P.ownerCursor[ow], 1u);
-          if (o < P.overflowCap) P.overflow[(uint64_t)ow * P.overflowCap + o] = km;
-        }
-      else
-        { const uint32_t o = atomicAdd(&P.cursors[P.nRegions], 1u);
-          if (o < P.overflowCap) P.overflow[o] = km;
-        }
+    { pPos = atomicAdd(&P.cursors[pRegion], 1u);
+      c2_place<PEER>(P, pRegion, pPos, ((uint64_t)pKh << 32) | pKl);
     }
   if (SCATTER)
     { nSelectedLocal = mg_warp_sum(nSelectedLocal);
@@ -360,15 +356,15 @@ __global__ void C2_BOUNDS(SCAN) hash_count2_kernel(const SelectParams P)
 }
 
 // ------------------------------------------------------------------- host
-template <int SCAN, int LUTK, int OUT, bool ASCII, bool ENDS>
+template <int SCAN, int LUTK, int OUT, bool ASCII, bool ENDS, bool P2>
 static int c2_launch(const SelectParams &P0, cudaStream_t st)
 {
   static int blocksPerSm = 0;
   constexpr int WARPS = C2_WARPS(SCAN);
   const size_t smem = (SCAN ? MG_LUT_SIZE : 0) + WARPS * sizeof(C2WarpSmem<ENDS>);
   if (!blocksPerSm)
-    { MG_CUDA(cudaFuncSetAttribute(hash_count2_kernel<SCAN, LUTK, OUT, ASCII, ENDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      MG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, hash_count2_kernel<SCAN, LUTK, OUT, ASCII, ENDS>, WARPS * 32, smem));
+    { MG_CUDA(cudaFuncSetAttribute(hash_count2_kernel<SCAN, LUTK, OUT, ASCII, ENDS, P2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      MG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, hash_count2_kernel<SCAN, LUTK, OUT, ASCII, ENDS, P2>, WARPS * 32, smem));
       if (blocksPerSm < 1) blocksPerSm = 1;
     }
   SelectParams P = P0;
@@ -382,16 +378,23 @@ static int c2_launch(const SelectParams &P0, cudaStream_t st)
     { lut_build_kernel<<<MG_LUT_SIZE / 256, 256, 0, st>>>(P.H, const_cast<uint8_t *>(P.lut));
       MG_LAUNCH_CHECK("lut_build");
     }
-  hash_count2_kernel<SCAN, LUTK, OUT, ASCII, ENDS><<<(unsigned)grid, WARPS * 32, smem, st>>>(P);
+  hash_count2_kernel<SCAN, LUTK, OUT, ASCII, ENDS, P2><<<(unsigned)grid, WARPS * 32, smem, st>>>(P);
   MG_LAUNCH_CHECK("hash_count2");
   return MODGPU_OK;
+}
+
+template <int SCAN, int LUTK, int OUT, bool P2>
+static int c2_dispatch_io2(const SelectParams &P, bool ends, cudaStream_t st)
+{
+  if (P.rawAscii) return ends ? c2_launch<SCAN, LUTK, OUT, true, true, P2>(P, st) : c2_launch<SCAN, LUTK, OUT, true, false, P2>(P, st);
+  return ends ? c2_launch<SCAN, LUTK, OUT, false, true, P2>(P, st) : c2_launch<SCAN, LUTK, OUT, false, false, P2>(P, st);
 }
 
 template <int SCAN, int LUTK, int OUT>
 static int c2_dispatch_io(const SelectParams &P, bool ends, cudaStream_t st)
 {
-  if (P.rawAscii) return ends ? c2_launch<SCAN, LUTK, OUT, true, true>(P, st) : c2_launch<SCAN, LUTK, OUT, true, false>(P, st);
-  return ends ? c2_launch<SCAN, LUTK, OUT, false, true>(P, st) : c2_launch<SCAN, LUTK, OUT, false, false>(P, st);
+  if (SCAN == 1 && P.H.oddInv == 1) return c2_dispatch_io2<SCAN, LUTK, OUT, SCAN == 1>(P, ends, st);     // d a power of two
+  return c2_dispatch_io2<SCAN, LUTK, OUT, false>(P, ends, st);
 }
 
 template <int OUT>
