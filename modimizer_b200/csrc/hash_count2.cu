@@ -79,7 +79,7 @@ __device__ __forceinline__ void c2_issue_tile(const SelectParams &P, C2WarpSmem<
 }
 
 // a selected k-mer goes to position pos of bucket `region` (pos from the bucket's cursor), or - bucket full - to the
-// overflow list (PEER: of its owner).  The address is two wide multiply-adds on byte offsets; PEER buckets are many and
+// overflow list (PEER: of its owner).  The address is built from byte offsets; PEER buckets are many and
 // small: their stores ask L2 to keep the line until its four k-mers have arrived (evict-last)
 template <bool PEER>
 __device__ __forceinline__ void c2_place(const SelectParams &P, uint32_t region, uint32_t pos, uint64_t km)
@@ -131,7 +131,7 @@ __global__ void C2_BOUNDS(SCAN) hash_count2_kernel(const SelectParams P)
   uint32_t phase = 0;
   // scatter: the k-mer whose bucket position is still on its way (stored one round later, also across tiles)
   uint32_t pKl = 0, pKh = 0, pRegion = 0, pPos = 0;
-  bool pOn = false;
+  uint32_t pOn = 0;                                         // (a word, not a bool: no byte packing around the predicate)
 
   if (lane == 0)
     { mg_mbar_init(&S->bar, 1);
@@ -287,13 +287,13 @@ __global__ void C2_BOUNDS(SCAN) hash_count2_kernel(const SelectParams P)
               if (pOn) pPos = atomicAdd(&P.cursors[pRegion], 1u);
               asm volatile("" : "+r"(ent) :: "memory");
             }
-          uint32_t kl = 0, kh = 0;
-          bool isF = false, ok = false;
+          uint32_t kl = 0, kh = 0, ok = 0;
+          bool isF = false;
           if (have)
             { const uint32_t src = ent >> 5, bit = ent & 31u;
               const uint2 x0 = *reinterpret_cast<const uint2 *>(S->half + 2 * src), x1 = *reinterpret_cast<const uint2 *>(S->half + 2 * src + 2);
               const uint32_t shiftK = SCAN == 1 ? (uint32_t)(64 - 2 * LUTK) : H.shift;     // the table scan knows k at compile time
-              ok = mg_eval32_single<SCAN == 1 && P2>(E, shiftK, x0.y, x0.x, x1.y, x1.x, bit, &kl, &kh, &isF);
+              ok = mg_eval32_single<SCAN == 1 && P2>(E, shiftK, x0.y, x0.x, x1.y, x1.x, bit, &kl, &kh, &isF) ? 1u : 0u;
             }
           if (SCATTER)
             { asm volatile("" : "+r"(pPos), "+r"(kl), "+r"(kh) :: "memory");   // (the store below stays behind the evaluation)
