@@ -503,8 +503,8 @@ def run_ours(args):
                 "frac": (kern[dom]["achieved_gbs"] / peak) if kern[dom]["achieved_gbs"] else None,
                 "traffic": traffic, "traffic_source": traffic_src, "kernels": kern,
                 "note": "hash_count2_kernel (fused pack + hash/select + scatter) is bound by instruction issue and the shared-memory "
-                        "pipe, not by HBM (ncu r02, profiles/ncu_summary_r02_lut.json: issue 84 %, ALU pipe 74 %, shared-memory pipe 64 %, "
-                        "11.7 thread instructions per base, DRAM traffic 1.05x the algorithmic bytes); 1 + 8/d algorithmic bytes per base; "
+                        "pipe, not by HBM (ncu r02, profiles/ncu_summary_r02_lut.json: issue 79 %, shared-memory pipe 69 %, ALU pipe 66 %, "
+                        "10.3 thread instructions per base, DRAM traffic 1.05x the algorithmic bytes); 1 + 8/d algorithmic bytes per base; "
                         "see DESIGN.md section 3 and profiles/"}
 
     # ---- e2e: host buffers through the C ABI, H2D inside the timed region
